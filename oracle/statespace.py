@@ -1,0 +1,219 @@
+"""Oracle stage 3: T,R -> P0 -> Kalman log-likelihood, and the full theta -> logp path.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).
+
+PARITY UNPINNED for the Kalman filter: the reference delegates it to ``pymc_extras`` (third party, >= 0.12.0,
+``pyproject.toml:45``; call site ``gEconpy/model/statespace.py:1151-1157``), whose source is not under
+``/root/reference`` and which is not installed here.  ``kalman_loglik`` restates the published ``StandardFilter``
+algorithm as recorded in SURVEY.md Appendix A.5 (update -> jitter -> predict; Joseph form; log det F; jitter on
+both H and the filtered covariance; missing entries masked out of Z and H).  The two details that upstream has
+changed across versions are options: ``mvn_const`` ("per_obs": p * log(2 pi) [default]; "bare": log(2 pi)).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+from . import solvers
+
+JITTER_DEFAULT = 1e-8  # pymc_extras.statespace.utils.constants.JITTER_DEFAULT for float64
+MISSING_FILL = -9999.0  # pymc_extras.statespace.utils.constants.MISSING_FILL
+
+
+def dlyap(T, RQR, method="bilinear"):
+    """``pt.linalg.solve_discrete_lyapunov(T, R Q R^T, method)`` (gEconpy/model/statespace.py:814-815):
+    X = T X T^T + RQR.  pytensor's "bilinear" method is the same bilinear transform + continuous Lyapunov solve
+    that scipy implements; "direct" is the Kronecker solve."""
+    with np.errstate(all="ignore"):
+        try:
+            return sla.solve_discrete_lyapunov(T, RQR, method=method)
+        except Exception:
+            return np.full_like(RQR, np.nan)
+
+
+def _sym(X):
+    return 0.5 * (X + X.T)
+
+
+def kalman_loglik(
+    Y,
+    T,
+    R,
+    Q,
+    Z,
+    H,
+    d=None,
+    c=None,
+    a0=None,
+    P0=None,
+    jitter=JITTER_DEFAULT,
+    missing_fill=MISSING_FILL,
+    mvn_const="per_obs",
+    return_all=False,
+):
+    """Standard (covariance-form) Kalman filter log-likelihood, SURVEY.md Appendix A.5.
+
+    Y: (T_obs, p); T: (n,n); R: (n,k); Q: (k,k); Z: (p,n); H: (p,p); d: (p,) or None; c: (n,) or None.
+    a0/P0 are the PREDICTED moments of the first observation (a0 = 0, P0 = dlyap by default).
+    """
+    Y = np.asarray(Y, dtype=np.float64)
+    n = T.shape[0]
+    p = Z.shape[0]
+    d = np.zeros(p) if d is None else np.asarray(d, dtype=np.float64)
+    c = np.zeros(n) if c is None else np.asarray(c, dtype=np.float64)
+    RQR = _sym(R @ Q @ R.T)
+    a = np.zeros(n) if a0 is None else np.asarray(a0, dtype=np.float64).copy()
+    P = dlyap(T, R @ Q @ R.T) if P0 is None else np.asarray(P0, dtype=np.float64).copy()
+    I_n = np.eye(n)
+    I_p = np.eye(p)
+    lls = np.zeros(Y.shape[0])
+    log2pi = np.log(2.0 * np.pi)
+    with np.errstate(all="ignore"):
+        for t in range(Y.shape[0]):
+            y = Y[t]
+            mask = np.isnan(y) | (y == missing_fill)
+            all_missing = bool(mask.all())
+            W = np.diag((~mask).astype(np.float64))
+            Zm = W @ Z
+            Hm = W @ H
+            ym = np.where(mask, 0.0, y)
+            # update
+            v = ym - (d + Zm @ a)
+            PZt = P @ Zm.T
+            F = Zm @ PZt + Hm + jitter * I_p
+            try:
+                cF = sla.cho_factor(F, lower=True, check_finite=False)
+                K = sla.cho_solve(cF, PZt.T, check_finite=False).T
+                Finv_v = sla.cho_solve(cF, v, check_finite=False)
+                logdet = 2.0 * np.log(np.diag(cF[0])).sum()
+            except Exception:
+                K = np.full((n, p), np.nan)
+                Finv_v = np.full(p, np.nan)
+                logdet = np.nan
+            IKZ = I_n - K @ Zm
+            a_f = a + K @ v
+            P_f = _sym(IKZ @ P @ IKZ.T) + _sym(K @ Hm @ K.T)
+            const = p * log2pi if mvn_const == "per_obs" else log2pi
+            lls[t] = 0.0 if all_missing else -0.5 * (const + logdet + v @ Finv_v)
+            P_f = P_f + jitter * I_n
+            # predict
+            a = T @ a_f + c
+            P = _sym(T @ P_f @ T.T) + RQR
+    if return_all:
+        return float(lls.sum()), lls
+    return float(lls.sum())
+
+
+def selector_design(var_names, observed):
+    """gEconpy/model/statespace.py:282-296: one-hot selector rows (no aggregation, no obs equations)."""
+    Z = np.zeros((len(observed), len(var_names)))
+    for i, name in enumerate(observed):
+        Z[i, var_names.index(name)] = 1.0
+    return Z
+
+
+def loglik_from_matrices(
+    A,
+    B,
+    C,
+    D,
+    Y,
+    obs_idx,
+    sigma_shock,
+    sigma_err=None,
+    inv_var_order=None,
+    permuted_lead_idx=None,
+    solver="cycle_reduction",
+    tol=1e-8,
+    max_iter=1000,
+    solver_tol=1e-8,
+    jitter=JITTER_DEFAULT,
+    check_bk=True,
+    check_resid=True,
+    mvn_const="per_obs",
+    lyapunov_method="bilinear",
+):
+    """One likelihood evaluation from already-evaluated (permuted) Jacobians.
+
+    Follows gEconpy/model/statespace.py:197-222 (solve, residual in solver order, un-permute),
+    :769-770 (BK on permuted lead positions), :800-820 (Q, H, a0 = 0, P0) and :1206-1215 (-inf gating).
+    Returns a dict with ll (gated), ll_raw, flags and intermediates.
+    """
+    n = A.shape[0]
+    out = {}
+    if solver == "cycle_reduction":
+        T, conv, n_iter = solvers.cycle_reduction_core(A, B, C, max_iter=max_iter, tol=tol)
+        out["converged"], out["n_iter"] = bool(conv), n_iter
+    elif solver == "gensys":
+        T, _R, success, eu = solvers.gensys_policy(A, B, C, D, tol=tol)
+        if T is None:
+            T = np.full((n, n), np.nan)
+        out["converged"], out["n_iter"], out["eu"] = bool(success), 0, eu
+    else:
+        raise ValueError(solver)
+    R = solvers.selection_matrix(B, C, D, T)
+    resid = solvers.policy_residual(A, B, C, T)
+    out["resid"] = resid
+    if permuted_lead_idx is not None:
+        bk_ok, n_fwd, n_unst = solvers.bk_condition_pt(A, B, C, D, permuted_lead_idx)
+    else:
+        bk_ok, n_fwd, n_unst = True, 0, 0
+    out["bk_ok"], out["n_forward"], out["n_unstable"] = bool(bk_ok), n_fwd, n_unst
+    out["T_solver"], out["R_solver"] = T, R
+    if inv_var_order is not None:
+        T = T[inv_var_order][:, inv_var_order]
+        R = R[inv_var_order]
+    out["T"], out["R"] = T, R
+    Q = np.diag(np.asarray(sigma_shock, dtype=np.float64) ** 2)
+    p = len(obs_idx)
+    Z = np.zeros((p, n))
+    Z[np.arange(p), obs_idx] = 1.0
+    H = np.zeros((p, p))
+    if sigma_err is not None:
+        H = np.diag(np.asarray(sigma_err, dtype=np.float64) ** 2)
+    with np.errstate(all="ignore"):
+        P0 = dlyap(T, R @ Q @ R.T, method=lyapunov_method)
+        ll_raw = kalman_loglik(Y, T, R, Q, Z, H, P0=P0, jitter=jitter, mvn_const=mvn_const) if np.all(np.isfinite(P0)) else np.nan
+    out["P0"] = P0
+    out["ll_raw"] = ll_raw
+    ok = True
+    if check_bk and not bk_ok:
+        ok = False
+    if check_resid and not (resid < solver_tol):
+        ok = False
+    out["ok"] = ok
+    out["ll"] = ll_raw if ok else -np.inf
+    return out
+
+
+def loglik(model, theta, Y, observed, sigma_shock, sigma_err=None, **kwargs):
+    """theta -> logp for an ``oracle.model.OracleModel`` (the path of SURVEY.md section 3.3, without priors)."""
+    A, B, C, D = model.jacobians(theta, mode="statespace")
+    obs_idx = [model.var_names.index(v) for v in observed]
+    return loglik_from_matrices(
+        A,
+        B,
+        C,
+        D,
+        Y,
+        obs_idx,
+        sigma_shock,
+        sigma_err,
+        inv_var_order=model.inv_var_order,
+        permuted_lead_idx=model.permuted_lead_var_idx,
+        **kwargs,
+    )
+
+
+def simulate(T, R, sigma_shock, n_steps, seed=0, x0=None):
+    """x_t = T x_{t-1} + R eps_t (gEconpy/model/simulate.py:171-183), eps ~ N(0, diag(sigma^2))."""
+    rng = np.random.default_rng(seed)
+    n, k = R.shape
+    x = np.zeros(n) if x0 is None else np.asarray(x0, dtype=np.float64)
+    out = np.zeros((n_steps, n))
+    eps = rng.standard_normal((n_steps, k)) * np.asarray(sigma_shock)
+    for t in range(n_steps):
+        x = T @ x + R @ eps[t]
+        out[t] = x
+    return out
