@@ -1,0 +1,316 @@
+"""Batched-over-draws entry points of the hot path (thin layer over the C ABI).
+
+Every function takes either numpy arrays (HOST path: the library copies in, launches, copies out) or torch CUDA
+tensors (DEVICE path: pointers + the current torch stream are handed to the ``*_batched`` entry points, nothing is
+copied).  Arrays carry a leading draw axis: ``A[N, n, n]``, ``D[N, n, k]``...; 2-D inputs are treated as N = 1.
+There is no CPU implementation behind these functions.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # torch is plumbing (device memory, streams); the host path works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class _Marshal:
+    """Keeps converted arrays alive and yields raw pointers for either path."""
+
+    def __init__(self, device: bool):
+        self.device = device
+        self.keep = []
+
+    def inp(self, x, dtype=np.float64):
+        if x is None:
+            return None, None
+        if self.device:
+            tdt = torch.float64 if dtype == np.float64 else torch.int32
+            if not _is_torch(x):
+                x = torch.as_tensor(np.ascontiguousarray(x, dtype=dtype), device=self.dev)
+            if x.dtype != tdt or not x.is_contiguous():
+                x = x.to(tdt).contiguous()
+            self.keep.append(x)
+            return x, x.data_ptr()
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        a = np.ascontiguousarray(x, dtype=dtype)
+        self.keep.append(a)
+        return a, a.ctypes.data
+
+    def out(self, shape, dtype=np.float64):
+        if self.device:
+            tdt = torch.float64 if dtype == np.float64 else torch.int32
+            t = torch.empty(shape, dtype=tdt, device=self.dev)
+            self.keep.append(t)
+            return t, t.data_ptr()
+        a = np.empty(shape, dtype=dtype)
+        self.keep.append(a)
+        return a, a.ctypes.data
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream) if self.device else None
+
+
+def _marshal_for(*arrays) -> _Marshal:
+    dev = None
+    for a in arrays:
+        if _is_torch(a) and a.is_cuda:
+            dev = a.device
+            break
+    m = _Marshal(dev is not None)
+    m.dev = dev
+    if dev is None:
+        L.require_device()
+    return m
+
+
+def _batch3(x):
+    """(n,n) -> (1,n,n); returns (array, was_2d)."""
+    if x is None:
+        return None, False
+    if x.ndim == 2:
+        return x[None], True
+    if x.ndim != 3:
+        raise ValueError(f"expected a 2-D or 3-D array, got shape {tuple(x.shape)}")
+    return x, False
+
+
+@dataclass
+class CycleReductionResult:
+    T: object
+    R: object
+    status: object
+    n_iter: object
+    resid: object
+    norms: object
+
+    @property
+    def converged(self):
+        return (self.status & L.ST_CR_NOT_CONVERGED) == 0
+
+
+def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None) -> CycleReductionResult:
+    """Batched cycle reduction + R + residual (``gecon_cr_solve_*``).
+
+    Reference: ``_cycle_reduction_core`` (gEconpy/solvers/cycle_reduction.py:127-183), ``pt_compute_selection_matrix``
+    (solvers/shared.py:74-75), residual (model/statespace.py:213).  ``C_ = None`` solves the backward-looking system
+    (solvers/backward_looking.py).
+    """
+    m = _marshal_for(A, B, C_, D)
+    A, pA = m.inp(A)
+    B, pB = m.inp(B)
+    C_, pC = m.inp(C_)
+    D, pD = m.inp(D)
+    A, squeeze = _batch3(A)
+    N, n = A.shape[0], A.shape[1]
+    k = 0
+    if D is not None:
+        k = D.shape[-1]
+    T, pT = m.out((N, n, n))
+    R, pR = m.out((N, n, k)) if D is not None else (None, None)
+    status, pS = m.out((N,), np.int32)
+    n_iter, pI = m.out((N,), np.int32)
+    resid, pRes = m.out((N,))
+    norms, pNo = m.out((N, 2))
+    _, pU = m.inp(unperm, np.int32)
+    args = L.CrArgs(
+        struct_size=C.sizeof(L.CrArgs), A=pA, B=pB, C=pC, D=pD, N=N, n=n, k=k, max_iter=int(max_iter), tol=float(tol),
+        resid_tol=float(resid_tol), unperm=pU, T=pT, R=pR, status=pS, n_iter=pI, resid=pRes, norms=pNo,
+    )  # fmt: skip
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_cr_solve_batched(C.byref(args), m.stream()), "gecon_cr_solve_batched")
+    else:
+        L.check(lib.gecon_cr_solve_host(C.byref(args)), "gecon_cr_solve_host")
+    if squeeze:
+        return CycleReductionResult(T[0], None if R is None else R[0], status[0], n_iter[0], resid[0], norms[0])
+    return CycleReductionResult(T, R, status, n_iter, resid, norms)
+
+
+def bk_count(A, B, C_, lead_idx, status=None, max_iter=0):
+    """Batched Blanchard-Kahn count (``gecon_bk_count_*``): returns (n_unstable[N], status[N]).
+
+    Reference: ``check_bk_condition_pt`` (gEconpy/model/perturbation.py:586-625).
+    """
+    m = _marshal_for(A, B, C_)
+    A, pA = m.inp(A)
+    B, pB = m.inp(B)
+    C_, pC = m.inp(C_)
+    A, squeeze = _batch3(A)
+    N, n = A.shape[0], A.shape[1]
+    lead = np.ascontiguousarray(lead_idx, dtype=np.int32)
+    _, pL = m.inp(lead, np.int32)
+    nu, pNu = m.out((N,), np.int32)
+    if status is None:
+        st, pS = m.out((N,), np.int32)
+        acc = 0
+    else:
+        st, pS = m.inp(status, np.int32)
+        acc = 1
+    args = L.BkArgs(
+        struct_size=C.sizeof(L.BkArgs), A=pA, B=pB, C=pC, N=N, n=n, n_lead=int(lead.size), lead_idx=pL, accumulate=acc,
+        max_iter=int(max_iter), n_unstable=pNu, status=pS,
+    )  # fmt: skip
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_bk_count_batched(C.byref(args), m.stream()), "gecon_bk_count_batched")
+    else:
+        L.check(lib.gecon_bk_count_host(C.byref(args)), "gecon_bk_count_host")
+    if squeeze:
+        return nu[0], st[0]
+    return nu, st
+
+
+def dlyap(T, R, qdiag, max_iter=0):
+    """Batched discrete Lyapunov solve P = T P T' + R diag(q) R' (``gecon_dlyap_*``): returns (P, status, n_iter).
+
+    Reference call site: gEconpy/model/statespace.py:814-815.
+    """
+    m = _marshal_for(T, R)
+    T, pT = m.inp(T)
+    R, pR = m.inp(R)
+    T, squeeze = _batch3(T)
+    N, n = T.shape[0], T.shape[1]
+    k = R.shape[-1]
+    q, pq = m.inp(qdiag)
+    q_stride = k if q.ndim == 2 else 0
+    P, pP = m.out((N, n, n))
+    st, pS = m.out((N,), np.int32)
+    it, pI = m.out((N,), np.int32)
+    args = L.DlyapArgs(
+        struct_size=C.sizeof(L.DlyapArgs), T=pT, R=pR, qdiag=pq, q_stride=q_stride, N=N, n=n, k=k, max_iter=int(max_iter),
+        accumulate=0, P=pP, status=pS, n_iter=pI,
+    )  # fmt: skip
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_dlyap_batched(C.byref(args), m.stream()), "gecon_dlyap_batched")
+    else:
+        L.check(lib.gecon_dlyap_host(C.byref(args)), "gecon_dlyap_host")
+    if squeeze:
+        return P[0], st[0], it[0]
+    return P, st, it
+
+
+def kalman_loglik(
+    T,
+    R,
+    qdiag,
+    Y,
+    Z=None,
+    obs_idx=None,
+    hdiag=None,
+    d=None,
+    P0=None,
+    jitter=1e-8,
+    missing_fill=-9999.0,
+    mvn_const="per_obs",
+    status_in=None,
+    gate_mask=0,
+    return_per_step=False,
+    lyap_max_iter=0,
+):
+    """Batched Kalman-filter log-likelihood (``gecon_kalman_ll_*``): returns (ll[N], status[N][, ll_t[N, Tobs]]).
+
+    Reference call site: gEconpy/model/statespace.py:1151-1157 (pymc_extras StandardFilter); semantics in
+    SURVEY.md Appendix A.5.  ``qdiag`` / ``hdiag`` are VARIANCES, per draw (N, k) / (N, p) or shared (k,) / (p,).
+    """
+    if (Z is None) == (obs_idx is None):
+        raise ValueError("give exactly one of Z (dense design matrix) and obs_idx (selector)")
+    m = _marshal_for(T, R)
+    T, pT = m.inp(T)
+    R, pR = m.inp(R)
+    T, squeeze = _batch3(T)
+    N, n = T.shape[0], T.shape[1]
+    k = R.shape[-1]
+    Ya, pY = m.inp(Y)
+    if Ya.ndim == 1:
+        Tobs, p = Ya.shape[0], 1
+    else:
+        Tobs, p = Ya.shape
+    q, pq = m.inp(qdiag)
+    h, ph = m.inp(hdiag)
+    dd, pd_ = m.inp(d)
+    _, pZ = m.inp(Z)
+    _, pO = m.inp(None if obs_idx is None else np.ascontiguousarray(obs_idx, dtype=np.int32), np.int32)
+    _, pP0 = m.inp(P0)
+    _, pSin = m.inp(status_in, np.int32)
+    ll, pll = m.out((N,))
+    st, pS = m.out((N,), np.int32)
+    llt, pllt = m.out((N, Tobs)) if return_per_step else (None, None)
+    args = L.KalmanArgs(
+        struct_size=C.sizeof(L.KalmanArgs), T=pT, R=pR, qdiag=pq, q_stride=(k if q.ndim == 2 else 0), hdiag=ph,
+        h_stride=(p if (h is not None and h.ndim == 2) else 0), Z=pZ, obs_idx=pO, d=pd_,
+        d_stride=(p if (dd is not None and dd.ndim == 2) else 0), Y=pY, P0=pP0, N=N, n=n, k=k, p=p, Tobs=Tobs,
+        jitter=float(jitter), missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1),
+        lyap_max_iter=int(lyap_max_iter), status_in=pSin, gate_mask=int(gate_mask), ll=pll, status=pS, ll_t=pllt,
+    )  # fmt: skip
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_kalman_ll_batched(C.byref(args), m.stream()), "gecon_kalman_ll_batched")
+    else:
+        L.check(lib.gecon_kalman_ll_host(C.byref(args)), "gecon_kalman_ll_host")
+    if squeeze:
+        ll, st = ll[0], st[0]
+        llt = None if llt is None else llt[0]
+    return (ll, st, llt) if return_per_step else (ll, st)
+
+
+def solve(M, RHS):
+    """Batched general solve with partial pivoting (``gecon_solve_*``): returns (X, status)."""
+    m = _marshal_for(M, RHS)
+    M, pM = m.inp(M)
+    RHS, pR = m.inp(RHS)
+    M, squeeze = _batch3(M)
+    N, n = M.shape[0], M.shape[1]
+    mm = RHS.shape[-1]
+    X, pX = m.out((N, n, mm))
+    st, pS = m.out((N,), np.int32)
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_solve_batched(pM, pR, N, n, mm, pX, pS, m.stream()), "gecon_solve_batched")
+    else:
+        L.check(lib.gecon_solve_host(pM, pR, N, n, mm, pX, pS), "gecon_solve_host")
+    if squeeze:
+        return X[0], st[0]
+    return X, st
+
+
+def gemm(A, B, trans_a=False, trans_b=False, alpha=1.0):
+    """Batched n x n product alpha * op(A) op(B) on the in-CTA DMMA path (``gecon_gemm_*``)."""
+    m = _marshal_for(A, B)
+    A, pA = m.inp(A)
+    B, pB = m.inp(B)
+    A, squeeze = _batch3(A)
+    N, n = A.shape[0], A.shape[1]
+    out, pC = m.out((N, n, n))
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_gemm_batched(pA, pB, N, n, int(trans_a), int(trans_b), float(alpha), pC, m.stream()), "gecon_gemm_batched")
+    else:
+        L.check(lib.gecon_gemm_host(pA, pB, N, n, int(trans_a), int(trans_b), float(alpha), pC), "gecon_gemm_host")
+    return out[0] if squeeze else out
+
+
+def kernel_info(which: str, n: int, p: int = 1, Tobs: int = 1) -> dict:
+    """Resident CTAs per SM, dynamic shared memory and threads per CTA of a kernel (needs a device)."""
+    idx = {"cr_solve": 0, "kalman_ll": 1, "bk_count": 2, "dlyap": 3}[which]
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    L.check(L.load_library().gecon_kernel_info(idx, n, p, Tobs, C.byref(a), C.byref(b), C.byref(c)), "gecon_kernel_info")
+    return {"ctas_per_sm": a.value, "smem_bytes": b.value, "threads": c.value}
+
+
+def launch_count() -> int:
+    return int(L.load_library().gecon_launch_count())

@@ -1,0 +1,102 @@
+"""Build the sm_100a shared libraries in-tree with nvcc (no JIT cache: the built .so files travel with the repo).
+
+``build_core()``  -> geconpy_b200/_lib/libgecon_b200.so   (cycle reduction, BK count, dlyap, Kalman, solve, gemm)
+``build_model()`` -> geconpy_b200/_lib/models/libgecon_model_<name>_<hash>.so  (generated Jacobian kernels)
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIBDIR = PKG / "_lib"
+MODEL_LIBDIR = LIBDIR / "models"
+CORE_LIB = LIBDIR / "libgecon_b200.so"
+CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu"]
+
+NVCC_FLAGS = [
+    "-O3",
+    "-std=c++17",
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler",
+    "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA libraries of geconpy_b200 cannot be built")
+
+
+def _digest(paths, extra=()) -> str:
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(Path(p).read_bytes())
+    for e in extra:
+        h.update(str(e).encode())
+    return h.hexdigest()
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: " + " ".join(map(str, cmd)) + "\n" + r.stdout + r.stderr)
+    return r.stdout + r.stderr
+
+
+def build_core(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/*.cu -> _lib/libgecon_b200.so (skipped when the sources are unchanged)."""
+    LIBDIR.mkdir(exist_ok=True)
+    deps = [CSRC / s for s in CORE_SOURCES] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "gecon_b200.h"]
+    stamp = LIBDIR / "libgecon_b200.stamp"
+    dig = _digest(deps, NVCC_FLAGS)
+    if not force and CORE_LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+        return CORE_LIB
+    nvcc = find_nvcc()
+    objdir = LIBDIR / "obj"
+    objdir.mkdir(exist_ok=True)
+
+    def compile_one(src):
+        obj = objdir / (Path(src).stem + ".o")
+        out = _run([nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", str(CSRC / src), "-o", str(obj)])
+        if verbose:
+            print(out)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(CORE_SOURCES)) as ex:
+        objs = list(ex.map(compile_one, CORE_SOURCES))
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CORE_LIB), *map(str, objs), "-lcudart"])
+    stamp.write_text(dig)
+    return CORE_LIB
+
+
+def build_model(name: str, source: str, force: bool = False) -> Path:
+    """Compile one generated model source (a string of CUDA C++) into its own shared library."""
+    MODEL_LIBDIR.mkdir(parents=True, exist_ok=True)
+    dig = hashlib.sha256((source + " ".join(NVCC_FLAGS)).encode()).hexdigest()[:16]
+    lib = MODEL_LIBDIR / f"libgecon_model_{name}_{dig}.so"
+    if lib.exists() and not force:
+        return lib
+    src = MODEL_LIBDIR / f"gecon_model_{name}_{dig}.cu"
+    src.write_text(source)
+    nvcc = find_nvcc()
+    _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-o", str(lib), str(src), "-lcudart"])
+    return lib
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build_core(force="--force" in sys.argv, verbose="-v" in sys.argv))

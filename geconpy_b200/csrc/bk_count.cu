@@ -1,0 +1,211 @@
+// Batched Blanchard-Kahn eigenvalue count, one CTA per parameter draw.
+//
+// Reference quantity (gEconpy/model/perturbation.py:448-505,586-625 check_bk_condition_pt; pencil assembly as in
+// gEconpy/solvers/gensys.py:568-614; count rule gEconpy/pytensorf/real_eig.py:31-36 + perturbation.py:618-620):
+//     Gamma0 = [[B, C], [-I, 0]],  Gamma1 = [[A, 0], [0, I]],  rows/cols sel = {0..n-1} U {n + lead_idx},
+//     G = -Gamma0[sel, sel] + 1e-8 I,  M = G^-1 Gamma1[sel, sel],  n_unstable = #{ |eig(M)| > 1 }.
+//
+// The count is computed without an eigen-solver.  The Cayley transform N = (Gamma1 - G)(Gamma1 + G)^-1 is similar to
+// (M - I)(M + I)^-1, which maps |lambda| > 1 to Re > 0 (infinite eigenvalues of the pencil go to +1, zeros to -1), and
+//     #{Re eig(N) > 0} = (m + trace sign(N)) / 2,
+// with sign(N) from the determinant-scaled Newton iteration S <- (mu S + (mu S)^-1) / 2.  Only Gauss-Jordan inverses
+// and elementwise updates are needed, i.e. the same in-CTA primitives as the cycle-reduction kernel.  The iteration
+// works on N' (trace and sign commute with transposition), which is what one solve with (Gamma1 + G)' produces.
+// A draw whose trace does not settle on an integer of the right parity (an eigenvalue on or next to the unit circle)
+// is flagged GECON_ST_BK_INCONCLUSIVE instead of being guessed.
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace gecon {
+
+template <int NP>
+struct BkSmem {
+    static constexpr size_t bytes = sizeof(double) * (3 * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (2 * NP + 4);
+};
+
+template <int NP>
+__global__ void __launch_bounds__(Cfg<NP>::NT) bk_count_kernel(const gecon_bk_args p) {
+    using C = Cfg<NP>;
+    constexpr int LD = C::LD, NT = C::NT;
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;
+    double* W = S + C::TILE;
+    double* X = W + C::TILE;
+    double* s_inv = X + C::TILE;
+    double* s_red = s_inv + NP;
+    int* s_piv = reinterpret_cast<int*>(s_red + NP);
+    int* s_sel = s_piv + NP;
+
+    const int n = p.n, nl = p.n_lead, m = n + nl;
+    const int cap = p.max_iter > 0 ? p.max_iter : 60;
+    for (int i = threadIdx.x; i < m; i += NT) s_sel[i] = (i < n) ? i : n + p.lead_idx[i - n];
+    __syncthreads();
+
+    for (long long draw = blockIdx.x; draw < p.N; draw += gridDim.x) {
+        const double* gA = p.A + (size_t)draw * n * n;
+        const double* gB = p.B + (size_t)draw * n * n;
+        const double* gC = p.C + (size_t)draw * n * n;
+        // W = (Gamma1 + G)',  X = (Gamma1 - G)'   (element [r][c] of the transpose = element (c, r))
+        for (int i = threadIdx.x; i < C::TILE; i += NT) {
+            const int r = i / LD, c = i - r * LD;
+            double wv = 0.0, xv = 0.0;
+            if (r < m && c < m) {
+                const int R = s_sel[c], Cc = s_sel[r];  // (row, col) in the 2n x 2n pencil
+                double g0, g1;
+                if (R < n) {
+                    g0 = (Cc < n) ? gB[R * n + Cc] : gC[R * n + (Cc - n)];
+                    g1 = (Cc < n) ? gA[R * n + Cc] : 0.0;
+                } else {
+                    g0 = (Cc == R - n) ? -1.0 : 0.0;
+                    g1 = (Cc == R) ? 1.0 : 0.0;
+                }
+                const double g = -g0 + ((r == c) ? 1e-8 : 0.0);
+                wv = g1 + g;
+                xv = g1 - g;
+            }
+            W[i] = wv;
+            X[i] = xv;
+        }
+        __syncthreads();
+        bool ok = gj_solve<NP>(W, X, 0, m, nullptr, 0, 0, m, s_piv, s_inv);
+        tile_copy<NP>(S, X);
+        __syncthreads();
+
+        bool settled = false;
+        int it = 0;
+        while (ok && it < cap) {
+            ++it;
+            tile_copy<NP>(W, S);
+            for (int i = threadIdx.x; i < C::TILE; i += NT) {
+                const int r = i / LD, c = i - r * LD;
+                X[i] = (r == c && r < m) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            ok = gj_solve<NP>(W, X, 0, m, nullptr, 0, 0, m, s_piv, s_inv);
+            if (!ok) break;
+            // determinant scaling: mu = |det S|^(-1/m) = exp(mean log |1/pivot|)
+            double lg = ((int)threadIdx.x < m) ? log(fabs(s_inv[threadIdx.x])) : 0.0;
+            lg = block_sum<NP>(lg, s_red);
+            double mu = exp(lg / m);
+            if (!(mu > 1e-150 && mu < 1e150)) mu = 1.0;
+            const double hm = 0.5 * mu, hi = 0.5 / mu;
+            double dmax = 0.0, smax = 0.0;
+            for (int i = threadIdx.x; i < C::TILE; i += NT) {
+                const double so = S[i];
+                const double sn = hm * so + hi * X[i];
+                S[i] = sn;
+                const double d = fabs(sn - so), a = fabs(sn);
+                if (d > dmax || d != d) dmax = d;
+                if (a > smax || a != a) smax = a;
+            }
+            dmax = block_max<NP>(dmax, s_red);
+            smax = block_max<NP>(smax, s_red);
+            if (dmax != dmax || smax != smax) {
+                ok = false;
+                break;
+            }
+            if (dmax <= 1e-6 * (1.0 + smax)) {
+                settled = true;
+                break;
+            }
+        }
+        __syncthreads();
+        double tr = ((int)threadIdx.x < m) ? S[threadIdx.x * LD + threadIdx.x] : 0.0;
+        tr = block_sum<NP>(tr, s_red);
+        if (threadIdx.x == 0) {
+            int st = 0, nu = -1;
+            const double cnt = 0.5 * (m + tr);
+            const double rc = rint(cnt);
+            if (ok && settled && fabs(cnt - rc) < 0.05 && rc >= 0.0 && rc <= (double)m) {
+                nu = (int)rc;
+                if (nu != nl) st |= GECON_ST_BK;
+            } else {
+                st |= GECON_ST_BK | GECON_ST_BK_INCONCLUSIVE;
+            }
+            if (p.n_unstable) p.n_unstable[draw] = nu;
+            p.status[draw] = p.accumulate ? (p.status[draw] | st) : st;
+        }
+        __syncthreads();
+    }
+}
+
+template <int NP>
+static int launch_bk(const gecon_bk_args& a, cudaStream_t st) {
+    int grid = 0;
+    int rc = persistent_grid(bk_count_kernel<NP>, Cfg<NP>::NT, BkSmem<NP>::bytes, a.N, &grid, nullptr);
+    if (rc) return rc;
+    bk_count_kernel<NP><<<grid, Cfg<NP>::NT, BkSmem<NP>::bytes, st>>>(a);
+    g_launch_count++;
+    GECON_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bk_kernel_info(int m, int* ctas, int* smem, int* threads) {
+    const int np = round_up8(m);
+    GECON_DISPATCH_NP(np, {
+        int grid = 0;
+        int rc = persistent_grid(bk_count_kernel<NP_>, Cfg<NP_>::NT, BkSmem<NP_>::bytes, 1 << 30, &grid, ctas);
+        if (rc) return rc;
+        *smem = (int)BkSmem<NP_>::bytes;
+        *threads = Cfg<NP_>::NT;
+    });
+    return 0;
+}
+
+static int check_bk_args(const gecon_bk_args* a) {
+    if (!a || a->struct_size != sizeof(gecon_bk_args)) {
+        set_last_error("gecon_bk_args: bad struct_size");
+        return GECON_E_BADARG;
+    }
+    if (!a->A || !a->B || !a->C || !a->status || a->N < 0 || a->n < 1 || a->n_lead < 0 || a->n_lead > a->n || (a->n_lead > 0 && !a->lead_idx)) {
+        set_last_error("gecon_bk_args: null pointer or bad dimension");
+        return GECON_E_BADARG;
+    }
+    return 0;
+}
+
+}  // namespace gecon
+
+using namespace gecon;
+
+extern "C" int gecon_bk_count_batched(const gecon_bk_args* args, void* stream) {
+    int rc = check_bk_args(args);
+    if (rc) return rc;
+    if (args->N == 0) return 0;
+    const int np = round_up8(args->n + args->n_lead);
+    GECON_DISPATCH_NP(np, return launch_bk<NP_>(*args, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int gecon_bk_count_host(const gecon_bk_args* a) {
+    int rc = check_bk_args(a);
+    if (rc) return rc;
+    if (a->N == 0) return 0;
+    const size_t N = (size_t)a->N, n = a->n, bm = N * n * n * 8;
+    DevBuf dA, dB, dC, dL, dU, dS;
+    gecon_bk_args d = *a;
+    GECON_CUDA(dA.alloc(bm));
+    GECON_CUDA(dB.alloc(bm));
+    GECON_CUDA(dC.alloc(bm));
+    GECON_CUDA(dL.alloc((size_t)a->n_lead * 4));
+    GECON_CUDA(dS.alloc(N * 4));
+    GECON_CUDA(cudaMemcpy(dA.p, a->A, bm, cudaMemcpyHostToDevice));
+    GECON_CUDA(cudaMemcpy(dB.p, a->B, bm, cudaMemcpyHostToDevice));
+    GECON_CUDA(cudaMemcpy(dC.p, a->C, bm, cudaMemcpyHostToDevice));
+    if (a->n_lead) GECON_CUDA(cudaMemcpy(dL.p, a->lead_idx, (size_t)a->n_lead * 4, cudaMemcpyHostToDevice));
+    if (a->accumulate) GECON_CUDA(cudaMemcpy(dS.p, a->status, N * 4, cudaMemcpyHostToDevice));
+    d.A = dA.as<double>();
+    d.B = dB.as<double>();
+    d.C = dC.as<double>();
+    d.lead_idx = dL.as<int32_t>();
+    d.status = dS.as<int32_t>();
+    if (a->n_unstable) {
+        GECON_CUDA(dU.alloc(N * 4));
+        d.n_unstable = dU.as<int32_t>();
+    }
+    rc = gecon_bk_count_batched(&d, nullptr);
+    if (rc) return rc;
+    GECON_CUDA(cudaMemcpy(a->status, d.status, N * 4, cudaMemcpyDeviceToHost));
+    if (a->n_unstable) GECON_CUDA(cudaMemcpy(a->n_unstable, d.n_unstable, N * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -1,0 +1,84 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/gecon_b200.h"
+
+namespace gecon {
+
+void set_last_error(const char* fmt, ...);
+extern std::atomic<long long> g_launch_count;
+
+inline int fail_cuda(cudaError_t e, const char* what) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+#define GECON_CUDA(call)                                   \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+inline int round_up8(int n) { return (n + 7) / 8 * 8; }
+
+// number of SMs of the current device (cached per device would be nicer; the query is cheap)
+inline int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sms;
+}
+
+// Persistent-grid launch helper: sets the dynamic shared memory attribute, asks the occupancy calculator for the
+// resident CTAs per SM and returns grid = min(N, SMs * CTAs/SM).
+template <typename K>
+inline int persistent_grid(K kernel, int threads, size_t smem, long long N, int* grid, int* ctas_per_sm) {
+    GECON_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GECON_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) {
+        set_last_error("kernel does not fit on an SM (threads=%d, smem=%zu)", threads, smem);
+        return GECON_E_UNSUPPORTED_SIZE;
+    }
+    const int sms = sm_count();
+    long long g = (long long)sms * per_sm;
+    if (g > N) g = N;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    if (ctas_per_sm) *ctas_per_sm = per_sm;
+    return 0;
+}
+
+// RAII device buffer for the *_host entry points
+struct DevBuf {
+    void* p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    template <typename T>
+    T* as() {
+        return static_cast<T*>(p);
+    }
+};
+
+#define GECON_DISPATCH_NP(np, ...)                  \
+    switch (np) {                                   \
+        case 8: { constexpr int NP_ = 8; __VA_ARGS__; } break;   \
+        case 16: { constexpr int NP_ = 16; __VA_ARGS__; } break; \
+        case 24: { constexpr int NP_ = 24; __VA_ARGS__; } break; \
+        case 32: { constexpr int NP_ = 32; __VA_ARGS__; } break; \
+        case 40: { constexpr int NP_ = 40; __VA_ARGS__; } break; \
+        case 48: { constexpr int NP_ = 48; __VA_ARGS__; } break; \
+        case 56: { constexpr int NP_ = 56; __VA_ARGS__; } break; \
+        default:                                    \
+            set_last_error("unsupported matrix dimension (padded %d > 56)", np); \
+            return GECON_E_UNSUPPORTED_SIZE;        \
+    }
+
+}  // namespace gecon

@@ -1,0 +1,309 @@
+// Batched cycle reduction + selection matrix + policy residual, one CTA per parameter draw.
+//
+// Restates gEconpy/solvers/cycle_reduction.py:127-183 (_cycle_reduction_core; authoritative flags),
+// gEconpy/solvers/shared.py:74-75 (R = -(C T + B)^-1 D), gEconpy/model/statespace.py:213 (residual) and
+// gEconpy/solvers/backward_looking.py:8-133 (C == NULL).  See DESIGN.md "cr_solve".
+//
+// Shared memory: 7 tiles (A0, A1, A2, A1hat, W, X0, X2).  Per iteration: copy A1->W, A0->X0, A2->X2; one
+// Gauss-Jordan solve for [X0 | X2] = A1^-1 [A0 | A2]; four DMMA products; norms.  The non-zero column ranges of
+// A0 (= lag columns) and A2 (= lead columns) are invariant under the iteration and are used to skip the zero blocks
+// of the right-hand sides and of the products.
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace gecon {
+
+template <int NP>
+__device__ __forceinline__ void acc_sub(Acc<NP>& a, const Acc<NP>& b) {
+#pragma unroll
+    for (int ct = 0; ct < NP / 8; ++ct) {
+        a.v[ct][0] -= b.v[ct][0];
+        a.v[ct][1] -= b.v[ct][1];
+    }
+}
+
+template <int NP>
+struct CrSmem {
+    static constexpr int TILES = 7;
+    static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (2 * NP + 4);
+};
+
+template <int NP>
+__global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_args p) {
+    using C = Cfg<NP>;
+    constexpr int LD = C::LD;
+    extern __shared__ __align__(16) double sm[];
+    double* A0 = sm;
+    double* A1 = A0 + C::TILE;
+    double* A2 = A1 + C::TILE;
+    double* A1h = A2 + C::TILE;
+    double* W = A1h + C::TILE;
+    double* X0 = W + C::TILE;
+    double* X2 = X0 + C::TILE;
+    double* s_inv = X2 + C::TILE;
+    double* s_red = s_inv + NP;
+    int* s_piv = reinterpret_cast<int*>(s_red + NP);
+    int* s_perm = s_piv + NP;
+    int* s_i = s_perm + NP;
+
+    const int n = p.n, k = p.k;
+    if (p.unperm) {
+        for (int i = threadIdx.x; i < n; i += C::NT) s_perm[i] = p.unperm[i];
+    }
+    const int* perm = p.unperm ? s_perm : nullptr;
+
+    for (long long draw = blockIdx.x; draw < p.N; draw += gridDim.x) {
+        const double* gA = p.A + (size_t)draw * n * n;
+        const double* gB = p.B + (size_t)draw * n * n;
+        const double* gC = p.C ? p.C + (size_t)draw * n * n : nullptr;
+        const double* gD = p.D ? p.D + (size_t)draw * n * k : nullptr;
+
+        tile_load<NP>(A0, gA, n, n, n);
+        tile_load<NP>(A1, gB, n, n, n);
+        tile_load<NP>(A1h, gB, n, n, n);
+        if (gC) tile_load<NP>(A2, gC, n, n, n);
+        else tile_zero<NP>(A2);
+        __syncthreads();
+
+        int lo0, hi0, lo2, hi2;
+        nonzero_col_range<NP>(A0, n, s_i, lo0, hi0);
+        nonzero_col_range<NP>(A2, n, s_i, lo2, hi2);
+        // GEMM ranges: k in multiples of 4, output column tiles in multiples of 8
+        const int k0lo = lo0 & ~3, k0hi = (hi0 + 3) & ~3, k2lo = lo2 & ~3, k2hi = (hi2 + 3) & ~3;
+        const int c0lo = lo0 >> 3, c0hi = (hi0 + 7) >> 3, c2lo = lo2 >> 3, c2hi = (hi2 + 7) >> 3;
+
+        int status = 0;
+        bool converged = false;
+        int it = 0;
+        double a0n = 0.0, a2n = 0.0;
+
+        if (gC) {
+            while (it < p.max_iter) {
+                ++it;
+                tile_copy<NP>(W, A1);
+                tile_copy<NP>(X0, A0);
+                tile_copy<NP>(X2, A2);
+                __syncthreads();
+                const bool ok = gj_solve<NP>(W, X0, lo0, hi0, X2, lo2, hi2, n, s_piv, s_inv);
+                if (!ok) {  // LAPACK: singular U -> inf/NaN in getrs; the norm test below then stops the loop
+                    tile_nanfill<NP>(X0, n, n);
+                    tile_nanfill<NP>(X2, n, n);
+                    __syncthreads();
+                }
+                {
+                    Acc<NP> m20, t;
+                    acc_zero(m20);
+                    gemm_acc<NP, false, false>(m20, A2, X0, 1.0, k2lo, k2hi, ok ? c0lo : 0, ok ? c0hi : C::CT);
+                    acc_load<NP>(t, A1);
+                    gemm_acc<NP, false, false>(t, A0, X2, -1.0, k0lo, k0hi, ok ? c2lo : 0, ok ? c2hi : C::CT);
+                    acc_sub(t, m20);
+                    acc_store<NP>(t, A1);
+                    acc_load<NP>(t, A1h);
+                    acc_sub(t, m20);
+                    acc_store<NP>(t, A1h);
+                }
+                Acc<NP> m00, m22;
+                acc_zero(m00);
+                acc_zero(m22);
+                gemm_acc<NP, false, false>(m00, A0, X0, -1.0, k0lo, k0hi, ok ? c0lo : 0, ok ? c0hi : C::CT);
+                gemm_acc<NP, false, false>(m22, A2, X2, -1.0, k2lo, k2hi, ok ? c2lo : 0, ok ? c2hi : C::CT);
+                __syncthreads();  // every warp is done reading A0, A2
+                acc_store<NP>(m00, A0);
+                acc_store<NP>(m22, A2);
+                __syncthreads();
+                a0n = norm1<NP>(A0, n, s_red);
+                if (a0n < p.tol) {
+                    a2n = norm1<NP>(A2, n, s_red);
+                    if (a2n < p.tol) {
+                        converged = true;
+                        break;
+                    }
+                } else if (a0n != a0n) {
+                    status |= GECON_ST_CR_NAN;
+                    break;
+                }
+            }
+            if (!converged) status |= GECON_ST_CR_NOT_CONVERGED;
+        }
+
+        // ---- T = -A1hat^-1 A (cycle_reduction.py:181), or T = -B^-1 A for backward-looking models; 0 if not converged
+        if (converged || !gC) {
+            tile_copy<NP>(W, A1h);  // backward looking: A1h == B
+            tile_load<NP>(X0, gA, n, n, n);
+            __syncthreads();
+            const bool ok = gj_solve<NP>(W, X0, lo0, hi0, nullptr, 0, 0, n, s_piv, s_inv);
+            if (!ok) {
+                status |= GECON_ST_SINGULAR;
+                tile_nanfill<NP>(X0, n, n);
+            } else {
+                for (int i = threadIdx.x; i < C::TILE; i += C::NT) X0[i] = -X0[i];
+            }
+        } else {
+            tile_zero<NP>(X0);
+        }
+        double* Tt = X0;
+        __syncthreads();
+
+        // ---- CT = C T (A0 tile), W = B + CT, R = -W^-1 D (shared.py:74-75)
+        if (gC) tile_load<NP>(A2, gC, n, n, n);
+        tile_load<NP>(A1, gB, n, n, n);
+        tile_load<NP>(A1h, gA, n, n, n);
+        __syncthreads();
+        {
+            Acc<NP> ct;
+            acc_zero(ct);
+            if (gC) gemm_acc<NP, false, false>(ct, A2, Tt, 1.0, (status & GECON_ST_SINGULAR) ? 0 : k2lo, (status & GECON_ST_SINGULAR) ? NP : k2hi);
+            acc_store<NP>(ct, A0);
+        }
+        __syncthreads();
+        if (gD && p.R) {
+            for (int i = threadIdx.x; i < C::TILE; i += C::NT) W[i] = A1[i] + A0[i];
+            tile_load<NP>(X2, gD, n, k, k);
+            __syncthreads();
+            const bool ok = gj_solve<NP>(W, X2, 0, k, nullptr, 0, 0, n, s_piv, s_inv);
+            if (!ok) {
+                status |= GECON_ST_SINGULAR;
+                tile_nanfill<NP>(X2, n, k);
+                __syncthreads();
+            }
+            tile_store<NP>(p.R + (size_t)draw * n * k, X2, n, k, k, -1.0, perm, nullptr);
+        }
+
+        // ---- residual sum((A + B T + (C T) T)^2) in solver order (statespace.py:213)
+        {
+            Acc<NP> e;
+            acc_load<NP>(e, A1h);
+            gemm_acc<NP, false, false>(e, A1, Tt, 1.0);
+            gemm_acc<NP, false, false>(e, A0, Tt, 1.0);
+            double ss = 0.0;
+#pragma unroll
+            for (int ct = 0; ct < C::CT; ++ct) ss += e.v[ct][0] * e.v[ct][0] + e.v[ct][1] * e.v[ct][1];
+            const double resid = block_sum<NP>(ss, s_red);
+            if (p.resid_tol > 0.0 && !(resid < p.resid_tol)) status |= GECON_ST_RESID;
+            if (threadIdx.x == 0) {
+                if (p.resid) p.resid[draw] = resid;
+                if (p.n_iter) p.n_iter[draw] = it;
+                if (p.norms) {
+                    p.norms[2 * draw] = a0n;
+                    p.norms[2 * draw + 1] = a2n;
+                }
+                p.status[draw] = status;
+            }
+        }
+        tile_store<NP>(p.T + (size_t)draw * n * n, Tt, n, n, n, 1.0, perm, perm);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------- host
+static int check_cr_args(const gecon_cr_args* a) {
+    if (!a || a->struct_size != sizeof(gecon_cr_args)) {
+        set_last_error("gecon_cr_args: bad struct_size");
+        return GECON_E_BADARG;
+    }
+    if (!a->A || !a->B || !a->T || !a->status || a->N < 0 || a->n < 1 || a->k < 0 || (a->R && !a->D)) {
+        set_last_error("gecon_cr_args: null pointer or bad dimension");
+        return GECON_E_BADARG;
+    }
+    if (a->k > round_up8(a->n)) {
+        set_last_error("gecon_cr_args: k = %d exceeds the padded state dimension", a->k);
+        return GECON_E_UNSUPPORTED_SIZE;
+    }
+    return 0;
+}
+
+template <int NP>
+static int launch_cr(const gecon_cr_args& a, cudaStream_t st) {
+    int grid = 0;
+    int rc = persistent_grid(cr_solve_kernel<NP>, Cfg<NP>::NT, CrSmem<NP>::bytes, a.N, &grid, nullptr);
+    if (rc) return rc;
+    cr_solve_kernel<NP><<<grid, Cfg<NP>::NT, CrSmem<NP>::bytes, st>>>(a);
+    g_launch_count++;
+    GECON_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int cr_kernel_info(int n, int* ctas, int* smem, int* threads) {
+    const int np = round_up8(n);
+    GECON_DISPATCH_NP(np, {
+        int grid = 0;
+        int rc = persistent_grid(cr_solve_kernel<NP_>, Cfg<NP_>::NT, CrSmem<NP_>::bytes, 1 << 30, &grid, ctas);
+        if (rc) return rc;
+        *smem = (int)CrSmem<NP_>::bytes;
+        *threads = Cfg<NP_>::NT;
+    });
+    return 0;
+}
+
+}  // namespace gecon
+
+using namespace gecon;
+
+extern "C" int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream) {
+    int rc = check_cr_args(args);
+    if (rc) return rc;
+    if (args->N == 0) return 0;
+    const int np = round_up8(args->n);
+    GECON_DISPATCH_NP(np, return launch_cr<NP_>(*args, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
+    int rc = check_cr_args(args);
+    if (rc) return rc;
+    if (args->N == 0) return 0;
+    const size_t N = (size_t)args->N, n = args->n, k = args->k;
+    const size_t bm = N * n * n * sizeof(double), bd = N * n * k * sizeof(double);
+    DevBuf dA, dB, dC, dD, dT, dR, dSt, dIt, dRes, dNo, dPerm;
+    gecon_cr_args d = *args;
+    GECON_CUDA(dA.alloc(bm));
+    GECON_CUDA(dB.alloc(bm));
+    GECON_CUDA(dT.alloc(bm));
+    GECON_CUDA(dSt.alloc(N * sizeof(int32_t)));
+    GECON_CUDA(cudaMemcpy(dA.p, args->A, bm, cudaMemcpyHostToDevice));
+    GECON_CUDA(cudaMemcpy(dB.p, args->B, bm, cudaMemcpyHostToDevice));
+    d.A = dA.as<double>();
+    d.B = dB.as<double>();
+    d.T = dT.as<double>();
+    d.status = dSt.as<int32_t>();
+    if (args->C) {
+        GECON_CUDA(dC.alloc(bm));
+        GECON_CUDA(cudaMemcpy(dC.p, args->C, bm, cudaMemcpyHostToDevice));
+        d.C = dC.as<double>();
+    }
+    if (args->D) {
+        GECON_CUDA(dD.alloc(bd));
+        GECON_CUDA(cudaMemcpy(dD.p, args->D, bd, cudaMemcpyHostToDevice));
+        d.D = dD.as<double>();
+    }
+    if (args->R) {
+        GECON_CUDA(dR.alloc(bd));
+        d.R = dR.as<double>();
+    }
+    if (args->n_iter) {
+        GECON_CUDA(dIt.alloc(N * sizeof(int32_t)));
+        d.n_iter = dIt.as<int32_t>();
+    }
+    if (args->resid) {
+        GECON_CUDA(dRes.alloc(N * sizeof(double)));
+        d.resid = dRes.as<double>();
+    }
+    if (args->norms) {
+        GECON_CUDA(dNo.alloc(2 * N * sizeof(double)));
+        d.norms = dNo.as<double>();
+    }
+    if (args->unperm) {
+        GECON_CUDA(dPerm.alloc(n * sizeof(int32_t)));
+        GECON_CUDA(cudaMemcpy(dPerm.p, args->unperm, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        d.unperm = dPerm.as<int32_t>();
+    }
+    rc = gecon_cr_solve_batched(&d, nullptr);
+    if (rc) return rc;
+    GECON_CUDA(cudaMemcpy(args->T, d.T, bm, cudaMemcpyDeviceToHost));
+    if (args->R) GECON_CUDA(cudaMemcpy(args->R, d.R, bd, cudaMemcpyDeviceToHost));
+    GECON_CUDA(cudaMemcpy(args->status, d.status, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (args->n_iter) GECON_CUDA(cudaMemcpy(args->n_iter, d.n_iter, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (args->resid) GECON_CUDA(cudaMemcpy(args->resid, d.resid, N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (args->norms) GECON_CUDA(cudaMemcpy(args->norms, d.norms, 2 * N * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}

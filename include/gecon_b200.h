@@ -1,0 +1,214 @@
+/* gecon_b200.h -- C ABI of libgecon_b200.so: the B200 (sm_100a, fp64) implementation of gEconpy's per-draw
+ * estimation hot path, batched over parameter draws.
+ *
+ * Reference interfaces replaced (paths relative to the gEconpy source tree):
+ *   gecon_cr_solve_*      gEconpy/solvers/cycle_reduction.py:127-183 (_cycle_reduction_core), :23-114 (numpy twin),
+ *                         gEconpy/solvers/shared.py:74-75 (R = -(C T + B)^-1 D), gEconpy/model/statespace.py:213
+ *                         (policy residual), gEconpy/solvers/backward_looking.py:8-133 (C == 0 special case)
+ *   gecon_bk_count_*      gEconpy/model/perturbation.py:448-505,586-625 (check_bk_condition_pt),
+ *                         gEconpy/solvers/gensys.py:568-614 (pencil assembly), gEconpy/pytensorf/real_eig.py:31-36
+ *   gecon_dlyap_*         pt.linalg.solve_discrete_lyapunov call at gEconpy/model/statespace.py:814-815
+ *   gecon_kalman_ll_*     PyMCStateSpace.build_statespace_graph call at gEconpy/model/statespace.py:1151-1157
+ *                         (pymc_extras StandardFilter), with Q/H/Z/d as built at statespace.py:240-296,334-388,800-812
+ *   gecon_solve_*         the np.linalg.solve / _solve_gen call sites (cycle_reduction.py:181,396; backward_looking.py)
+ *
+ * Conventions
+ *   - All matrices are IEEE fp64, C-contiguous (row-major), batched on a leading draw axis:
+ *     A[N][n][n], D[N][n][k], T[N][n][n], R[N][n][k].  Inputs are never written.
+ *   - Entry points ending in `_batched` take DEVICE pointers and a CUDA stream (a cudaStream_t passed as
+ *     void*; NULL = default stream) and return immediately after the launch.  Entry points ending in `_host` take
+ *     HOST pointers, copy in, launch, copy out and synchronise.
+ *   - The return value is 0 on success, a negative GECON_E_* for bad arguments, or a positive cudaError_t.
+ *     gecon_get_last_error() returns a message for the calling thread's last failure.
+ *   - Numerical failure is never an error code: it is reported per draw in `status` (bit field below), exactly as
+ *     the reference reports it through flags / NaN fills / -inf potentials.
+ *   - Supported sizes: 1 <= n <= 56, 0 <= k <= n, 1 <= p <= 8.
+ */
+#ifndef GECON_B200_H
+#define GECON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GECON_ABI_VERSION 1
+
+/* argument errors */
+#define GECON_E_BADARG (-1)
+#define GECON_E_UNSUPPORTED_SIZE (-2)
+#define GECON_E_NO_DEVICE (-3)
+
+/* per-draw status bits (0 = everything fine) */
+#define GECON_ST_CR_NOT_CONVERGED 0x001  /* cycle reduction hit max_iter or a NaN norm: T = 0 (cycle_reduction.py:181-183) */
+#define GECON_ST_CR_NAN 0x002            /* the A0 norm became NaN */
+#define GECON_ST_SINGULAR 0x004          /* a linear solve met a zero / non-finite pivot: output NaN-filled */
+#define GECON_ST_RESID 0x008             /* sum((A + B T + C T T)^2) >= resid_tol (statespace.py:1210-1215) */
+#define GECON_ST_BK 0x010                /* n_unstable != n_forward (perturbation.py:612-625) */
+#define GECON_ST_BK_INCONCLUSIVE 0x020   /* eigenvalue count could not be resolved (eigenvalue on the unit circle) */
+#define GECON_ST_LYAP 0x040              /* doubling iteration for P0 did not converge (rho(T) >= 1) */
+#define GECON_ST_NOT_PD 0x080            /* innovation covariance F_t not positive definite at some t */
+#define GECON_ST_LL_NONFINITE 0x100      /* log-likelihood is NaN or +-inf */
+#define GECON_ST_JAC_NONFINITE 0x200     /* steady state / Jacobian evaluation produced a non-finite entry */
+#define GECON_ST_SKIPPED 0x400           /* draw skipped because status_in & gate_mask != 0 */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Cycle reduction:  A + B T + C T T = 0,  R = -(C T + B)^-1 D,  resid = sum((A + B T + C T T)^2).
+ * A = d/dx_{t-1}, B = d/dx_t, C = d/dx_{t+1}, D = d/deps  (the REFERENCE's naming, perturbation.py:42-46).
+ * Follows _cycle_reduction_core: T = 0 and GECON_ST_CR_NOT_CONVERGED unless ||A0||_1 < tol and ||A2||_1 < tol
+ * within max_iter iterations.  If C is NULL the system is backward looking: T = -B^-1 A, R = -B^-1 D.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gecon_cr_args {
+    size_t struct_size;  /* sizeof(gecon_cr_args) */
+    const double* A;     /* [N][n][n] */
+    const double* B;     /* [N][n][n] */
+    const double* C;     /* [N][n][n] or NULL */
+    const double* D;     /* [N][n][k] or NULL (then R is not computed) */
+    int64_t N;
+    int32_t n;
+    int32_t k;
+    int32_t max_iter;
+    int32_t reserved0;
+    double tol;
+    double resid_tol;       /* sets GECON_ST_RESID when resid >= resid_tol or NaN; <= 0 disables */
+    const int32_t* unperm;  /* [n] or NULL: outputs are T[unperm][:, unperm], R[unperm] (statespace.py:217-220) */
+    double* T;              /* [N][n][n] out */
+    double* R;              /* [N][n][k] out or NULL */
+    int32_t* status;        /* [N] out (overwritten) */
+    int32_t* n_iter;        /* [N] out or NULL: iterations executed */
+    double* resid;          /* [N] out or NULL */
+    double* norms;          /* [N][2] out or NULL: final ||A0||_1, ||A2||_1 */
+} gecon_cr_args;
+
+int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream);
+int gecon_cr_solve_host(const gecon_cr_args* args);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Blanchard-Kahn count on the regularised Sims pencil of check_bk_condition_pt:
+ *   Gamma0 = [[B, C], [-I, 0]], Gamma1 = [[A, 0], [0, I]], rows/cols {0..n-1} U {n + lead_idx[j]},
+ *   M = (-Gamma0_sel + 1e-8 I)^-1 Gamma1_sel,  n_unstable = #{|eig(M)| > 1},  ok = (n_unstable == n_lead).
+ * The count is obtained without forming eigenvalues: #{|lambda| > 1} = (m + trace sign(N)) / 2 with
+ * N = (Gamma1_sel - G)(Gamma1_sel + G)^-1, G = -Gamma0_sel + 1e-8 I  (Cayley transform + matrix sign function).
+ * Sets GECON_ST_BK / GECON_ST_BK_INCONCLUSIVE in status (OR-ed into the existing value when accumulate != 0).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gecon_bk_args {
+    size_t struct_size;
+    const double* A;
+    const double* B;
+    const double* C;
+    int64_t N;
+    int32_t n;
+    int32_t n_lead;
+    const int32_t* lead_idx; /* [n_lead] column positions (in the order of A,B,C) of the structural lead variables */
+    int32_t accumulate;      /* 0: status is overwritten, else OR-ed */
+    int32_t max_iter;        /* Newton iterations of the sign function (<= 0: default 60) */
+    int32_t* n_unstable;     /* [N] out or NULL (-1 when inconclusive) */
+    int32_t* status;         /* [N] in/out */
+} gecon_bk_args;
+
+int gecon_bk_count_batched(const gecon_bk_args* args, void* stream);
+int gecon_bk_count_host(const gecon_bk_args* args);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Discrete Lyapunov equation P = T P T' + R diag(q) R' by Smith doubling.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gecon_dlyap_args {
+    size_t struct_size;
+    const double* T;     /* [N][n][n] */
+    const double* R;     /* [N][n][k] */
+    const double* qdiag; /* shock variances: [N][k] (q_stride = k) or [k] shared (q_stride = 0) */
+    int64_t q_stride;
+    int64_t N;
+    int32_t n;
+    int32_t k;
+    int32_t max_iter; /* <= 0: default 64 */
+    int32_t accumulate;
+    double* P;        /* [N][n][n] out */
+    int32_t* status;  /* [N] */
+    int32_t* n_iter;  /* [N] out or NULL */
+} gecon_dlyap_args;
+
+int gecon_dlyap_batched(const gecon_dlyap_args* args, void* stream);
+int gecon_dlyap_host(const gecon_dlyap_args* args);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Kalman-filter log-likelihood (pymc_extras StandardFilter semantics: update -> jitter -> predict, Joseph form,
+ * missing observations masked out of Z and H, a0 = 0, P0 = dlyap(T, R Q R') unless P0 is given):
+ *   x_t = T x_{t-1} + R eps_t, eps ~ N(0, diag(q));   y_t = d + Z x_t + eta_t, eta ~ N(0, diag(h)).
+ * Z is either dense (p x n, shared by all draws) or a selector given by obs_idx (Z[a][obs_idx[a]] = 1).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gecon_kalman_args {
+    size_t struct_size;
+    const double* T;     /* [N][n][n] */
+    const double* R;     /* [N][n][k] */
+    const double* qdiag; /* shock variances, [N][k] or shared [k] */
+    int64_t q_stride;    /* k or 0 */
+    const double* hdiag; /* measurement-error variances, [N][p] or shared [p]; NULL = 0 */
+    int64_t h_stride;    /* p or 0 */
+    const double* Z;     /* [p][n] shared, or NULL when obs_idx is given */
+    const int32_t* obs_idx; /* [p] or NULL */
+    const double* d;     /* observation intercept: [N][p] (d_stride = p), shared [p] (0), or NULL = 0 */
+    int64_t d_stride;
+    const double* Y;     /* [Tobs][p] shared by all draws; NaN or missing_fill marks a missing entry */
+    const double* P0;    /* [N][n][n] or NULL (computed in-kernel by doubling) */
+    int64_t N;
+    int32_t n;
+    int32_t k;
+    int32_t p;
+    int32_t Tobs;
+    double jitter;        /* cov_jitter, reference default 1e-8 */
+    double missing_fill;  /* reference default -9999.0 */
+    int32_t mvn_const_mode; /* 0: -0.5 * (p log 2pi + ...) per step; 1: bare log 2pi (older pymc_extras) */
+    int32_t lyap_max_iter;  /* <= 0: default 64 */
+    const int32_t* status_in; /* [N] or NULL */
+    int32_t gate_mask;    /* draws with status_in & gate_mask get ll = -inf and are skipped (the reference's
+                             pm.Potential(-inf) gates, statespace.py:1206-1215) */
+    int32_t reserved0;
+    double* ll;           /* [N] out */
+    int32_t* status;      /* [N] out: status_in | new bits (may alias status_in) */
+    double* ll_t;         /* [N][Tobs] out or NULL: per-observation log-likelihood */
+} gecon_kalman_args;
+
+int gecon_kalman_ll_batched(const gecon_kalman_args* args, void* stream);
+int gecon_kalman_ll_host(const gecon_kalman_args* args);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched general solve X = M^-1 RHS with partial pivoting (NaN-filled + GECON_ST_SINGULAR on failure),
+ * and a batched product C = alpha * op(A) * op(B) (exercises the in-CTA DMMA GEMM; used by tests).
+ * ------------------------------------------------------------------------------------------------------------- */
+int gecon_solve_batched(const double* M, const double* RHS, int64_t N, int32_t n, int32_t m, double* X, int32_t* status,
+                        void* stream);
+int gecon_solve_host(const double* M, const double* RHS, int64_t N, int32_t n, int32_t m, double* X, int32_t* status);
+int gecon_gemm_batched(const double* A, const double* B, int64_t N, int32_t n, int32_t trans_a, int32_t trans_b, double alpha,
+                       double* C, void* stream);
+int gecon_gemm_host(const double* A, const double* B, int64_t N, int32_t n, int32_t trans_a, int32_t trans_b, double alpha,
+                    double* C);
+
+/* library / device information */
+int gecon_abi_version(void);
+int gecon_device_count(void);
+const char* gecon_get_last_error(void);
+/* resident CTAs per SM and dynamic shared memory (bytes) of a kernel for state dimension n:
+ * which = 0 cr_solve, 1 kalman_ll (needs p, Tobs), 2 bk_count (n = pencil size), 3 dlyap */
+int gecon_kernel_info(int32_t which, int32_t n, int32_t p, int32_t Tobs, int32_t* ctas_per_sm, int32_t* smem_bytes,
+                      int32_t* threads);
+/* counts kernel launches made by this library in the calling process (bench.py's gpu_launches) */
+int64_t gecon_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Per-model generated libraries (geconpy_b200/model/codegen.py emits one per model spec) export:
+ *   int gecon_model_info(int32_t* n, int32_t* k, int32_t* n_theta);
+ *   int gecon_model_jacobian_batched(const double* theta, int64_t N, double* A, double* B, double* C, double* D,
+ *                                    double* xss, int32_t* status, void* stream);
+ * theta is [N][n_theta]; A,B,C,D come out in the reference's permuted solver order (perturbation.py:130-158).
+ * Replaces the compiled pytensor function f(*ss, *params) -> [A,B,C,D] (model.py:1647-1664, build.py:681-695).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef int (*gecon_model_jacobian_fn)(const double* theta, int64_t N, double* A, double* B, double* C, double* D, double* xss,
+                                       int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GECON_B200_H */

@@ -1,0 +1,250 @@
+"""GPU parity tests: every CUDA kernel, called through the C ABI, against the CPU oracle on identical seeded inputs.
+
+Tolerances are the north star's (BASELINE.json): flags exact, T/R <= 1e-9 relative Frobenius, log-likelihood
+<= 1e-7 absolute.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from helpers import SIGMA_ERR, SIGMA_SHOCK, draws, jacobian_batch, model, observed_idx, rel_fro, simulate_obs
+from oracle import solvers as osol
+from oracle import statespace as oss
+
+pytestmark = pytest.mark.gpu
+
+TOL_TR = 1e-9
+TOL_LL = 1e-7
+
+MODELS = ["rbc", "one_block_1_ss", "rbc_extended", "full_nk", "new_keynesian", "nk_complete_more_shocks"]
+
+
+@pytest.fixture(scope="module")
+def B():
+    from geconpy_b200 import batched
+
+    return batched
+
+
+# ------------------------------------------------------------------------------------------- building blocks
+@pytest.mark.parametrize("n", [1, 3, 8, 9, 16, 17, 24, 31, 40, 45, 56])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_matches_numpy(B, rng, n, ta, tb):
+    A = rng.standard_normal((5, n, n))
+    Bm = rng.standard_normal((5, n, n))
+    out = B.gemm(A, Bm, trans_a=ta, trans_b=tb, alpha=-0.5)
+    ref = -0.5 * np.matmul(A.transpose(0, 2, 1) if ta else A, Bm.transpose(0, 2, 1) if tb else Bm)
+    assert np.abs(out - ref).max() <= 1e-13 * n
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (5, 2), (9, 9), (24, 24), (24, 4), (31, 9), (45, 13), (56, 56)])
+def test_solve_matches_lapack(B, rng, n, m):
+    M = rng.standard_normal((7, n, n)) + 0.1 * np.eye(n)
+    M[1, [0, -1]] = M[1, [-1, 0]]  # force pivoting
+    rhs = rng.standard_normal((7, n, m))
+    X, st = B.solve(M, rhs)
+    ref = np.linalg.solve(M, rhs)
+    assert (st == 0).all()
+    for i in range(7):
+        assert rel_fro(X[i], ref[i]) <= 1e-11 * max(1.0, np.linalg.cond(M[i]) / 1e3)
+
+
+def test_solve_singular_is_nan_filled(B, rng):
+    n = 6
+    M = rng.standard_normal((3, n, n))
+    M[1, :, 2] = 0.0
+    X, st = B.solve(M, rng.standard_normal((3, n, 2)))
+    assert st[0] == 0 and st[2] == 0 and st[1] != 0
+    assert np.isnan(X[1]).all() and np.isfinite(X[0]).all()
+
+
+# ------------------------------------------------------------------------------------------- cycle reduction
+@pytest.mark.parametrize("name", MODELS)
+def test_cycle_reduction_parity(B, name):
+    mod = model(name)
+    th = draws(mod, 24, seed=1)
+    A, Bm, C, D = jacobian_batch(mod, th)
+    res = B.cr_solve(A, Bm, C, D, max_iter=1000, tol=1e-9, resid_tol=1e-8)
+    n_conv = 0
+    for i in range(len(th)):
+        T, conv, n_iter = osol.cycle_reduction_core(A[i], Bm[i], C[i], max_iter=1000, tol=1e-9)
+        assert bool(res.converged[i]) == bool(conv), (name, i)
+        assert int(res.n_iter[i]) == n_iter, (name, i)
+        if conv:
+            n_conv += 1
+            R = osol.selection_matrix(Bm[i], C[i], D[i], T)
+            assert rel_fro(res.T[i], T) <= TOL_TR, (name, i)
+            assert rel_fro(res.R[i], R) <= TOL_TR, (name, i)
+            assert abs(res.resid[i] - osol.policy_residual(A[i], Bm[i], C[i], T)) <= 1e-18 + 1e-6 * res.resid[i]
+            # jumper columns of T are exactly zero (tests/model/test_perturbation.py:166-206)
+            zero_cols = np.abs(A[i]).sum(axis=0) == 0
+            assert (res.T[i][:, zero_cols] == 0).all()
+    assert n_conv >= len(th) // 2
+
+
+def test_cycle_reduction_unpermute_and_flags(B):
+    mod = model("full_nk")
+    th = draws(mod, 4, seed=2)
+    A, Bm, C, D = jacobian_batch(mod, th)
+    res = B.cr_solve(A, Bm, C, D, unperm=mod.inv_var_order.astype(np.int32))
+    raw = B.cr_solve(A, Bm, C, D)
+    for i in range(4):
+        T, R = mod.unpermute_policy(raw.T[i], raw.R[i])
+        assert np.array_equal(res.T[i], T) and np.array_equal(res.R[i], R)
+    # max_iter exhausted -> not converged, T = 0 (cycle_reduction.py:181-183)
+    short = B.cr_solve(A, Bm, C, D, max_iter=3)
+    assert not short.converged.any()
+    assert (short.T == 0).all()
+    assert (short.n_iter == 3).all()
+    for i in range(4):
+        T, conv, n_iter = osol.cycle_reduction_core(A[i], Bm[i], C[i], max_iter=3, tol=1e-9)
+        assert not conv and n_iter == 3
+        assert rel_fro(short.R[i], osol.selection_matrix(Bm[i], C[i], D[i], T)) <= TOL_TR
+
+
+def test_backward_looking(B, rng):
+    n, k = 7, 2
+    A = rng.standard_normal((3, n, n)) * 0.3
+    Bm = rng.standard_normal((3, n, n)) + 2 * np.eye(n)
+    D = rng.standard_normal((3, n, k))
+    res = B.cr_solve(A, Bm, None, D)
+    for i in range(3):
+        T, R = osol.backward_direct(A[i], Bm[i], None, D[i])
+        assert rel_fro(res.T[i], T) <= TOL_TR and rel_fro(res.R[i], R) <= TOL_TR
+        assert np.abs(A[i] + Bm[i] @ res.T[i]).max() <= 1e-12  # tests/solvers/test_backward_looking.py:38-63
+
+
+# ------------------------------------------------------------------------------------------- Blanchard-Kahn
+@pytest.mark.parametrize("name", MODELS)
+def test_bk_count_parity(B, name):
+    mod = model(name)
+    th = draws(mod, 24, seed=3, width=0.1)
+    A, Bm, C, D = jacobian_batch(mod, th)
+    fin = np.isfinite(A).all(axis=(1, 2)) & np.isfinite(Bm).all(axis=(1, 2)) & np.isfinite(C).all(axis=(1, 2))
+    assert fin.sum() >= 8
+    A, Bm, C, D, th = A[fin], Bm[fin], C[fin], D[fin], th[fin]
+    lead = mod.permuted_lead_var_idx.astype(np.int32)
+    nu, st = B.bk_count(A, Bm, C, lead)
+    from geconpy_b200 import _lib as L
+
+    for i in range(len(th)):
+        ok, n_fwd, n_unst = osol.bk_condition_pt(A[i], Bm[i], C[i], D[i], mod.permuted_lead_var_idx)
+        assert not (st[i] & L.ST_BK_INCONCLUSIVE), (name, i)
+        assert int(nu[i]) == n_unst, (name, i)
+        assert bool(st[i] & L.ST_BK) == (not ok), (name, i)
+
+
+def test_bk_pert_fails_model(B):
+    """pert_fails.gcn is the reference's broken-model fixture (tests/model/test_model.py:501-529)."""
+    mod = model("pert_fails")
+    if not mod.analytic_ss:
+        pytest.skip("pert_fails has no analytic steady state in the spec")
+    th = draws(mod, 2, seed=0)
+    A, Bm, C, D = jacobian_batch(mod, th)
+    nu, st = B.bk_count(A, Bm, C, mod.permuted_lead_var_idx.astype(np.int32))
+    for i in range(2):
+        ok, _, n_unst = osol.bk_condition_pt(A[i], Bm[i], C[i], D[i], mod.permuted_lead_var_idx)
+        assert int(nu[i]) == n_unst
+
+
+# ------------------------------------------------------------------------------------------- Lyapunov / Kalman
+def _policies(mod, th):
+    A, Bm, C, D = jacobian_batch(mod, th)
+    T, R = [], []
+    for i in range(len(th)):
+        t, conv, _ = osol.cycle_reduction_core(A[i], Bm[i], C[i], max_iter=1000, tol=1e-9)
+        assert conv
+        r = osol.selection_matrix(Bm[i], C[i], D[i], t)
+        t, r = mod.unpermute_policy(t, r)
+        T.append(t), R.append(r)
+    return np.stack(T), np.stack(R)
+
+
+@pytest.mark.parametrize("name", ["rbc", "full_nk", "nk_complete_more_shocks"])
+def test_dlyap_parity(B, name):
+    mod = model(name)
+    th = draws(mod, 6, seed=4, width=0.02)
+    T, R = _policies(mod, th)
+    q = np.full(mod.k, SIGMA_SHOCK**2)
+    P, st, it = B.dlyap(T, R, q)
+    assert (st == 0).all()
+    for i in range(len(th)):
+        ref = oss.dlyap(T[i], R[i] @ np.diag(q) @ R[i].T)
+        assert np.abs(P[i] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc", 200), ("full_nk", 200), ("nk_complete_more_shocks", 50)])
+@pytest.mark.parametrize("selector", [True, False])
+def test_kalman_parity(B, name, Tobs, selector):
+    mod = model(name)
+    th = draws(mod, 6, seed=5, width=0.02)
+    T, R = _policies(mod, th)
+    Y = simulate_obs(mod, Tobs, seed=0, sigma_err=SIGMA_ERR)
+    obs = observed_idx(mod)
+    p = len(obs)
+    q = np.full((len(th), mod.k), SIGMA_SHOCK**2) * (1.0 + 0.1 * np.arange(len(th)))[:, None]
+    h = np.full(p, SIGMA_ERR**2)
+    Z = oss.selector_design(mod.var_names, mod.spec["observed_default"])
+    kw = dict(obs_idx=obs) if selector else dict(Z=Z)
+    ll, st, llt = B.kalman_loglik(T, R, q, Y, hdiag=h, return_per_step=True, **kw)
+    for i in range(len(th)):
+        ref, ref_t = oss.kalman_loglik(Y, T[i], R[i], np.diag(q[i]), Z, np.diag(h), return_all=True)
+        assert st[i] == 0
+        assert np.abs(llt[i] - ref_t).max() <= TOL_LL, (name, i, np.abs(llt[i] - ref_t).max())
+        assert abs(ll[i] - ref) <= TOL_LL, (name, i, ll[i], ref)
+
+
+def test_kalman_missing_data_no_measurement_error_and_intercept(B):
+    mod = model("full_nk")
+    th = draws(mod, 3, seed=6, width=0.02)
+    T, R = _policies(mod, th)
+    Y = simulate_obs(mod, 120, seed=1)
+    rng = np.random.default_rng(7)
+    Ym = Y.copy()
+    Ym[rng.random(Y.shape) < 0.25] = np.nan
+    Ym[5] = np.nan          # a fully missing row
+    Ym[9, 0] = -9999.0      # the fill value also marks a missing entry
+    obs = observed_idx(mod)
+    q = np.full(mod.k, SIGMA_SHOCK**2)
+    Z = oss.selector_design(mod.var_names, mod.spec["observed_default"])
+    d = np.array([0.01, -0.02, 0.005])
+    for Yc, dd in ((Y, None), (Ym, None), (Y, d)):
+        ll, st = B.kalman_loglik(T, R, q, Yc, obs_idx=obs, d=dd)
+        ll2, _ = B.kalman_loglik(T, R, q, Yc, Z=Z, d=dd, mvn_const="bare")
+        for i in range(len(th)):
+            ref = oss.kalman_loglik(Yc, T[i], R[i], np.diag(q), Z, np.zeros((3, 3)), d=dd)
+            ref2 = oss.kalman_loglik(Yc, T[i], R[i], np.diag(q), Z, np.zeros((3, 3)), d=dd, mvn_const="bare")
+            assert abs(ll[i] - ref) <= TOL_LL, (i, ll[i], ref)
+            assert abs(ll2[i] - ref2) <= TOL_LL, (i, ll2[i], ref2)
+
+
+def test_kalman_gating_and_given_P0(B):
+    mod = model("rbc")
+    th = draws(mod, 4, seed=8, width=0.02)
+    T, R = _policies(mod, th)
+    Y = simulate_obs(mod, 60, seed=2)
+    q = np.full(mod.k, SIGMA_SHOCK**2)
+    obs = observed_idx(mod)
+    P0 = np.stack([oss.dlyap(T[i], R[i] @ np.diag(q) @ R[i].T) for i in range(4)])
+    status_in = np.array([0, 0x10, 0, 0x8], dtype=np.int32)
+    ll, st = B.kalman_loglik(T, R, q, Y, obs_idx=obs, P0=P0, status_in=status_in, gate_mask=0x18)
+    assert np.isneginf(ll[1]) and np.isneginf(ll[3])
+    Z = oss.selector_design(mod.var_names, mod.spec["observed_default"])
+    for i in (0, 2):
+        ref = oss.kalman_loglik(Y, T[i], R[i], np.diag(q), Z, np.zeros((1, 1)), P0=P0[i])
+        assert abs(ll[i] - ref) <= TOL_LL
+
+
+def test_device_pointer_path_matches_host_path(B):
+    import torch
+
+    mod = model("full_nk")
+    th = draws(mod, 8, seed=9)
+    A, Bm, C, D = jacobian_batch(mod, th)
+    host = B.cr_solve(A, Bm, C, D)
+    dev = B.cr_solve(*(torch.as_tensor(x, device="cuda") for x in (A, Bm, C, D)))
+    assert np.array_equal(dev.T.cpu().numpy(), host.T)
+    assert np.array_equal(dev.R.cpu().numpy(), host.R)
+    assert np.array_equal(dev.status.cpu().numpy(), host.status)
