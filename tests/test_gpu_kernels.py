@@ -77,7 +77,8 @@ def test_cycle_reduction_parity(B, name):
             R = osol.selection_matrix(Bm[i], C[i], D[i], T)
             assert rel_fro(res.T[i], T) <= TOL_TR, (name, i)
             assert rel_fro(res.R[i], R) <= TOL_TR, (name, i)
-            assert abs(res.resid[i] - osol.policy_residual(A[i], Bm[i], C[i], T)) <= 1e-18 + 1e-6 * res.resid[i]
+            # the residual of a converged draw is rounding noise (~1e-16..1e-25); the gate it feeds is 1e-8
+            assert abs(res.resid[i] - osol.policy_residual(A[i], Bm[i], C[i], T)) <= 1e-13 + 1e-6 * res.resid[i]
             # jumper columns of T are exactly zero (tests/model/test_perturbation.py:166-206)
             zero_cols = np.abs(A[i]).sum(axis=0) == 0
             assert (res.T[i][:, zero_cols] == 0).all()
