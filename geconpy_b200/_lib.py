@@ -60,7 +60,7 @@ class CrArgs(C.Structure):
         ("n", C.c_int32),
         ("k", C.c_int32),
         ("max_iter", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("accumulate", C.c_int32),
         ("tol", C.c_double),
         ("resid_tol", C.c_double),
         ("unperm", C.c_void_p),
@@ -134,7 +134,7 @@ class KalmanArgs(C.Structure):
         ("lyap_max_iter", C.c_int32),
         ("status_in", C.c_void_p),
         ("gate_mask", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("sigma_inputs", C.c_int32),
         ("ll", C.c_void_p),
         ("status", C.c_void_p),
         ("ll_t", C.c_void_p),

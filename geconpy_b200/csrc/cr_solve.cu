@@ -31,7 +31,6 @@ struct CrSmem {
 template <int NP>
 __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_args p) {
     using C = Cfg<NP>;
-    constexpr int LD = C::LD;
     extern __shared__ __align__(16) double sm[];
     double* A0 = sm;
     double* A1 = A0 + C::TILE;
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
                     p.norms[2 * draw] = a0n;
                     p.norms[2 * draw + 1] = a2n;
                 }
-                p.status[draw] = status;
+                p.status[draw] = p.accumulate ? (p.status[draw] | status) : status;
             }
         }
         tile_store<NP>(p.T + (size_t)draw * n * n, Tt, n, n, n, 1.0, perm, perm);
@@ -262,6 +261,7 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
     GECON_CUDA(dSt.alloc(N * sizeof(int32_t)));
     GECON_CUDA(cudaMemcpy(dA.p, args->A, bm, cudaMemcpyHostToDevice));
     GECON_CUDA(cudaMemcpy(dB.p, args->B, bm, cudaMemcpyHostToDevice));
+    if (args->accumulate) GECON_CUDA(cudaMemcpy(dSt.p, args->status, N * sizeof(int32_t), cudaMemcpyHostToDevice));
     d.A = dA.as<double>();
     d.B = dB.as<double>();
     d.T = dT.as<double>();

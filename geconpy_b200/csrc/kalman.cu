@@ -206,9 +206,13 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) kalman_ll_kernel(const gecon_kalm
         tile_load<NP>(Tm, p.T + (size_t)draw * n * n, n, n, n);
         tile_load<NP>(W, p.R + (size_t)draw * n * k, n, k, k);
         tile_zero<NP>(RQ);
-        if (tid < k) s_q[tid] = p.qdiag[(size_t)draw * p.q_stride + tid];
+        if (tid < k) {
+            const double qv = p.qdiag[(size_t)draw * p.q_stride + tid];
+            s_q[tid] = p.sigma_inputs ? qv * qv : qv;
+        }
         if (tid < np) {
-            s_h[tid] = p.hdiag ? p.hdiag[(size_t)draw * p.h_stride + tid] : 0.0;
+            const double hv = p.hdiag ? p.hdiag[(size_t)draw * p.h_stride + tid] : 0.0;
+            s_h[tid] = p.sigma_inputs ? hv * hv : hv;
             s_d[tid] = p.d ? p.d[(size_t)draw * p.d_stride + tid] : 0.0;
         }
         if (tid < NP) s_a[tid] = 0.0;

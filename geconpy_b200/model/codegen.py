@@ -1,0 +1,346 @@
+"""Model spec -> CUDA device code for  theta -> deterministic parameters -> x_ss(theta) -> A, B, C, D.
+
+This is the B200 replacement for the compiled pytensor function ``f(*ss, *params) -> [A, B, C, D]`` that the
+reference builds in ``statespace_from_gcn`` (gEconpy/model/build.py:640-695) from
+
+* ``compile_param_dict_func``  (gEconpy/model/parameters.py:11-69)    free -> deterministic parameters,
+* ``compile_known_ss``         (gEconpy/model/steady_state.py:315-357) analytic steady state,
+* ``linearize_model``          (gEconpy/model/perturbation.py:97-198)  incidence -> eq_order / var_order, entries
+                                                                       d eq_i / d x_j at the steady state with
+                                                                       shocks = 0, log-linear column scaling,
+* ``build_symbolic_jacobians`` (gEconpy/model/compile.py:163-222)      one shared ``sp.cse`` over all four matrices;
+                                                                       constant entries baked in, symbolic scattered.
+
+The contract is the same -- same entries, same orderings, one shared CSE -- but the expression DAG is printed as a
+CUDA ``__global__`` function (one thread per parameter draw) instead of being handed to a tracing compiler, and is
+compiled by nvcc for sm_100a at model-build time (``geconpy_b200.build.build_model``).
+
+The input is this repo's model-spec format (``tests/golden/models/*.json``: variables, shocks, equations with
+``<name>__tm1 | __t | __tp1 | __ss`` symbols, free / deterministic parameters, analytic steady state, sign
+assumptions).  Parsing GCN files and deriving first-order conditions is out of scope.
+"""
+
+from __future__ import annotations
+
+import json
+import re
+
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+import sympy as sp
+
+_TIME_SUFFIX = {-1: "__tm1", 0: "__t", 1: "__tp1"}
+
+
+def load_spec(path_or_dict) -> dict:
+    if isinstance(path_or_dict, dict):
+        return path_or_dict
+    return json.loads(Path(path_or_dict).read_text())
+
+
+def _c_ident(prefix: str, name: str) -> str:
+    return prefix + re.sub(r"[^0-9A-Za-z_]", "_", name)
+
+
+@dataclass
+class LinearizedModel:
+    """Symbolic linearisation of one model spec plus everything the kernels need to know about its structure."""
+
+    spec: dict
+    log_linearize: bool = True
+    not_loglin_variables: tuple = ()
+    name: str = field(init=False)
+
+    def __post_init__(self):
+        spec = self.spec
+        self.name = spec["name"]
+        self.var_names = list(spec["variables"])
+        self.shock_names = list(spec["shocks"])
+        self.param_names = list(spec["free_params"])
+        self.defaults = {k: float(v) for k, v in spec["free_params"].items()}
+        self.det_names = list(spec.get("deterministic_params", {}))
+        self.n = len(self.var_names)
+        self.k = len(self.shock_names)
+        self.n_theta = len(self.param_names)
+        if spec.get("calibrated_params"):
+            raise NotImplementedError("calibrated parameters are not supported on the estimation path (build.py:637-638)")
+        if any(spec["steady_state"].get(v) is None for v in self.var_names):
+            raise NotImplementedError("a complete analytic steady state is required on the estimation path (build.py:658-659)")
+        unknown = set(self.not_loglin_variables) - set(self.var_names)
+        if unknown:
+            raise ValueError(f"unknown variables in not_loglin_variables: {sorted(unknown)}")
+        if len(spec["equations"]) != self.n:
+            raise ValueError(f"{self.name}: {len(spec['equations'])} equations for {self.n} variables")
+
+        # ---- symbols: C-safe names, looked up from the spec's names while parsing
+        ns = {}
+        self.p_sym = {p: sp.Symbol(_c_ident("p_", p)) for p in self.param_names + self.det_names}
+        self.ss_sym = {v: sp.Symbol(_c_ident("ss_", v)) for v in self.var_names}
+        ns.update(self.p_sym)
+        self.t_sym = {}
+        for v in self.var_names:
+            ns[v + "__ss"] = self.ss_sym[v]
+            for t, suf in _TIME_SUFFIX.items():
+                self.t_sym[(v, t)] = ns[v + suf] = sp.Symbol(_c_ident(f"x{t + 1}_", v))
+        self.e_sym = {}
+        for s in self.shock_names:
+            for t, suf in _TIME_SUFFIX.items():
+                self.e_sym[(s, t)] = ns[s + suf] = sp.Symbol(_c_ident(f"e{t + 1}_", s))
+            ns[s + "__ss"] = sp.Float(0.0)
+
+        def parse(text):
+            return sp.sympify(text, locals=ns)
+
+        self.det_exprs = [parse(spec["deterministic_params"][d]) for d in self.det_names]
+        self.ss_exprs = [parse(spec["steady_state"][v]) for v in self.var_names]
+        equations = [parse(e) for e in spec["equations"]]
+
+        # ---- incidence and the [S|L|E|B] x [s|p|m|f] permutations (perturbation.py:112-158)
+        n = self.n
+        eq_lag = np.zeros(n, bool)
+        eq_lead = np.zeros(n, bool)
+        var_lag = np.zeros(n, bool)
+        var_lead = np.zeros(n, bool)
+        for i, eq in enumerate(equations):
+            free = eq.free_symbols
+            for j, v in enumerate(self.var_names):
+                if self.t_sym[(v, -1)] in free:
+                    eq_lag[i] = var_lag[j] = True
+                if self.t_sym[(v, 1)] in free:
+                    eq_lead[i] = var_lead[j] = True
+        groups_e = (~eq_lag & ~eq_lead, eq_lag & ~eq_lead, ~eq_lag & eq_lead, eq_lag & eq_lead)
+        groups_v = (~var_lag & ~var_lead, var_lag & ~var_lead, var_lag & var_lead, ~var_lag & var_lead)
+        self.eq_order = np.concatenate([np.flatnonzero(g) for g in groups_e]).astype(np.int32)
+        self.var_order = np.concatenate([np.flatnonzero(g) for g in groups_v]).astype(np.int32)
+        self.inv_var_order = np.argsort(self.var_order).astype(np.int32)
+        self.inv_eq_order = np.argsort(self.eq_order).astype(np.int32)
+        self.var_has_lag, self.var_has_lead = var_lag, var_lead
+        # structural lead variables (statespace.py:224-233), translated to permuted positions (statespace.py:769)
+        self.lead_var_idx = np.flatnonzero(var_lead).astype(np.int32)
+        self.permuted_lead_var_idx = self.inv_var_order[self.lead_var_idx].astype(np.int32)
+        # state (lagged) variables occupy one contiguous column block in solver order
+        self.state_var_idx = np.flatnonzero(var_lag).astype(np.int32)
+
+        # ---- entries in solver order: rows eq_order, columns var_order; vars -> ss, shocks -> 0 (compile.py:196-202)
+        to_ss = {}
+        for v in self.var_names:
+            for t in _TIME_SUFFIX:
+                to_ss[self.t_sym[(v, t)]] = self.ss_sym[v]
+        for s in self.shock_names:
+            for t in _TIME_SUFFIX:
+                to_ss[self.e_sym[(s, t)]] = sp.Integer(0)
+        eqs_perm = [equations[i] for i in self.eq_order]
+        vars_perm = [self.var_names[j] for j in self.var_order]
+
+        def grid(wrt):
+            return [[eq.diff(x).xreplace(to_ss) for x in wrt] for eq in eqs_perm]
+
+        self.entries = {
+            "A": grid([self.t_sym[(v, -1)] for v in vars_perm]),
+            "B": grid([self.t_sym[(v, 0)] for v in vars_perm]),
+            "C": grid([self.t_sym[(v, 1)] for v in vars_perm]),
+            "D": grid([self.e_sym[(s, 0)] for s in self.shock_names]),
+        }
+
+        # ---- log-linear column scale per variable, in solver column order (perturbation.py:178-190)
+        linear = bool(spec.get("linear", False))
+        self.scale_kind = []  # "one" | "ss" | "switch"
+        for v in vars_perm:
+            assum = spec.get("assumptions", {}).get(v, {})
+            if linear or not self.log_linearize or v in self.not_loglin_variables or assum.get("negative", False):
+                self.scale_kind.append("one")
+            elif assum.get("positive", False):
+                self.scale_kind.append("ss")
+            else:
+                self.scale_kind.append("switch")
+        self.vars_perm = vars_perm
+
+    # ------------------------------------------------------------------------------------------------ statistics
+    def dag_stats(self) -> dict:
+        flat = [e for m in "ABCD" for row in self.entries[m] for e in row]
+        sym = [e for e in flat if not e.is_number]
+        subs, red = sp.cse(sym, optimizations="basic")
+        return {
+            "symbolic_entries": len(sym),
+            "constant_nonzero_entries": sum(1 for e in flat if e.is_number and e != 0),
+            "cse_temporaries": len(subs),
+            "ops": int(sum(sp.count_ops(r) for _, r in subs) + sum(sp.count_ops(r) for r in red)),
+        }
+
+    # ------------------------------------------------------------------------------------------------ code
+    def cuda_source(self) -> str:
+        """One translation unit: the per-draw device function, the batched kernel and the C-ABI launchers."""
+        n, k = self.n, self.k
+        lines = []
+        emit = lines.append
+        cc = lambda e: sp.ccode(e, strict=True)  # noqa: E731
+
+        emit("    // free parameters")
+        for i, p in enumerate(self.param_names):
+            emit(f"    const double {self.p_sym[p].name} = th[{i}];")
+        if self.det_names:
+            emit("    // deterministic parameters (parameters.py:11-69)")
+            for d, e in zip(self.det_names, self.det_exprs):
+                emit(f"    const double {self.p_sym[d].name} = {cc(e)};")
+        emit("    // analytic steady state (steady_state.py:315-357), one CSE pass")
+        ss_subs, ss_red = sp.cse(self.ss_exprs, symbols=sp.numbered_symbols("s_tmp_"), optimizations="basic")
+        for s, e in ss_subs:
+            emit(f"    const double {s.name} = {cc(e)};")
+        for v, e in zip(self.var_names, ss_red):
+            emit(f"    const double {self.ss_sym[v].name} = {cc(e)};")
+        emit("    if (xss) {")
+        for i, v in enumerate(self.var_names):
+            emit(f"        xss[{i}] = {self.ss_sym[v].name};")
+        emit("    }")
+        emit("    // log-linearisation column scales in solver column order (perturbation.py:178-190)")
+        for j, (v, kind) in enumerate(zip(self.vars_perm, self.scale_kind)):
+            ss = self.ss_sym[v].name
+            rhs = {"one": "1.0", "ss": ss, "switch": f"(({ss} > 0.0) ? {ss} : 1.0)"}[kind]
+            emit(f"    const double sc{j} = {rhs};")
+
+        # one shared CSE over the symbolic entries of all four matrices (compile.py:207-212)
+        sym_entries, where = [], []
+        const_entries = []
+        for m in "ABCD":
+            for i, row in enumerate(self.entries[m]):
+                for j, e in enumerate(row):
+                    if e.is_number:
+                        if e != 0:
+                            const_entries.append((m, i, j, float(e)))
+                    else:
+                        sym_entries.append(e)
+                        where.append((m, i, j))
+        subs, red = sp.cse(sym_entries, symbols=sp.numbered_symbols("j_tmp_"), optimizations="basic") if sym_entries else ([], [])
+        emit("    // Jacobian entries: shared CSE temporaries, then scatter (rows eq_order, columns var_order)")
+        for s, e in subs:
+            emit(f"    const double {s.name} = {cc(e)};")
+        emit("    double v; bool fin = true;")
+        width = {"A": n, "B": n, "C": n, "D": k}
+        for (m, i, j), e in zip(where, red):
+            scale = f" * sc{j}" if (m != "D" and self.scale_kind[j] != "one") else ""
+            emit(f"    v = ({cc(e)}){scale}; fin = fin && (fabs(v) <= 1.7e308); {m}[{i * width[m] + j}] = v;")
+        emit("    // constant entries")
+        for m, i, j, val in const_entries:
+            scale = f" * sc{j}" if (m != "D" and self.scale_kind[j] != "one") else ""
+            if scale:
+                emit(f"    v = {val!r}{scale}; fin = fin && (fabs(v) <= 1.7e308); {m}[{i * width[m] + j}] = v;")
+            else:
+                emit(f"    {m}[{i * width[m] + j}] = {val!r};")
+        body = "\n".join(lines)
+        ident = re.sub(r"[^0-9A-Za-z_]", "_", self.name)
+        return _TEMPLATE.format(name=ident, n=n, k=k, n_theta=self.n_theta, body=body)
+
+
+_TEMPLATE = r"""// GENERATED by geconpy_b200/model/codegen.py for model "{name}" -- do not edit.
+// theta -> deterministic parameters -> analytic steady state -> A, B, C (n x n), D (n x k) in solver order.
+// One thread per parameter draw; the matrices are zero-filled by the launcher and only non-zero entries are written.
+#include <math.h>
+#include <stdint.h>
+#include <stddef.h>
+#ifdef GECON_HOST_CHECK
+// Test-only build (g++, no CUDA): the generated expression code is compiled as a host function so that the CPU test
+// suite can check the code generator against the oracle without a GPU.  Never used by the product.
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#else
+#include <cuda_runtime.h>
+#endif
+
+#define GECON_MODEL_N {n}
+#define GECON_MODEL_K {k}
+#define GECON_MODEL_NTHETA {n_theta}
+#define GECON_ST_JAC_NONFINITE 0x200
+
+__device__ __forceinline__ bool gecon_model_eval(const double* __restrict__ th, double* __restrict__ A, double* __restrict__ B,
+                                                 double* __restrict__ C, double* __restrict__ D, double* __restrict__ xss) {{
+{body}
+    return fin;
+}}
+
+#ifdef GECON_HOST_CHECK
+extern "C" int gecon_model_eval_host_check(const double* theta, int64_t N, double* A, double* B, double* C, double* D, double* xss,
+                                           int32_t* status) {{
+    const size_t nn = (size_t)GECON_MODEL_N * GECON_MODEL_N;
+    for (int64_t i = 0; i < N; ++i) {{
+        const bool fin = gecon_model_eval(theta + (size_t)i * GECON_MODEL_NTHETA, A + i * nn, B + i * nn, C + i * nn,
+                                          D + (size_t)i * GECON_MODEL_N * GECON_MODEL_K, xss ? xss + (size_t)i * GECON_MODEL_N : nullptr);
+        if (status) status[i] = fin ? 0 : GECON_ST_JAC_NONFINITE;
+    }}
+    return 0;
+}}
+#else
+__global__ void __launch_bounds__(128) gecon_model_jacobian_kernel(const double* __restrict__ theta, long long N, double* __restrict__ A,
+                                                                   double* __restrict__ B, double* __restrict__ C,
+                                                                   double* __restrict__ D, double* __restrict__ xss,
+                                                                   int* __restrict__ status) {{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {{
+        const size_t nn = (size_t)GECON_MODEL_N * GECON_MODEL_N;
+        const bool fin = gecon_model_eval(theta + (size_t)i * GECON_MODEL_NTHETA, A + i * nn, B + i * nn, C + i * nn,
+                                          D + (size_t)i * GECON_MODEL_N * GECON_MODEL_K, xss ? xss + (size_t)i * GECON_MODEL_N : nullptr);
+        if (status) status[i] = fin ? 0 : GECON_ST_JAC_NONFINITE;
+    }}
+}}
+
+extern "C" int gecon_model_info(int32_t* n, int32_t* k, int32_t* n_theta) {{
+    if (n) *n = GECON_MODEL_N;
+    if (k) *k = GECON_MODEL_K;
+    if (n_theta) *n_theta = GECON_MODEL_NTHETA;
+    return 0;
+}}
+
+// DEVICE pointers; returns 0 or a cudaError_t.  Two memsets + one kernel on `stream`.
+extern "C" int gecon_model_jacobian_batched(const double* theta, int64_t N, double* A, double* B, double* C, double* D, double* xss,
+                                            int32_t* status, void* stream) {{
+    if (N <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nn = (size_t)N * GECON_MODEL_N * GECON_MODEL_N * sizeof(double);
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(A, 0, nn, st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(B, 0, nn, st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(C, 0, nn, st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(D, 0, (size_t)N * GECON_MODEL_N * GECON_MODEL_K * sizeof(double), st)) != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (N + 127) / 128;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    gecon_model_jacobian_kernel<<<(int)blocks, 128, 0, st>>>(theta, N, A, B, C, D, xss, status);
+    return (int)cudaGetLastError();
+}}
+
+// HOST pointers: copies theta in, runs, copies A, B, C, D (and xss, status if non-null) out, synchronises.
+extern "C" int gecon_model_jacobian_host(const double* theta, int64_t N, double* A, double* B, double* C, double* D, double* xss,
+                                         int32_t* status) {{
+    if (N <= 0) return 0;
+    const size_t nn = (size_t)N * GECON_MODEL_N * GECON_MODEL_N * sizeof(double);
+    const size_t nd = (size_t)N * GECON_MODEL_N * GECON_MODEL_K * sizeof(double);
+    const size_t nt = (size_t)N * GECON_MODEL_NTHETA * sizeof(double);
+    const size_t nx = (size_t)N * GECON_MODEL_N * sizeof(double);
+    double *dth = nullptr, *dA = nullptr, *dB = nullptr, *dC = nullptr, *dD = nullptr, *dx = nullptr;
+    int32_t* ds = nullptr;
+    cudaError_t e = cudaSuccess;
+#define TRY(x) if (e == cudaSuccess) e = (x)
+    TRY(cudaMalloc(&dth, nt));
+    TRY(cudaMalloc(&dA, nn));
+    TRY(cudaMalloc(&dB, nn));
+    TRY(cudaMalloc(&dC, nn));
+    TRY(cudaMalloc(&dD, nd ? nd : 8));
+    TRY(cudaMalloc(&dx, nx));
+    TRY(cudaMalloc(&ds, (size_t)N * sizeof(int32_t)));
+    TRY(cudaMemcpy(dth, theta, nt, cudaMemcpyHostToDevice));
+    if (e == cudaSuccess) e = (cudaError_t)gecon_model_jacobian_batched(dth, N, dA, dB, dC, dD, dx, ds, nullptr);
+    TRY(cudaMemcpy(A, dA, nn, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(B, dB, nn, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(C, dC, nn, cudaMemcpyDeviceToHost));
+    if (nd) TRY(cudaMemcpy(D, dD, nd, cudaMemcpyDeviceToHost));
+    if (xss) TRY(cudaMemcpy(xss, dx, nx, cudaMemcpyDeviceToHost));
+    if (status) TRY(cudaMemcpy(status, ds, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+#undef TRY
+    cudaFree(dth); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dD); cudaFree(dx); cudaFree(ds);
+    return (int)e;
+}}
+#endif  // GECON_HOST_CHECK
+"""

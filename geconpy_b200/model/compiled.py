@@ -1,0 +1,281 @@
+"""A model spec compiled to a per-model CUDA library, and the batched likelihood pipeline built on it.
+
+``CompiledModel``      theta -> A, B, C, D (generated kernel; replaces the compiled pytensor function of
+                       gEconpy/model/model.py:1647-1664 / build.py:681-695).
+``BatchedStateSpace``  the estimation graph of ``DSGEStateSpace`` (gEconpy/model/statespace.py:725-820, 1139-1215)
+                       evaluated for a whole population of draws:  Jacobian -> cycle reduction -> R, residual ->
+                       Blanchard-Kahn count -> P0 -> Kalman log-likelihood -> gating, four kernel launches per chunk.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+from pathlib import Path
+
+import numpy as np
+
+from .. import _lib as L
+from ..build import build_model
+from .codegen import LinearizedModel, load_spec
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+SPEC_DIR = Path(__file__).resolve().parent / "specs"
+
+
+class CompiledModel:
+    def __init__(self, spec, log_linearize: bool = True, not_loglin_variables=(), force_build: bool = False):
+        if isinstance(spec, (str, Path)) and not Path(spec).exists():
+            spec = SPEC_DIR / f"{spec}.json"
+        self.lin = LinearizedModel(load_spec(spec), log_linearize=log_linearize, not_loglin_variables=tuple(not_loglin_variables))
+        self.name = self.lin.name
+        self.n, self.k, self.n_theta = self.lin.n, self.lin.k, self.lin.n_theta
+        self.source = self.lin.cuda_source()
+        self.lib_path = build_model(self.name, self.source, force=force_build)
+        try:
+            self._lib = C.CDLL(str(self.lib_path))
+        except OSError as e:
+            raise L.GeconLibraryError(f"cannot load {self.lib_path}: {e}") from e
+        self._jac_dev = self._lib.gecon_model_jacobian_batched
+        self._jac_dev.restype = C.c_int
+        self._jac_dev.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        self._jac_host = self._lib.gecon_model_jacobian_host
+        self._jac_host.restype = C.c_int
+        self._jac_host.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        n, k, nt = C.c_int32(), C.c_int32(), C.c_int32()
+        self.launches = 0  # kernel launches made through this model library (bench.py's gpu_launches)
+        self._lib.gecon_model_info(C.byref(n), C.byref(k), C.byref(nt))
+        assert (n.value, k.value, nt.value) == (self.n, self.k, self.n_theta)
+
+    # structure, in the reference's vocabulary
+    var_names = property(lambda self: self.lin.var_names)
+    shock_names = property(lambda self: self.lin.shock_names)
+    param_names = property(lambda self: self.lin.param_names)
+    var_order = property(lambda self: self.lin.var_order)
+    eq_order = property(lambda self: self.lin.eq_order)
+    inv_var_order = property(lambda self: self.lin.inv_var_order)
+    permuted_lead_var_idx = property(lambda self: self.lin.permuted_lead_var_idx)
+
+    def theta_vector(self, **updates) -> np.ndarray:
+        d = dict(self.lin.defaults)
+        unknown = set(updates) - set(d)
+        if unknown:
+            raise KeyError(f"unknown parameters {sorted(unknown)}")
+        d.update(updates)
+        return np.array([d[p] for p in self.param_names], dtype=np.float64)
+
+    def jacobian_device(self, theta, A, B, Cm, D, xss, status, stream) -> None:
+        """Launch on device pointers (torch tensors); nothing is allocated or copied."""
+        N = theta.shape[0]
+        rc = self._jac_dev(
+            theta.data_ptr(), N, A.data_ptr(), B.data_ptr(), Cm.data_ptr(), D.data_ptr(),
+            xss.data_ptr() if xss is not None else None, status.data_ptr() if status is not None else None, C.c_void_p(stream),
+        )  # fmt: skip
+        self.launches += 1
+        if rc != 0:
+            raise L.GeconLibraryError(f"gecon_model_jacobian_batched({self.name}) failed with CUDA error {rc}")
+
+    def jacobian(self, theta):
+        """theta[N, n_theta] (numpy, host path) -> A, B, C, D, xss, status in the reference's permuted solver order
+        (rows eq_order, columns var_order; gEconpy/model/perturbation.py:130-158)."""
+        L.require_device()
+        th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        if th.shape[1] != self.n_theta:
+            raise ValueError(f"theta has {th.shape[1]} columns, model {self.name} has {self.n_theta} free parameters")
+        N, n, k = th.shape[0], self.n, self.k
+        A, B, Cm = (np.empty((N, n, n)) for _ in range(3))
+        D = np.empty((N, n, k))
+        xss = np.empty((N, n))
+        st = np.empty(N, dtype=np.int32)
+        rc = self._jac_host(th.ctypes.data, N, A.ctypes.data, B.ctypes.data, Cm.ctypes.data, D.ctypes.data, xss.ctypes.data, st.ctypes.data)
+        if rc != 0:
+            raise L.GeconLibraryError(f"gecon_model_jacobian_host({self.name}) failed with CUDA error {rc}")
+        return A, B, Cm, D, xss, st
+
+
+GATE_MASK = L.ST_CR_NOT_CONVERGED | L.ST_CR_NAN | L.ST_SINGULAR | L.ST_RESID | L.ST_BK | L.ST_BK_INCONCLUSIVE | L.ST_JAC_NONFINITE
+
+
+class BatchedStateSpace:
+    """Population-batched equivalent of ``DSGEStateSpace.configure`` + ``build_statespace_graph`` + compiled logp.
+
+    Parameter vector per draw (the reference's parameter names, statespace.py:1093-1137):
+    ``[free parameters..., sigma_<shock>..., error_sigma_<state>...]``.
+    """
+
+    def __init__(self, model: CompiledModel):
+        self.model = model
+        self.configured = False
+
+    def configure(
+        self,
+        observed_states,
+        measurement_error=None,
+        solver: str = "cycle_reduction",
+        tol: float = 1e-8,
+        max_iter: int = 1000,
+        solver_tol: float = 1e-8,
+        cov_jitter: float = 1e-8,
+        missing_fill_value: float = -9999.0,
+        mvn_const: str = "per_obs",
+        check_bk: bool = True,
+        chunk: int = 65536,
+    ):
+        m = self.model
+        if solver not in ("cycle_reduction", "gensys"):
+            raise NotImplementedError(f"solver={solver!r}: the B200 path solves by cycle reduction (gensys maps to CR + BK flag)")
+        unknown = [v for v in observed_states if v not in m.var_names]
+        if unknown:
+            raise ValueError(f"unknown observed states {unknown}")
+        measurement_error = list(measurement_error or [])
+        bad = [v for v in measurement_error if v not in observed_states]
+        if bad:
+            raise ValueError(f"measurement error on unobserved states {bad}")
+        # stochastic-singularity guard (statespace.py:994-1005)
+        if len(observed_states) > m.k + len(measurement_error):
+            raise ValueError(
+                f"stochastic singularity: {len(observed_states)} observed states but only {m.k} shocks + "
+                f"{len(measurement_error)} measurement errors"
+            )
+        self.observed_states = list(observed_states)
+        self.measurement_error = measurement_error
+        self.p = len(observed_states)
+        # filter runs in solver order: observed variable -> permuted position (T, R are not un-permuted in between)
+        self.obs_idx = m.inv_var_order[[m.var_names.index(v) for v in observed_states]].astype(np.int32)
+        self.err_pos = np.array([observed_states.index(v) for v in measurement_error], dtype=np.int64)
+        self.tol, self.max_iter, self.solver_tol = float(tol), int(max_iter), float(solver_tol)
+        self.cov_jitter, self.missing_fill_value, self.mvn_const = float(cov_jitter), float(missing_fill_value), mvn_const
+        self.check_bk = bool(check_bk)
+        self.chunk = int(chunk)
+        self.param_names = (
+            list(m.param_names) + [f"sigma_{s}" for s in m.shock_names] + [f"error_sigma_{v}" for v in measurement_error]
+        )
+        self.n_param = len(self.param_names)
+        self.configured = True
+        self._ws = None
+        return self
+
+    # ------------------------------------------------------------------------------------------------ workspace
+    def _workspace(self, device, nc):
+        if self._ws is not None and self._ws["nc"] >= nc and self._ws["device"] == device:
+            return self._ws
+        m = self.model
+        f64 = dict(dtype=torch.float64, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        ws = dict(
+            nc=nc, device=device,
+            theta=torch.empty((nc, m.n_theta), **f64), sig=torch.empty((nc, m.k), **f64), herr=torch.zeros((nc, self.p), **f64),
+            A=torch.empty((nc, m.n, m.n), **f64), B=torch.empty((nc, m.n, m.n), **f64), C=torch.empty((nc, m.n, m.n), **f64),
+            D=torch.empty((nc, m.n, m.k), **f64), T=torch.empty((nc, m.n, m.n), **f64), R=torch.empty((nc, m.n, m.k), **f64),
+            status=torch.empty((nc,), **i32), n_iter=torch.empty((nc,), **i32), n_unstable=torch.empty((nc,), **i32),
+            resid=torch.empty((nc,), **f64),
+            lead=torch.as_tensor(m.permuted_lead_var_idx, **i32), obs=torch.as_tensor(self.obs_idx, **i32),
+        )  # fmt: skip
+        self._ws = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------------ evaluation
+    def loglik_device(self, theta_full, Y, out_ll=None, out_status=None, out_n_iter=None, events=None):
+        """theta_full: torch CUDA tensor [N, n_param]; Y: torch CUDA tensor [Tobs, p].  Returns (ll, status) on device.
+        Four kernel launches (+4 memsets) per chunk of draws, all on the current stream; no host synchronisation."""
+        if not self.configured:
+            raise RuntimeError("call configure(...) first")
+        if not (torch is not None and isinstance(theta_full, torch.Tensor) and theta_full.is_cuda):
+            raise TypeError("loglik_device needs CUDA tensors; use loglik() for host arrays")
+        m = self.model
+        lib = L.load_library()
+        dev = theta_full.device
+        N = theta_full.shape[0]
+        if theta_full.shape[1] != self.n_param:
+            raise ValueError(f"theta has {theta_full.shape[1]} columns, expected {self.n_param}: {self.param_names}")
+        Y = Y.to(torch.float64).contiguous().reshape(-1, self.p)
+        Tobs = Y.shape[0]
+        ll = out_ll if out_ll is not None else torch.empty((N,), dtype=torch.float64, device=dev)
+        status = out_status if out_status is not None else torch.empty((N,), dtype=torch.int32, device=dev)
+        nc = min(self.chunk, N)
+        ws = self._workspace(dev, nc)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        n_err = len(self.measurement_error)
+
+        def mark(name):
+            """bench.py hook: CUDA events on the launching stream around each kernel (per-kernel roofline)."""
+            if events is None:
+                return None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            events.append((name, e0, e1))
+            return e1
+
+        for lo in range(0, N, nc):
+            cnt = min(nc, N - lo)
+            th = theta_full[lo : lo + cnt]
+            # split the parameter vector (strided device copies; no arithmetic)
+            ws["theta"][:cnt].copy_(th[:, : m.n_theta])
+            ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
+            if n_err:
+                ws["herr"][:cnt, self.err_pos] = th[:, m.n_theta + m.k :]
+            st = ws["status"][:cnt]
+            e = mark("jacobian")
+            m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], None, st, stream)
+            e and e.record()
+            cr = L.CrArgs(
+                struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
+                D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
+                resid_tol=self.solver_tol, unperm=None, T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), status=st.data_ptr(),
+                n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
+            )  # fmt: skip
+            e = mark("cr_solve")
+            L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
+            e and e.record()
+            if self.check_bk:
+                bk = L.BkArgs(
+                    struct_size=C.sizeof(L.BkArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(), N=cnt,
+                    n=m.n, n_lead=int(ws["lead"].numel()), lead_idx=ws["lead"].data_ptr(), accumulate=1, max_iter=0,
+                    n_unstable=ws["n_unstable"].data_ptr(), status=st.data_ptr(),
+                )  # fmt: skip
+                e = mark("bk_count")
+                L.check(lib.gecon_bk_count_batched(C.byref(bk), C.c_void_p(stream)), "gecon_bk_count_batched")
+                e and e.record()
+            kf = L.KalmanArgs(
+                struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), qdiag=ws["sig"].data_ptr(),
+                q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p, Z=None,
+                obs_idx=ws["obs"].data_ptr(), d=None, d_stride=0, Y=Y.data_ptr(), P0=None, N=cnt, n=m.n, k=m.k, p=self.p,
+                Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
+                mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
+                gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),
+                ll_t=None,
+            )  # fmt: skip
+            e = mark("kalman_ll")
+            L.check(lib.gecon_kalman_ll_batched(C.byref(kf), C.c_void_p(stream)), "gecon_kalman_ll_batched")
+            e and e.record()
+            if out_n_iter is not None:
+                out_n_iter[lo : lo + cnt].copy_(ws["n_iter"][:cnt])
+        return ll, status
+
+    def loglik(self, theta_full, Y, device="cuda:0"):
+        """HOST arrays in, HOST arrays out (the end-to-end call a sampler makes): pinned staging, one H2D copy of the
+        parameter population, the kernels, one D2H copy of (ll, status)."""
+        L.require_device()
+        th = np.ascontiguousarray(np.atleast_2d(theta_full), dtype=np.float64)
+        dev = torch.device(device)
+        th_d = torch.from_numpy(th).pin_memory().to(dev, non_blocking=True)
+        Y_d = torch.as_tensor(np.ascontiguousarray(Y, dtype=np.float64).reshape(-1, self.p)).to(dev)
+        ll, st = self.loglik_device(th_d, Y_d)
+        return ll.cpu().numpy(), st.cpu().numpy()
+
+    def solve(self, theta, device="cuda:0"):
+        """theta[N, n_theta] -> dict(T, R, status, n_iter, resid, n_unstable) with T, R un-permuted to variable order
+        (statespace.py:217-220), host arrays."""
+        from .. import batched
+
+        A, B, Cm, D, _xss, st_j = self.model.jacobian(theta)
+        res = batched.cr_solve(
+            A, B, Cm, D, max_iter=self.max_iter if self.configured else 1000, tol=self.tol if self.configured else 1e-8,
+            resid_tol=self.solver_tol if self.configured else 1e-8, unperm=self.model.inv_var_order,
+        )  # fmt: skip
+        nu, st_b = batched.bk_count(A, B, Cm, self.model.permuted_lead_var_idx)
+        return dict(T=res.T, R=res.R, status=res.status | st_j | st_b, n_iter=res.n_iter, resid=res.resid, n_unstable=nu)

@@ -70,7 +70,7 @@ typedef struct gecon_cr_args {
     int32_t n;
     int32_t k;
     int32_t max_iter;
-    int32_t reserved0;
+    int32_t accumulate;     /* 0: status is overwritten, else new bits are OR-ed into the existing value */
     double tol;
     double resid_tol;       /* sets GECON_ST_RESID when resid >= resid_tol or NaN; <= 0 disables */
     const int32_t* unperm;  /* [n] or NULL: outputs are T[unperm][:, unperm], R[unperm] (statespace.py:217-220) */
@@ -165,7 +165,8 @@ typedef struct gecon_kalman_args {
     const int32_t* status_in; /* [N] or NULL */
     int32_t gate_mask;    /* draws with status_in & gate_mask get ll = -inf and are skipped (the reference's
                              pm.Potential(-inf) gates, statespace.py:1206-1215) */
-    int32_t reserved0;
+    int32_t sigma_inputs; /* 0: qdiag/hdiag hold variances; 1: they hold standard deviations (sigma_<shock>,
+                             error_sigma_<state>: statespace.py:255-258,800-810) and are squared in the kernel */
     double* ll;           /* [N] out */
     int32_t* status;      /* [N] out: status_in | new bits (may alias status_in) */
     double* ll_t;         /* [N][Tobs] out or NULL: per-observation log-likelihood */
