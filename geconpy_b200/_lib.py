@@ -70,6 +70,8 @@ class CrArgs(C.Structure):
         ("n_iter", C.c_void_p),
         ("resid", C.c_void_p),
         ("norms", C.c_void_p),
+        ("n_out", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 

@@ -102,13 +102,16 @@ class CycleReductionResult:
         return (self.status & L.ST_CR_NOT_CONVERGED) == 0
 
 
-def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None) -> CycleReductionResult:
+def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None, subset=None) -> CycleReductionResult:
     """Batched cycle reduction + R + residual (``gecon_cr_solve_*``).
 
     Reference: ``_cycle_reduction_core`` (gEconpy/solvers/cycle_reduction.py:127-183), ``pt_compute_selection_matrix``
     (solvers/shared.py:74-75), residual (model/statespace.py:213).  ``C_ = None`` solves the backward-looking system
-    (solvers/backward_looking.py).
+    (solvers/backward_looking.py).  ``unperm``: full permutation applied to the outputs (statespace.py:217-220);
+    ``subset``: index list, outputs are the sub-blocks ``T[subset][:, subset]``, ``R[subset]``.
     """
+    if unperm is not None and subset is not None:
+        raise ValueError("give at most one of unperm and subset")
     m = _marshal_for(A, B, C_, D)
     A, pA = m.inp(A)
     B, pB = m.inp(B)
@@ -119,16 +122,19 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     k = 0
     if D is not None:
         k = D.shape[-1]
-    T, pT = m.out((N, n, n))
-    R, pR = m.out((N, n, k)) if D is not None else (None, None)
+    n_out = 0 if subset is None else len(subset)
+    no = n_out or n
+    T, pT = m.out((N, no, no))
+    R, pR = m.out((N, no, k)) if D is not None else (None, None)
     status, pS = m.out((N,), np.int32)
     n_iter, pI = m.out((N,), np.int32)
     resid, pRes = m.out((N,))
     norms, pNo = m.out((N, 2))
-    _, pU = m.inp(unperm, np.int32)
+    gather = unperm if subset is None else subset
+    _, pU = m.inp(None if gather is None else np.ascontiguousarray(gather, dtype=np.int32), np.int32)
     args = L.CrArgs(
         struct_size=C.sizeof(L.CrArgs), A=pA, B=pB, C=pC, D=pD, N=N, n=n, k=k, max_iter=int(max_iter), tol=float(tol),
-        resid_tol=float(resid_tol), unperm=pU, T=pT, R=pR, status=pS, n_iter=pI, resid=pRes, norms=pNo,
+        resid_tol=float(resid_tol), unperm=pU, T=pT, R=pR, status=pS, n_iter=pI, resid=pRes, norms=pNo, n_out=n_out,
     )  # fmt: skip
     lib = L.load_library()
     if m.device:

@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
     int* s_i = s_perm + NP;
 
     const int n = p.n, k = p.k;
+    const int no = (p.unperm && p.n_out > 0) ? p.n_out : n;  // rows/cols written out (sub-block gather when < n)
     if (p.unperm) {
-        for (int i = threadIdx.x; i < n; i += C::NT) s_perm[i] = p.unperm[i];
+        for (int i = threadIdx.x; i < no; i += C::NT) s_perm[i] = p.unperm[i];
     }
     const int* perm = p.unperm ? s_perm : nullptr;
 
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
                 tile_nanfill<NP>(X2, n, k);
                 __syncthreads();
             }
-            tile_store<NP>(p.R + (size_t)draw * n * k, X2, n, k, k, -1.0, perm, nullptr);
+            tile_store<NP>(p.R + (size_t)draw * no * k, X2, no, k, k, -1.0, perm, nullptr);
         }
 
         // ---- residual sum((A + B T + (C T) T)^2) in solver order (statespace.py:213)
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
                 p.status[draw] = p.accumulate ? (p.status[draw] | status) : status;
             }
         }
-        tile_store<NP>(p.T + (size_t)draw * n * n, Tt, n, n, n, 1.0, perm, perm);
+        tile_store<NP>(p.T + (size_t)draw * no * no, Tt, no, no, no, 1.0, perm, perm);
         __syncthreads();
     }
 }
@@ -202,6 +203,10 @@ static int check_cr_args(const gecon_cr_args* a) {
     }
     if (!a->A || !a->B || !a->T || !a->status || a->N < 0 || a->n < 1 || a->k < 0 || (a->R && !a->D)) {
         set_last_error("gecon_cr_args: null pointer or bad dimension");
+        return GECON_E_BADARG;
+    }
+    if (a->n_out < 0 || a->n_out > a->n || (a->n_out > 0 && !a->unperm)) {
+        set_last_error("gecon_cr_args: n_out = %d needs 0 <= n_out <= n and an index list in unperm", a->n_out);
         return GECON_E_BADARG;
     }
     if (a->k > round_up8(a->n)) {
@@ -252,12 +257,14 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
     if (rc) return rc;
     if (args->N == 0) return 0;
     const size_t N = (size_t)args->N, n = args->n, k = args->k;
+    const size_t no = (args->unperm && args->n_out > 0) ? (size_t)args->n_out : n;
     const size_t bm = N * n * n * sizeof(double), bd = N * n * k * sizeof(double);
+    const size_t bmo = N * no * no * sizeof(double), bdo = N * no * k * sizeof(double);
     DevBuf dA, dB, dC, dD, dT, dR, dSt, dIt, dRes, dNo, dPerm;
     gecon_cr_args d = *args;
     GECON_CUDA(dA.alloc(bm));
     GECON_CUDA(dB.alloc(bm));
-    GECON_CUDA(dT.alloc(bm));
+    GECON_CUDA(dT.alloc(bmo));
     GECON_CUDA(dSt.alloc(N * sizeof(int32_t)));
     GECON_CUDA(cudaMemcpy(dA.p, args->A, bm, cudaMemcpyHostToDevice));
     GECON_CUDA(cudaMemcpy(dB.p, args->B, bm, cudaMemcpyHostToDevice));
@@ -277,7 +284,7 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
         d.D = dD.as<double>();
     }
     if (args->R) {
-        GECON_CUDA(dR.alloc(bd));
+        GECON_CUDA(dR.alloc(bdo));
         d.R = dR.as<double>();
     }
     if (args->n_iter) {
@@ -293,14 +300,14 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
         d.norms = dNo.as<double>();
     }
     if (args->unperm) {
-        GECON_CUDA(dPerm.alloc(n * sizeof(int32_t)));
-        GECON_CUDA(cudaMemcpy(dPerm.p, args->unperm, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        GECON_CUDA(dPerm.alloc(no * sizeof(int32_t)));
+        GECON_CUDA(cudaMemcpy(dPerm.p, args->unperm, no * sizeof(int32_t), cudaMemcpyHostToDevice));
         d.unperm = dPerm.as<int32_t>();
     }
     rc = gecon_cr_solve_batched(&d, nullptr);
     if (rc) return rc;
-    GECON_CUDA(cudaMemcpy(args->T, d.T, bm, cudaMemcpyDeviceToHost));
-    if (args->R) GECON_CUDA(cudaMemcpy(args->R, d.R, bd, cudaMemcpyDeviceToHost));
+    GECON_CUDA(cudaMemcpy(args->T, d.T, bmo, cudaMemcpyDeviceToHost));
+    if (args->R) GECON_CUDA(cudaMemcpy(args->R, d.R, bdo, cudaMemcpyDeviceToHost));
     GECON_CUDA(cudaMemcpy(args->status, d.status, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (args->n_iter) GECON_CUDA(cudaMemcpy(args->n_iter, d.n_iter, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (args->resid) GECON_CUDA(cudaMemcpy(args->resid, d.resid, N * sizeof(double), cudaMemcpyDeviceToHost));

@@ -458,8 +458,8 @@ static int check_kf_args(const gecon_kalman_args* a) {
         set_last_error("gecon_kalman_args: null pointer or bad dimension");
         return GECON_E_BADARG;
     }
-    if (a->p > PMAX || a->p > a->n || a->k > round_up8(a->n)) {
-        set_last_error("gecon_kalman_args: unsupported p = %d (max %d) or k = %d", a->p, PMAX, a->k);
+    if (a->p > PMAX || a->p > a->n) {
+        set_last_error("gecon_kalman_args: unsupported p = %d (max %d, and p <= n)", a->p, PMAX);
         return GECON_E_UNSUPPORTED_SIZE;
     }
     return 0;
@@ -525,19 +525,19 @@ extern "C" int gecon_kalman_ll_batched(const gecon_kalman_args* args, void* stre
     int rc = check_kf_args(args);
     if (rc) return rc;
     if (args->N == 0) return 0;
-    const int np = round_up8(args->n);
+    const int np = round_up8(args->n > args->k ? args->n : args->k);  // the R staging tile needs k columns
     GECON_DISPATCH_NP(np, return launch_kf<NP_>(*args, (cudaStream_t)stream));
     return 0;
 }
 
 extern "C" int gecon_dlyap_batched(const gecon_dlyap_args* a, void* stream) {
     if (!a || a->struct_size != sizeof(gecon_dlyap_args) || !a->T || !a->R || !a->qdiag || !a->P || !a->status || a->N < 0 ||
-        a->n < 1 || a->k < 0 || a->k > round_up8(a->n)) {
+        a->n < 1 || a->k < 0) {
         set_last_error("gecon_dlyap_args: bad argument");
         return GECON_E_BADARG;
     }
     if (a->N == 0) return 0;
-    const int np = round_up8(a->n);
+    const int np = round_up8(a->n > a->k ? a->n : a->k);
     GECON_DISPATCH_NP(np, return launch_lyap<NP_>(*a, (cudaStream_t)stream));
     return 0;
 }

@@ -124,6 +124,7 @@ class BatchedStateSpace:
         mvn_const: str = "per_obs",
         check_bk: bool = True,
         chunk: int = 65536,
+        reduce_state: bool = True,
     ):
         m = self.model
         if solver not in ("cycle_reduction", "gensys"):
@@ -147,6 +148,14 @@ class BatchedStateSpace:
         # filter runs in solver order: observed variable -> permuted position (T, R are not un-permuted in between)
         self.obs_idx = m.inv_var_order[[m.var_names.index(v) for v in observed_states]].astype(np.int32)
         self.err_pos = np.array([observed_states.index(v) for v in measurement_error], dtype=np.int64)
+        # The likelihood only depends on the lagged (state) variables and the observed variables: every other column of
+        # T is identically zero, so those variables never feed back into the recursion.  With reduce_state the solver
+        # kernel hands the filter the exact sub-blocks T[U][:, U], R[U] for U = states + observed (solver order).
+        state_pos = m.inv_var_order[m.lin.state_var_idx]
+        self.filter_vars = np.array(sorted(set(state_pos.tolist()) | set(self.obs_idx.tolist())), dtype=np.int32) if reduce_state else np.arange(m.n, dtype=np.int32)
+        self.n_filter = int(self.filter_vars.size)
+        self.obs_idx_filter = np.array([int(np.flatnonzero(self.filter_vars == o)[0]) for o in self.obs_idx], dtype=np.int32)
+        self.reduce_state = bool(reduce_state)
         self.tol, self.max_iter, self.solver_tol = float(tol), int(max_iter), float(solver_tol)
         self.cov_jitter, self.missing_fill_value, self.mvn_const = float(cov_jitter), float(missing_fill_value), mvn_const
         self.check_bk = bool(check_bk)
@@ -170,10 +179,11 @@ class BatchedStateSpace:
             nc=nc, device=device,
             theta=torch.empty((nc, m.n_theta), **f64), sig=torch.empty((nc, m.k), **f64), herr=torch.zeros((nc, self.p), **f64),
             A=torch.empty((nc, m.n, m.n), **f64), B=torch.empty((nc, m.n, m.n), **f64), C=torch.empty((nc, m.n, m.n), **f64),
-            D=torch.empty((nc, m.n, m.k), **f64), T=torch.empty((nc, m.n, m.n), **f64), R=torch.empty((nc, m.n, m.k), **f64),
+            D=torch.empty((nc, m.n, m.k), **f64), T=torch.empty((nc, self.n_filter, self.n_filter), **f64),
+            R=torch.empty((nc, self.n_filter, m.k), **f64), subset=torch.as_tensor(self.filter_vars, **i32),
             status=torch.empty((nc,), **i32), n_iter=torch.empty((nc,), **i32), n_unstable=torch.empty((nc,), **i32),
             resid=torch.empty((nc,), **f64),
-            lead=torch.as_tensor(m.permuted_lead_var_idx, **i32), obs=torch.as_tensor(self.obs_idx, **i32),
+            lead=torch.as_tensor(m.permuted_lead_var_idx, **i32), obs=torch.as_tensor(self.obs_idx_filter, **i32),
         )  # fmt: skip
         self._ws = ws
         return ws
@@ -225,8 +235,9 @@ class BatchedStateSpace:
             cr = L.CrArgs(
                 struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
                 D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
-                resid_tol=self.solver_tol, unperm=None, T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), status=st.data_ptr(),
-                n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
+                resid_tol=self.solver_tol, unperm=ws["subset"].data_ptr(), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
+                status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
+                n_out=self.n_filter,
             )  # fmt: skip
             e = mark("cr_solve")
             L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
@@ -243,7 +254,7 @@ class BatchedStateSpace:
             kf = L.KalmanArgs(
                 struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), qdiag=ws["sig"].data_ptr(),
                 q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p, Z=None,
-                obs_idx=ws["obs"].data_ptr(), d=None, d_stride=0, Y=Y.data_ptr(), P0=None, N=cnt, n=m.n, k=m.k, p=self.p,
+                obs_idx=ws["obs"].data_ptr(), d=None, d_stride=0, Y=Y.data_ptr(), P0=None, N=cnt, n=self.n_filter, k=m.k, p=self.p,
                 Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
                 mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
                 gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),

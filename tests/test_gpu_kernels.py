@@ -93,7 +93,7 @@ def test_cycle_reduction_unpermute_and_flags(B):
     raw = B.cr_solve(A, Bm, C, D)
     for i in range(4):
         T, R = mod.unpermute_policy(raw.T[i], raw.R[i])
-        assert np.array_equal(res.T[i], T) and np.array_equal(res.R[i], R)
+        assert np.array_equal(res.T[i], T, equal_nan=True) and np.array_equal(res.R[i], R, equal_nan=True)
     # max_iter exhausted -> not converged, T = 0 (cycle_reduction.py:181-183)
     short = B.cr_solve(A, Bm, C, D, max_iter=3)
     assert not short.converged.any()
@@ -102,7 +102,11 @@ def test_cycle_reduction_unpermute_and_flags(B):
     for i in range(4):
         T, conv, n_iter = osol.cycle_reduction_core(A[i], Bm[i], C[i], max_iter=3, tol=1e-9)
         assert not conv and n_iter == 3
-        assert rel_fro(short.R[i], osol.selection_matrix(Bm[i], C[i], D[i], T)) <= TOL_TR
+        Rref = osol.selection_matrix(Bm[i], C[i], D[i], T)
+        if np.isfinite(Rref).all():
+            assert rel_fro(short.R[i], Rref) <= TOL_TR
+        else:
+            assert np.isnan(short.R[i]).all()
 
 
 def test_backward_looking(B, rng):

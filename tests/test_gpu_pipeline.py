@@ -1,0 +1,118 @@
+"""GPU parity of the generated Jacobian kernels and of the whole theta -> log-likelihood pipeline against the oracle."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from helpers import SIGMA_ERR, SIGMA_SHOCK, draws, jacobian_batch, model, simulate_obs
+from oracle import statespace as oss
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ["rbc", "one_block_1_ss", "rbc_extended", "open_rbc", "full_nk", "new_keynesian", "nk_complete_more_shocks", "rbc_linearized"]
+
+
+@pytest.fixture(scope="module")
+def compiled():
+    from geconpy_b200.model.compiled import CompiledModel
+
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = CompiledModel(name)
+        return cache[name]
+
+    return get
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_generated_jacobian_matches_oracle(compiled, name):
+    """Same entries, orderings and log-linear scaling as linearize_model (perturbation.py:97-198); 1e-10 like the
+    reference's own sympy cross-check (tests/model/test_perturbation.py:95-160)."""
+    cm, mod = compiled(name), model(name)
+    assert list(cm.var_names) == mod.var_names and list(cm.param_names) == mod.param_names
+    assert np.array_equal(cm.var_order, mod.var_order) and np.array_equal(cm.eq_order, mod.eq_order)
+    assert np.array_equal(cm.permuted_lead_var_idx, mod.permuted_lead_var_idx)
+    th = draws(mod, 32, seed=21, width=0.05)
+    A, B, C, D, xss, st = cm.jacobian(th)
+    Ao, Bo, Co, Do = jacobian_batch(mod, th)
+    for i in range(len(th)):
+        fin = all(np.isfinite(M[i]).all() for M in (Ao, Bo, Co, Do))
+        assert (st[i] == 0) == fin, (name, i)
+        if not fin:
+            continue
+        np.testing.assert_allclose(xss[i], mod.steady_state(th[i]), rtol=1e-12, atol=1e-14)
+        for G, O in ((A, Ao), (B, Bo), (C, Co), (D, Do)):
+            np.testing.assert_allclose(G[i], O[i], rtol=1e-10, atol=1e-10)
+
+
+def _configure(compiled, name, reduce_state=True, with_err=True):
+    from geconpy_b200.model.compiled import BatchedStateSpace
+
+    cm, mod = compiled(name), model(name)
+    observed = mod.spec["observed_default"]
+    meas = observed if with_err else []
+    ss = BatchedStateSpace(cm).configure(observed_states=observed, measurement_error=meas, tol=1e-9, max_iter=200, reduce_state=reduce_state)
+    return cm, mod, ss, observed, meas
+
+
+@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc_extended", 80), ("full_nk", 200), ("nk_complete_more_shocks", 60)])
+@pytest.mark.parametrize("reduce_state", [True, False])
+def test_pipeline_loglik_matches_oracle(compiled, name, Tobs, reduce_state):
+    """North-star tolerances: flags exact, |ll - oracle| <= 1e-7, failures gated to -inf on both sides."""
+    with_err = name != "rbc"
+    cm, mod, ss, observed, meas = _configure(compiled, name, reduce_state, with_err)
+    th = draws(mod, 24, seed=31, width=0.03)
+    Y = simulate_obs(mod, Tobs, seed=3, sigma_err=SIGMA_ERR if with_err else 0.0)
+    sig = np.full((len(th), mod.k), SIGMA_SHOCK)
+    err = np.full((len(th), len(meas)), SIGMA_ERR)
+    ll, st = ss.loglik(np.hstack([th, sig, err]), Y)
+    n_ok = 0
+    for i in range(len(th)):
+        ref = oss.loglik(mod, th[i], Y, observed, sig[i], err[i] if with_err else None, tol=1e-9, max_iter=200)
+        if ref["ok"] and np.isfinite(ref["ll"]):
+            n_ok += 1
+            assert st[i] == 0, (name, i, st[i])
+            assert abs(ll[i] - ref["ll"]) <= 1e-7, (name, i, ll[i], ref["ll"])
+        else:
+            assert np.isneginf(ll[i]) and st[i] != 0, (name, i, ll[i], st[i])
+    assert n_ok >= len(th) // 3
+
+
+def test_pipeline_reports_failures(compiled):
+    """Invalid draws (beta > 1: NaN steady state; unit-root shocks: BK violated) are flagged, gated and counted."""
+    from geconpy_b200 import _lib as L
+
+    cm, mod, ss, observed, meas = _configure(compiled, "full_nk")
+    th = np.tile(mod.theta_vector(), (4, 1))
+    th[1, mod.param_names.index("beta")] = 1.05
+    th[2, mod.param_names.index("rho_technology")] = 1.08
+    Y = simulate_obs(mod, 40, seed=4, sigma_err=SIGMA_ERR)
+    full = np.hstack([th, np.full((4, mod.k), SIGMA_SHOCK), np.full((4, len(meas)), SIGMA_ERR)])
+    ll, st = ss.loglik(full, Y)
+    assert st[0] == 0 and st[3] == 0 and np.isfinite(ll[0]) and ll[0] == ll[3]
+    assert st[1] & L.ST_JAC_NONFINITE and np.isneginf(ll[1])
+    assert st[2] & L.ST_BK and np.isneginf(ll[2])
+    for i in (1, 2):
+        ref = oss.loglik(mod, th[i], Y, observed, np.full(mod.k, SIGMA_SHOCK), np.full(len(meas), SIGMA_ERR), tol=1e-9, max_iter=200)
+        assert not ref["ok"] or not np.isfinite(ref["ll"])
+
+
+def test_pipeline_device_path_and_chunking(compiled):
+    import torch
+
+    from geconpy_b200.model.compiled import BatchedStateSpace
+
+    cm, mod = compiled("rbc"), model("rbc")
+    ss = BatchedStateSpace(cm).configure(observed_states=["Y"], chunk=16)
+    th = draws(mod, 50, seed=5, width=0.02)
+    full = np.hstack([th, np.full((50, 1), SIGMA_SHOCK)])
+    Y = simulate_obs(mod, 30, seed=5)
+    ll_h, st_h = ss.loglik(full, Y)
+    ll_d, st_d = ss.loglik_device(torch.as_tensor(full, device="cuda"), torch.as_tensor(Y, device="cuda"))
+    assert np.array_equal(ll_d.cpu().numpy(), ll_h) and np.array_equal(st_d.cpu().numpy(), st_h)
+    big = BatchedStateSpace(cm).configure(observed_states=["Y"], chunk=65536)
+    ll_b, _ = big.loglik(full, Y)
+    assert np.array_equal(ll_b, ll_h)
