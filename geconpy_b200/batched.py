@@ -129,7 +129,7 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     status, pS = m.out((N,), np.int32)
     n_iter, pI = m.out((N,), np.int32)
     resid, pRes = m.out((N,))
-    norms, pNo = m.out((N, 2))
+    norms, pNo = m.out((N, 3))
     gather = unperm if subset is None else subset
     _, pU = m.inp(None if gather is None else np.ascontiguousarray(gather, dtype=np.int32), np.int32)
     args = L.CrArgs(

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
         int status = 0;
         bool converged = false;
         int it = 0;
-        double a0n = 0.0, a2n = 0.0;
+        double a0n = 0.0, a2n = 0.0, a1n = 0.0;
 
         if (gC) {
             while (it < p.max_iter) {
@@ -123,7 +123,13 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
                     break;
                 }
             }
-            if (!converged) status |= GECON_ST_CR_NOT_CONVERGED;
+            if (!converged) {
+                status |= GECON_ST_CR_NOT_CONVERGED;
+                if (p.norms) {  // diagnostics of the numpy twin's failure tuple (cycle_reduction.py:101-109)
+                    a2n = norm1<NP>(A2, n, s_red);
+                    a1n = norm1<NP>(A1, n, s_red);
+                }
+            }
         }
 
         // ---- T = -A1hat^-1 A (cycle_reduction.py:181), or T = -B^-1 A for backward-looking models; 0 if not converged
@@ -184,8 +190,9 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
                 if (p.resid) p.resid[draw] = resid;
                 if (p.n_iter) p.n_iter[draw] = it;
                 if (p.norms) {
-                    p.norms[2 * draw] = a0n;
-                    p.norms[2 * draw + 1] = a2n;
+                    p.norms[3 * draw] = a0n;
+                    p.norms[3 * draw + 1] = a2n;
+                    p.norms[3 * draw + 2] = a1n;
                 }
                 p.status[draw] = p.accumulate ? (p.status[draw] | status) : status;
             }
@@ -296,7 +303,7 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
         d.resid = dRes.as<double>();
     }
     if (args->norms) {
-        GECON_CUDA(dNo.alloc(2 * N * sizeof(double)));
+        GECON_CUDA(dNo.alloc(3 * N * sizeof(double)));
         d.norms = dNo.as<double>();
     }
     if (args->unperm) {
@@ -311,6 +318,6 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
     GECON_CUDA(cudaMemcpy(args->status, d.status, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (args->n_iter) GECON_CUDA(cudaMemcpy(args->n_iter, d.n_iter, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (args->resid) GECON_CUDA(cudaMemcpy(args->resid, d.resid, N * sizeof(double), cudaMemcpyDeviceToHost));
-    if (args->norms) GECON_CUDA(cudaMemcpy(args->norms, d.norms, 2 * N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (args->norms) GECON_CUDA(cudaMemcpy(args->norms, d.norms, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }

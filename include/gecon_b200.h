@@ -79,7 +79,8 @@ typedef struct gecon_cr_args {
     int32_t* status;        /* [N] out (overwritten) */
     int32_t* n_iter;        /* [N] out or NULL: iterations executed */
     double* resid;          /* [N] out or NULL */
-    double* norms;          /* [N][2] out or NULL: final ||A0||_1, ||A2||_1 */
+    double* norms;          /* [N][3] out or NULL: final ||A0||_1, ||A2||_1, ||A1||_1 (the last two are always
+                               evaluated when the iteration did not converge) */
     int32_t n_out;          /* 0: outputs are n x n / n x k.  > 0 (needs unperm): unperm has n_out <= n entries and the
                                outputs are the SUB-BLOCKS T[unperm][:, unperm] (n_out x n_out), R[unperm] (n_out x k).
                                Used to hand the Kalman kernel only the variables the likelihood depends on (lagged

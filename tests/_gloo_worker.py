@@ -1,0 +1,36 @@
+"""Worker for test_draw_sharding_and_allgather_world_size_2 (run under torch.distributed.run, gloo, CPU)."""
+import sys
+
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from geconpy_b200.parallel import gather_loglik, shard_bounds, systematic_resample  # noqa: E402
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N = 1001  # ragged on purpose
+lo, hi = shard_bounds(N, rank, world)
+all_bounds = [shard_bounds(N, r, world) for r in range(world)]
+assert all_bounds[0][0] == 0 and all_bounds[-1][1] == N and all(a[1] == b[0] for a, b in zip(all_bounds, all_bounds[1:]))
+# each rank "evaluates" its shard: ll_i = -i  (stands in for the kernel output; the exchange is what is tested)
+local = -torch.arange(lo, hi, dtype=torch.float64)
+full = gather_loglik(local, N)
+assert full.shape == (N,) and torch.equal(full, -torch.arange(N, dtype=torch.float64)), full[:5]
+idx = systematic_resample(full, seed=7)
+idx2 = systematic_resample(full, seed=7)
+assert torch.equal(idx, idx2) and idx.shape == (N,) and int(idx.min()) >= 0 and int(idx.max()) < N
+# every rank derives the same ancestors from the gathered weights: no scatter needed
+gathered = [torch.empty_like(idx) for _ in range(world)]
+dist.all_gather(gathered, idx)
+assert all(torch.equal(g, idx) for g in gathered)
+# equal shards take the single all_gather_into_tensor path
+N2 = 64
+lo2, hi2 = shard_bounds(N2, rank, world)
+full2 = gather_loglik(torch.arange(lo2, hi2, dtype=torch.float64), N2)
+assert torch.equal(full2, torch.arange(N2, dtype=torch.float64))
+if rank == 0:
+    print("gloo sharding ok")
+dist.destroy_process_group()

@@ -98,10 +98,9 @@ def test_cycle_reduction_unpermute_and_flags(B):
     short = B.cr_solve(A, Bm, C, D, max_iter=3)
     assert not short.converged.any()
     assert (short.T == 0).all()
-    assert (short.n_iter == 3).all()
     for i in range(4):
         T, conv, n_iter = osol.cycle_reduction_core(A[i], Bm[i], C[i], max_iter=3, tol=1e-9)
-        assert not conv and n_iter == 3
+        assert not conv and n_iter == int(short.n_iter[i])  # 3, or 1 for a draw whose Jacobian is NaN
         Rref = osol.selection_matrix(Bm[i], C[i], D[i], T)
         if np.isfinite(Rref).all():
             assert rel_fro(short.R[i], Rref) <= TOL_TR
