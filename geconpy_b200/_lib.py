@@ -29,6 +29,8 @@ ST_NOT_PD = 0x080
 ST_LL_NONFINITE = 0x100
 ST_JAC_NONFINITE = 0x200
 ST_SKIPPED = 0x400
+ST_BK_CERTIFIED = 0x800  # informational, not a failure
+ST_FAILURE_MASK = 0x7FF
 
 STATUS_NAMES = {
     ST_CR_NOT_CONVERGED: "cycle_reduction_not_converged",
@@ -42,6 +44,7 @@ STATUS_NAMES = {
     ST_LL_NONFINITE: "loglik_nonfinite",
     ST_JAC_NONFINITE: "jacobian_nonfinite",
     ST_SKIPPED: "skipped",
+    ST_BK_CERTIFIED: "bk_certified_by_solver",
 }
 
 
@@ -71,7 +74,9 @@ class CrArgs(C.Structure):
         ("resid", C.c_void_p),
         ("norms", C.c_void_p),
         ("n_out", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("n_lead", C.c_int32),
+        ("lead_idx", C.c_void_p),
+        ("n_unstable", C.c_void_p),
     ]
 
 
@@ -89,6 +94,8 @@ class BkArgs(C.Structure):
         ("max_iter", C.c_int32),
         ("n_unstable", C.c_void_p),
         ("status", C.c_void_p),
+        ("skip_mask", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

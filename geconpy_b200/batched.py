@@ -96,19 +96,22 @@ class CycleReductionResult:
     n_iter: object
     resid: object
     norms: object
+    n_unstable: object = None
 
     @property
     def converged(self):
         return (self.status & L.ST_CR_NOT_CONVERGED) == 0
 
 
-def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None, subset=None) -> CycleReductionResult:
+def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None, subset=None, lead_idx=None) -> CycleReductionResult:
     """Batched cycle reduction + R + residual (``gecon_cr_solve_*``).
 
     Reference: ``_cycle_reduction_core`` (gEconpy/solvers/cycle_reduction.py:127-183), ``pt_compute_selection_matrix``
     (solvers/shared.py:74-75), residual (model/statespace.py:213).  ``C_ = None`` solves the backward-looking system
     (solvers/backward_looking.py).  ``unperm``: full permutation applied to the outputs (statespace.py:217-220);
     ``subset``: index list, outputs are the sub-blocks ``T[subset][:, subset]``, ``R[subset]``.
+    ``lead_idx``: lead-variable columns; converged draws then carry ``ST_BK_CERTIFIED`` in ``status`` when the kernel
+    could prove n_unstable == n_forward (``result.n_unstable`` = n_lead for those draws, -1 otherwise).
     """
     if unperm is not None and subset is not None:
         raise ValueError("give at most one of unperm and subset")
@@ -132,9 +135,13 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     norms, pNo = m.out((N, 3))
     gather = unperm if subset is None else subset
     _, pU = m.inp(None if gather is None else np.ascontiguousarray(gather, dtype=np.int32), np.int32)
+    lead = None if lead_idx is None else np.ascontiguousarray(lead_idx, dtype=np.int32)
+    _, pL = m.inp(lead, np.int32)
+    nu, pNu = m.out((N,), np.int32) if lead is not None else (None, None)
     args = L.CrArgs(
         struct_size=C.sizeof(L.CrArgs), A=pA, B=pB, C=pC, D=pD, N=N, n=n, k=k, max_iter=int(max_iter), tol=float(tol),
         resid_tol=float(resid_tol), unperm=pU, T=pT, R=pR, status=pS, n_iter=pI, resid=pRes, norms=pNo, n_out=n_out,
+        n_lead=(0 if lead is None else int(lead.size)), lead_idx=pL, n_unstable=pNu,
     )  # fmt: skip
     lib = L.load_library()
     if m.device:
@@ -142,11 +149,11 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     else:
         L.check(lib.gecon_cr_solve_host(C.byref(args)), "gecon_cr_solve_host")
     if squeeze:
-        return CycleReductionResult(T[0], None if R is None else R[0], status[0], n_iter[0], resid[0], norms[0])
-    return CycleReductionResult(T, R, status, n_iter, resid, norms)
+        return CycleReductionResult(T[0], None if R is None else R[0], status[0], n_iter[0], resid[0], norms[0], None if nu is None else nu[0])
+    return CycleReductionResult(T, R, status, n_iter, resid, norms, nu)
 
 
-def bk_count(A, B, C_, lead_idx, status=None, max_iter=0):
+def bk_count(A, B, C_, lead_idx, status=None, max_iter=0, skip_mask=0, n_unstable=None):
     """Batched Blanchard-Kahn count (``gecon_bk_count_*``): returns (n_unstable[N], status[N]).
 
     Reference: ``check_bk_condition_pt`` (gEconpy/model/perturbation.py:586-625).
@@ -159,7 +166,7 @@ def bk_count(A, B, C_, lead_idx, status=None, max_iter=0):
     N, n = A.shape[0], A.shape[1]
     lead = np.ascontiguousarray(lead_idx, dtype=np.int32)
     _, pL = m.inp(lead, np.int32)
-    nu, pNu = m.out((N,), np.int32)
+    nu, pNu = m.out((N,), np.int32) if n_unstable is None else m.inp(n_unstable, np.int32)
     if status is None:
         st, pS = m.out((N,), np.int32)
         acc = 0
@@ -168,7 +175,7 @@ def bk_count(A, B, C_, lead_idx, status=None, max_iter=0):
         acc = 1
     args = L.BkArgs(
         struct_size=C.sizeof(L.BkArgs), A=pA, B=pB, C=pC, N=N, n=n, n_lead=int(lead.size), lead_idx=pL, accumulate=acc,
-        max_iter=int(max_iter), n_unstable=pNu, status=pS,
+        max_iter=int(max_iter), n_unstable=pNu, status=pS, skip_mask=int(skip_mask),
     )  # fmt: skip
     lib = L.load_library()
     if m.device:

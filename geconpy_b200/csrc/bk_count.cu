@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) bk_count_kernel(const gecon_bk_ar
     __syncthreads();
 
     for (long long draw = blockIdx.x; draw < p.N; draw += gridDim.x) {
+        if (p.accumulate && (p.status[draw] & p.skip_mask)) continue;  // uniform: already decided upstream
         const double* gA = p.A + (size_t)draw * n * n;
         const double* gB = p.B + (size_t)draw * n * n;
         const double* gC = p.C + (size_t)draw * n * n;

@@ -25,12 +25,13 @@ __device__ __forceinline__ void acc_sub(Acc<NP>& a, const Acc<NP>& b) {
 template <int NP>
 struct CrSmem {
     static constexpr int TILES = 7;
-    static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (2 * NP + 4);
+    static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (3 * NP + 4);
 };
 
 template <int NP>
 __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_args p) {
     using C = Cfg<NP>;
+    constexpr int LD = C::LD;
     extern __shared__ __align__(16) double sm[];
     double* A0 = sm;
     double* A1 = A0 + C::TILE;
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
     double* s_red = s_inv + NP;
     int* s_piv = reinterpret_cast<int*>(s_red + NP);
     int* s_perm = s_piv + NP;
-    int* s_i = s_perm + NP;
+    int* s_lead = s_perm + NP;
+    int* s_i = s_lead + NP;
 
     const int n = p.n, k = p.k;
     const int no = (p.unperm && p.n_out > 0) ? p.n_out : n;  // rows/cols written out (sub-block gather when < n)
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
         for (int i = threadIdx.x; i < no; i += C::NT) s_perm[i] = p.unperm[i];
     }
     const int* perm = p.unperm ? s_perm : nullptr;
+    const int nl = p.lead_idx ? p.n_lead : 0;
+    for (int i = threadIdx.x; i < nl; i += C::NT) s_lead[i] = p.lead_idx[i];
 
     for (long long draw = blockIdx.x; draw < p.N; draw += gridDim.x) {
         const double* gA = p.A + (size_t)draw * n * n;
@@ -162,17 +166,23 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
             acc_store<NP>(ct, A0);
         }
         __syncthreads();
-        if (gD && p.R) {
+        // One solve with W for both right-hand sides: D (-> R) and, for the Blanchard-Kahn certificate, the non-zero
+        // columns of C (-> W^-1 C = -F, left in the A2 tile).
+        const bool want_cert = p.lead_idx && gC && converged && !(status & GECON_ST_SINGULAR);
+        bool have_F = false;
+        if ((gD && p.R) || want_cert) {
             for (int i = threadIdx.x; i < C::TILE; i += C::NT) W[i] = A1[i] + A0[i];
-            tile_load<NP>(X2, gD, n, k, k);
+            const int kd = (gD && p.R) ? k : 0;
+            if (kd) tile_load<NP>(X2, gD, n, k, k);
             __syncthreads();
-            const bool ok = gj_solve<NP>(W, X2, 0, k, nullptr, 0, 0, n, s_piv, s_inv);
+            const bool ok = gj_solve<NP>(W, X2, 0, kd, A2, want_cert ? lo2 : 0, want_cert ? hi2 : 0, n, s_piv, s_inv);
             if (!ok) {
                 status |= GECON_ST_SINGULAR;
-                tile_nanfill<NP>(X2, n, k);
+                if (kd) tile_nanfill<NP>(X2, n, k);
                 __syncthreads();
             }
-            tile_store<NP>(p.R + (size_t)draw * no * k, X2, no, k, k, -1.0, perm, nullptr);
+            have_F = ok && want_cert;
+            if (kd) tile_store<NP>(p.R + (size_t)draw * no * k, X2, no, k, k, -1.0, perm, nullptr);
         }
 
         // ---- residual sum((A + B T + (C T) T)^2) in solver order (statespace.py:213)
@@ -199,6 +209,68 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
         }
         tile_store<NP>(p.T + (size_t)draw * no * no, Tt, no, no, no, 1.0, perm, perm);
         __syncthreads();
+
+        // ---- Blanchard-Kahn certificate (see gecon_cr_args.lead_idx): rho(T) < 1 and rho(F_LL) < 1 by repeated squaring.
+        // Z1 = the lag-column block of T (its other columns are zero), Z2 = (W^-1 C)[lead][:, lead]; ping-pong tiles.
+        if (p.lead_idx) {
+            bool certified = false;
+            if (have_F) {
+                const int s1 = hi0 - lo0;
+                double* Z1 = W;
+                double* Z1b = A1;
+                double* Z2 = A0;
+                double* Z2b = A1h;
+                tile_zero<NP>(Z1);
+                tile_zero<NP>(Z2);
+                __syncthreads();
+                for (int idx = threadIdx.x; idx < s1 * s1; idx += C::NT) {
+                    const int a = idx / s1, b = idx - a * s1;
+                    Z1[a * LD + b] = Tt[(lo0 + a) * LD + lo0 + b];
+                }
+                for (int idx = threadIdx.x; idx < nl * nl; idx += C::NT) {
+                    const int a = idx / nl, b = idx - a * nl;
+                    Z2[a * LD + b] = A2[s_lead[a] * LD + s_lead[b]];
+                }
+                __syncthreads();
+                const int k1 = (s1 + 3) & ~3, c1 = (s1 + 7) >> 3, k2 = (nl + 3) & ~3, c2 = (nl + 7) >> 3;
+                bool ok1 = (s1 == 0), ok2 = (nl == 0);
+                for (int sq = 0; sq <= 14; ++sq) {
+                    const double n1 = ok1 ? 0.0 : norm1<NP>(Z1, s1, s_red);
+                    const double n2 = ok2 ? 0.0 : norm1<NP>(Z2, nl, s_red);
+                    ok1 = ok1 || (n1 < 1.0);
+                    ok2 = ok2 || (n2 < 1.0);
+                    if (ok1 && ok2) {
+                        certified = true;
+                        break;
+                    }
+                    if (!(n1 < 1e100) || !(n2 < 1e100) || sq == 14) break;  // growing powers / NaN: leave it to bk_count
+                    Acc<NP> q1, q2;
+                    acc_zero(q1);
+                    acc_zero(q2);
+                    const int wp = threadIdx.x >> 5;  // strips beyond the blocks hold nothing
+                    if (!ok1 && wp < c1) gemm_acc<NP, false, false>(q1, Z1, Z1, 1.0, 0, k1, 0, c1);
+                    if (!ok2 && wp < c2) gemm_acc<NP, false, false>(q2, Z2, Z2, 1.0, 0, k2, 0, c2);
+                    if (!ok1 && wp < c1) acc_store<NP>(q1, Z1b, 0, c1);
+                    if (!ok2 && wp < c2) acc_store<NP>(q2, Z2b, 0, c2);
+                    __syncthreads();
+                    if (!ok1) {
+                        double* t = Z1;
+                        Z1 = Z1b;
+                        Z1b = t;
+                    }
+                    if (!ok2) {
+                        double* t = Z2;
+                        Z2 = Z2b;
+                        Z2b = t;
+                    }
+                }
+            }
+            if (threadIdx.x == 0) {
+                if (certified) p.status[draw] |= GECON_ST_BK_CERTIFIED;
+                if (p.n_unstable) p.n_unstable[draw] = certified ? nl : -1;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -214,6 +286,10 @@ static int check_cr_args(const gecon_cr_args* a) {
     }
     if (a->n_out < 0 || a->n_out > a->n || (a->n_out > 0 && !a->unperm)) {
         set_last_error("gecon_cr_args: n_out = %d needs 0 <= n_out <= n and an index list in unperm", a->n_out);
+        return GECON_E_BADARG;
+    }
+    if (a->lead_idx && (a->n_lead < 0 || a->n_lead > a->n)) {
+        set_last_error("gecon_cr_args: n_lead = %d out of range", a->n_lead);
         return GECON_E_BADARG;
     }
     if (a->k > round_up8(a->n)) {
@@ -267,7 +343,7 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
     const size_t no = (args->unperm && args->n_out > 0) ? (size_t)args->n_out : n;
     const size_t bm = N * n * n * sizeof(double), bd = N * n * k * sizeof(double);
     const size_t bmo = N * no * no * sizeof(double), bdo = N * no * k * sizeof(double);
-    DevBuf dA, dB, dC, dD, dT, dR, dSt, dIt, dRes, dNo, dPerm;
+    DevBuf dA, dB, dC, dD, dT, dR, dSt, dIt, dRes, dNo, dPerm, dLead, dNu;
     gecon_cr_args d = *args;
     GECON_CUDA(dA.alloc(bm));
     GECON_CUDA(dB.alloc(bm));
@@ -311,8 +387,18 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
         GECON_CUDA(cudaMemcpy(dPerm.p, args->unperm, no * sizeof(int32_t), cudaMemcpyHostToDevice));
         d.unperm = dPerm.as<int32_t>();
     }
+    if (args->lead_idx) {
+        GECON_CUDA(dLead.alloc((size_t)args->n_lead * sizeof(int32_t)));
+        GECON_CUDA(cudaMemcpy(dLead.p, args->lead_idx, (size_t)args->n_lead * sizeof(int32_t), cudaMemcpyHostToDevice));
+        d.lead_idx = dLead.as<int32_t>();
+    }
+    if (args->n_unstable) {
+        GECON_CUDA(dNu.alloc(N * sizeof(int32_t)));
+        d.n_unstable = dNu.as<int32_t>();
+    }
     rc = gecon_cr_solve_batched(&d, nullptr);
     if (rc) return rc;
+    if (args->n_unstable) GECON_CUDA(cudaMemcpy(args->n_unstable, d.n_unstable, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
     GECON_CUDA(cudaMemcpy(args->T, d.T, bmo, cudaMemcpyDeviceToHost));
     if (args->R) GECON_CUDA(cudaMemcpy(args->R, d.R, bdo, cudaMemcpyDeviceToHost));
     GECON_CUDA(cudaMemcpy(args->status, d.status, N * sizeof(int32_t), cudaMemcpyDeviceToHost));

@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) kalman_ll_kernel(const gecon_kalm
     const int lyap_cap = p.lyap_max_iter > 0 ? p.lyap_max_iter : 64;
 
     for (long long draw = blockIdx.x; draw < p.N; draw += gridDim.x) {
-        int status = p.status_in ? p.status_in[draw] : 0;
+        // GECON_ST_BK_CERTIFIED is informational (set by the solver kernel): a clean draw leaves this kernel with status 0
+        int status = p.status_in ? (p.status_in[draw] & ~GECON_ST_BK_CERTIFIED) : 0;
         if (status & p.gate_mask) {  // uniform: same value for every thread
             if (tid == 0) {
                 p.ll[draw] = -INFINITY;

@@ -155,65 +155,97 @@ __device__ double norm1(const double* __restrict__ M, int n, double* __restrict_
 // One barrier per column.  Returns false on a zero or non-finite pivot (caller NaN-fills, as the reference's
 // _solve_gen does).  Contains barriers: every thread of the CTA must call it with identical arguments.
 template <int NP>
-__device__ bool gj_solve(double* __restrict__ M, double* __restrict__ R1, int lo1, int hi1, double* __restrict__ R2, int lo2,
-                         int hi2, int n, int* __restrict__ s_piv, double* __restrict__ s_inv) {
+__device__ bool gj_solve(double* M, double* R1, int lo1, int hi1, double* R2, int lo2, int hi2, int n, int* __restrict__ s_piv,
+                         double* __restrict__ s_inv) {
     constexpr int LD = Cfg<NP>::LD, NW = Cfg<NP>::NW, CH = Cfg<NP>::CH;
+    constexpr int SL = (3 * NP + 31) / 32;  // slots per lane over the concatenated live columns [M | R1 | R2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w1 = hi1 - lo1, w2 = hi2 - lo2;
+    // R1 / R2 live in the same shared-memory array as M: address them as offsets from M so that one slot loop serves all
+    const int off1 = (w1 > 0) ? (int)(R1 - M) + lo1 : 0;
+    const int off2 = (w2 > 0) ? (int)(R2 - M) + lo2 : 0;
     unsigned long long used = 0ull;
     bool ok = true;
     for (int j = 0; j < n; ++j) {
-        // ---- pivot search, done redundantly by every warp on identical data (no barrier needed to share it)
-        double best = -1.0;
-        int bi = NP;
-        for (int i = lane; i < n; i += 32) {
-            if (!((used >> i) & 1ull)) {
-                const double v = fabs(M[i * LD + j]);
-                if (v > best) {
-                    best = v;
-                    bi = i;
+        // ---- pivot search, done redundantly by every warp on identical data (no barrier needed to share it).
+        // |x| as an orderable 64-bit key; max over the warp with two 32-bit redux.sync, lowest row index on ties.
+        unsigned long long key = 0ull;
+        int row = NP;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+            const int i = lane + 32 * ch;
+            if (i < n && !((used >> i) & 1ull)) {
+                const unsigned long long kk = (unsigned long long)__double_as_longlong(fabs(M[i * LD + j]));
+                if (kk > key || row == NP) {
+                    key = kk;
+                    row = i;
                 }
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ov > best || (ov == best && oi < bi)) {
-                best = ov;
-                bi = oi;
-            }
-        }
-        if (bi >= n || !(best > 0.0) || best > 1.7e308) {
+        const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, (khi == mhi) ? klo : 0u);
+        const int r = (int)__reduce_min_sync(0xffffffffu, (unsigned)((khi == mhi && klo == mlo) ? row : NP));
+        const double best = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        if (r >= n || !(best > 0.0) || best > 1.7e308) {
             ok = false;
             break;  // uniform across the CTA
         }
-        const int r = bi;
         const double inv = 1.0 / M[r * LD + j];
         used |= 1ull << r;
         if (threadIdx.x == 0) {
             s_piv[j] = r;
             s_inv[j] = inv;
         }
-        // ---- pivot row into registers (columns right of j in M, all of R1, R2)
-        double pm[CH], p1[CH], p2[CH];
+        // ---- slots: lane q + 32 s of the live columns (columns right of j in M, then the R1 range, then the R2 range).
+        // A lane without a live column in a slot points at the tile's first padding column (index NP: never read as
+        // matrix data) with a zero pivot-row value, so that the update loop below runs without per-element predicates.
+        const int nM = n - 1 - j;
+        const int live = nM + w1 + w2;
+        const int ns = (live + 31) >> 5;
+        int coff[SL];
+        double pv[SL];
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-            const int c = lane + 32 * ch;
-            pm[ch] = (c > j && c < n) ? M[r * LD + c] : 0.0;
-            p1[ch] = (lo1 + c < hi1) ? R1[r * LD + lo1 + c] : 0.0;
-            p2[ch] = (lo2 + c < hi2) ? R2[r * LD + lo2 + c] : 0.0;
+        for (int s = 0; s < SL; ++s) {
+            const int q = lane + 32 * s;
+            int c = NP;
+            if (q < nM) c = j + 1 + q;
+            else if (q < nM + w1) c = off1 + (q - nM);
+            else if (q < live) c = off2 + (q - nM - w1);
+            coff[s] = c;
+            pv[s] = (c != NP) ? M[r * LD + c] : 0.0;
         }
-        // ---- eliminate column j from every other row; warps split rows, lanes split columns
-        for (int i = warp; i < n; i += NW) {
-            if (i == r) continue;
-            const double mlt = M[i * LD + j] * inv;
-            if (mlt == 0.0) continue;  // structural zeros: nothing to do (reference BLAS skips them too)
+        // ---- eliminate column j from every other row; warps split rows (two at a time for ILP), lanes split columns.
+        // Row r and rows with a zero multiplier get multiplier 0 (an exact no-op) instead of a branch.
+        for (int i0 = warp; i0 < n; i0 += 2 * NW) {
+            const int i1 = i0 + NW;
+            double* row0 = M + i0 * LD;
+            const double m0 = (i0 == r) ? 0.0 : row0[j] * inv;
+            if (i1 < n) {
+                double* row1 = M + i1 * LD;
+                const double m1 = (i1 == r) ? 0.0 : row1[j] * inv;
+                if (m0 == 0.0 && m1 == 0.0) continue;  // structural zeros: nothing to do (reference BLAS skips them too)
+                double x0[SL], x1[SL];
 #pragma unroll
-            for (int ch = 0; ch < CH; ++ch) {
-                const int c = lane + 32 * ch;
-                if (c > j && c < n) M[i * LD + c] = fma(-mlt, pm[ch], M[i * LD + c]);
-                if (lo1 + c < hi1) R1[i * LD + lo1 + c] = fma(-mlt, p1[ch], R1[i * LD + lo1 + c]);
-                if (lo2 + c < hi2) R2[i * LD + lo2 + c] = fma(-mlt, p2[ch], R2[i * LD + lo2 + c]);
+                for (int s = 0; s < SL; ++s) {
+                    if (s < ns) {
+                        x0[s] = row0[coff[s]];
+                        x1[s] = row1[coff[s]];
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < SL; ++s) {
+                    if (s < ns) {
+                        row0[coff[s]] = fma(-m0, pv[s], x0[s]);
+                        row1[coff[s]] = fma(-m1, pv[s], x1[s]);
+                    }
+                }
+            } else {
+                if (m0 == 0.0) continue;
+#pragma unroll
+                for (int s = 0; s < SL; ++s) {
+                    if (s < ns) row0[coff[s]] = fma(-m0, pv[s], row0[coff[s]]);
+                }
             }
         }
         __syncthreads();

@@ -97,6 +97,7 @@ class CompiledModel:
         return A, B, Cm, D, xss, st
 
 
+# draws whose Jacobian is NaN never reach the BK kernel: flag them as BK failures here so that the gate sees them
 GATE_MASK = L.ST_CR_NOT_CONVERGED | L.ST_CR_NAN | L.ST_SINGULAR | L.ST_RESID | L.ST_BK | L.ST_BK_INCONCLUSIVE | L.ST_JAC_NONFINITE
 
 
@@ -237,7 +238,8 @@ class BatchedStateSpace:
                 D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
                 resid_tol=self.solver_tol, unperm=ws["subset"].data_ptr(), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
                 status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
-                n_out=self.n_filter,
+                n_out=self.n_filter, n_lead=(int(ws["lead"].numel()) if self.check_bk else 0),
+                lead_idx=(ws["lead"].data_ptr() if self.check_bk else None), n_unstable=ws["n_unstable"].data_ptr(),
             )  # fmt: skip
             e = mark("cr_solve")
             L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
@@ -247,6 +249,7 @@ class BatchedStateSpace:
                     struct_size=C.sizeof(L.BkArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(), N=cnt,
                     n=m.n, n_lead=int(ws["lead"].numel()), lead_idx=ws["lead"].data_ptr(), accumulate=1, max_iter=0,
                     n_unstable=ws["n_unstable"].data_ptr(), status=st.data_ptr(),
+                    skip_mask=L.ST_BK_CERTIFIED | L.ST_JAC_NONFINITE,
                 )  # fmt: skip
                 e = mark("bk_count")
                 L.check(lib.gecon_bk_count_batched(C.byref(bk), C.c_void_p(stream)), "gecon_bk_count_batched")

@@ -53,6 +53,7 @@ extern "C" {
 #define GECON_ST_LL_NONFINITE 0x100      /* log-likelihood is NaN or +-inf */
 #define GECON_ST_JAC_NONFINITE 0x200     /* steady state / Jacobian evaluation produced a non-finite entry */
 #define GECON_ST_SKIPPED 0x400           /* draw skipped because status_in & gate_mask != 0 */
+#define GECON_ST_BK_CERTIFIED 0x800      /* informational: n_unstable == n_forward proved by the solver kernel */
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Cycle reduction:  A + B T + C T T = 0,  R = -(C T + B)^-1 D,  resid = sum((A + B T + C T T)^2).
@@ -85,7 +86,13 @@ typedef struct gecon_cr_args {
                                outputs are the SUB-BLOCKS T[unperm][:, unperm] (n_out x n_out), R[unperm] (n_out x k).
                                Used to hand the Kalman kernel only the variables the likelihood depends on (lagged
                                variables + observed variables): an exact restriction, see DESIGN.md */
-    int32_t reserved1;
+    int32_t n_lead;         /* entries of lead_idx */
+    const int32_t* lead_idx; /* [n_lead] or NULL.  When given, converged draws also get a Blanchard-Kahn CERTIFICATE:
+                               with W = C T + B the pencil's finite spectrum is eig(T) U {1/mu : mu in eig(F)},
+                               F = -W^-1 C restricted to the lead columns, so rho(T) < 1 and rho(F) < 1 (each proved by
+                               a power of the matrix having 1-norm < 1, repeated squaring) imply n_unstable == n_lead.
+                               Certified draws get GECON_ST_BK_CERTIFIED; the others are left to gecon_bk_count_* */
+    int32_t* n_unstable;    /* [N] out or NULL: n_lead for certified draws, -1 otherwise */
 } gecon_cr_args;
 
 int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream);
@@ -112,6 +119,9 @@ typedef struct gecon_bk_args {
     int32_t max_iter;        /* Newton iterations of the sign function (<= 0: default 60) */
     int32_t* n_unstable;     /* [N] out or NULL (-1 when inconclusive) */
     int32_t* status;         /* [N] in/out */
+    int32_t skip_mask;       /* with accumulate != 0: draws with status & skip_mask are left untouched (e.g.
+                                GECON_ST_BK_CERTIFIED | GECON_ST_JAC_NONFINITE) */
+    int32_t reserved0;
 } gecon_bk_args;
 
 int gecon_bk_count_batched(const gecon_bk_args* args, void* stream);

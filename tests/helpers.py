@@ -20,9 +20,11 @@ def model(name: str) -> OracleModel:
     return OracleModel(name)
 
 
-def draws(mod: OracleModel, N: int, seed: int = 0, width: float = 0.05) -> np.ndarray:
+def draws(mod: OracleModel, N: int, seed: int = 0, width: float = 0.05, valid: bool = False) -> np.ndarray:
     """theta[N, n_theta]: defaults perturbed uniformly by +-width (relative), clipped into the GCN's prior bounds.
-    Row 0 is the default parameter vector."""
+    Row 0 is the default parameter vector.  ``valid=True`` also keeps the discount factor and the AR coefficients
+    strictly inside the unit interval and pins steady-state targets, so that (almost) every draw is solvable;
+    ``valid=False`` deliberately leaves NaN steady states and unit roots in the population."""
     rng = np.random.default_rng(seed)
     th0 = mod.theta_vector()
     th = th0 * (1.0 + width * (2.0 * rng.random((N, th0.size)) - 1.0))
@@ -32,6 +34,14 @@ def draws(mod: OracleModel, N: int, seed: int = 0, width: float = 0.05) -> np.nd
             lo, hi = bounds[pname]
             eps = 1e-6 * (hi - lo)
             th[:, j] = np.clip(th[:, j], lo + eps, hi - eps)
+    if valid:
+        for j, pname in enumerate(mod.param_names):
+            if pname == "beta":
+                th[:, j] = np.minimum(th[:, j], 0.999)
+            elif pname.startswith("rho_"):
+                th[:, j] = np.minimum(th[:, j], 0.99)
+            elif pname in ("pi_bar", "phi_pi_obj"):
+                th[:, j] = th0[j]
     th[0] = th0
     return th
 
