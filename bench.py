@@ -162,13 +162,12 @@ _ORACLE = {}
 def _oracle_eval(args):
     name, theta, sig, herr, observed, Y = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle import statespace as oss
+    from oracle import fast
     from oracle.model import OracleModel
 
     if name not in _ORACLE:
         _ORACLE[name] = OracleModel(str(ROOT / "geconpy_b200" / "model" / "specs" / f"{name}.json"))
-    r = oss.loglik(_ORACLE[name], theta, Y, observed, sig, herr if len(herr) else None, tol=1e-8, max_iter=100)
-    return r["ll"]
+    return fast.loglik(_ORACLE[name], theta, Y, observed, sig, herr if len(herr) else None, tol=1e-8, max_iter=100)
 
 
 def cpu_reference_rate(wl: dict, Y: np.ndarray, n_sample: int, cores: int, seed: int = 0):
@@ -235,7 +234,7 @@ def main():
         th0 = om.theta_vector()
         r0 = oss.loglik(om, th0, np.zeros((1, p)), wl["observed"], np.full(k, SIGMA_SHOCK))
         Y = simulate_from_policy(r0["T"], r0["R"], k, tobs, [om.var_names.index(v) for v in wl["observed"]])
-        n_sample = args.cpu_sample or max(cores * 8, 64)
+        n_sample = args.cpu_sample or 256 * cores
         rates = []
         for s in range(args.warmup + args.steps):
             rate, dt, nfin = cpu_reference_rate(wl, Y, n_sample, cores, seed=s)
@@ -247,7 +246,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{n_sample} draws of the workload per step, fork pool of {cores} workers, "
-                                           "numpy/scipy restatement of the reference path (oracle/)"},
+                                           "numba-compiled restatement of the reference path (oracle/fast.py)"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return
@@ -387,11 +386,11 @@ def main():
                               "of": int(draws_per_gpu), "rank": 0}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_sample = args.cpu_sample or max(cores * 8, 64)
+        n_sample = args.cpu_sample or 256 * cores
         rate, dt, nfin = cpu_reference_rate(wl, Y, n_sample, cores, seed=0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n_sample} draws of the same workload in {dt:.1f} s, fork pool of {cores} workers, "
-                                          "numpy/scipy restatement of the reference path (oracle/)"}
+                                          "numba-compiled restatement of the reference path (oracle/fast.py)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

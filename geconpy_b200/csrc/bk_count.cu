@@ -202,6 +202,7 @@ extern "C" int gecon_bk_count_host(const gecon_bk_args* a) {
     d.status = dS.as<int32_t>();
     if (a->n_unstable) {
         GECON_CUDA(dU.alloc(N * 4));
+        if (a->accumulate) GECON_CUDA(cudaMemcpy(dU.p, a->n_unstable, N * 4, cudaMemcpyHostToDevice));  // skipped draws keep theirs
         d.n_unstable = dU.as<int32_t>();
     }
     rc = gecon_bk_count_batched(&d, nullptr);

@@ -206,7 +206,9 @@ def test_dlyap_parity(B, name):
     assert (st == 0).all()
     for i in range(len(th)):
         ref = oss.dlyap(T[i], R[i] @ np.diag(q) @ R[i].T)
-        assert np.abs(P[i] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+        # scipy's bilinear-transform solve and the doubling iteration both carry ~cond * eps error when rho(T) -> 1
+        assert np.abs(P[i] - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+        assert np.abs(P[i] - (T[i] @ P[i] @ T[i].T + R[i] @ np.diag(q) @ R[i].T)).max() <= 1e-13 * max(1.0, np.abs(ref).max())
 
 
 @pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc", 200), ("full_nk", 200), ("nk_complete_more_shocks", 50)])

@@ -228,3 +228,24 @@ def test_dlyap_fixed_point():
     Q = np.eye(mod.k) * SIGMA_SHOCK**2
     P = oss.dlyap(T, R @ Q @ R.T)
     assert np.abs(P - (T @ P @ T.T + R @ Q @ R.T)).max() < 1e-14 * max(1, np.abs(P).max())
+
+
+@pytest.mark.parametrize("name,with_err", [("rbc", False), ("full_nk", True)])
+def test_compiled_cpu_port_matches_the_numpy_oracle(name, with_err):
+    """oracle/fast.py (numba; what bench.py times as the CPU baseline) computes the same gated log-likelihood."""
+    from helpers import SIGMA_ERR, draws, simulate_obs
+    from oracle import fast
+
+    mod = model(name)
+    observed = mod.spec["observed_default"]
+    Y = simulate_obs(mod, 60, seed=0, sigma_err=SIGMA_ERR if with_err else 0.0)
+    sig = np.full(mod.k, SIGMA_SHOCK)
+    err = np.full(len(observed), SIGMA_ERR) if with_err else None
+    th = np.vstack([draws(mod, 5, seed=2, width=0.04, valid=True), draws(mod, 3, seed=3, width=0.08, valid=False)])
+    for t in th:
+        ref = oss.loglik(mod, t, Y, observed, sig, err, tol=1e-8, max_iter=100)
+        got = fast.loglik(mod, t, Y, observed, sig, err, tol=1e-8, max_iter=100)
+        if ref["ok"] and np.isfinite(ref["ll"]):
+            assert abs(got - ref["ll"]) <= 1e-8
+        else:
+            assert np.isneginf(got)
