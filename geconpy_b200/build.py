@@ -20,6 +20,9 @@ LIBDIR = PKG / "_lib"
 MODEL_LIBDIR = LIBDIR / "models"
 CORE_LIB = LIBDIR / "libgecon_b200.so"
 CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu"]
+# the Kalman kernel is instantiated for (NP, p) in 7 x 8 combinations: one object per padded dimension NP, built in parallel
+KALMAN_INST = "kalman_inst.cu"
+KALMAN_NPS = [8, 16, 24, 32, 40, 48, 56]
 
 NVCC_FLAGS = [
     "-O3",
@@ -59,7 +62,7 @@ def _run(cmd):
 def build_core(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu -> _lib/libgecon_b200.so (skipped when the sources are unchanged)."""
     LIBDIR.mkdir(exist_ok=True)
-    deps = [CSRC / s for s in CORE_SOURCES] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "gecon_b200.h"]
+    deps = [CSRC / s for s in CORE_SOURCES + [KALMAN_INST]] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "gecon_b200.h"]
     stamp = LIBDIR / "libgecon_b200.stamp"
     dig = _digest(deps, NVCC_FLAGS)
     if not force and CORE_LIB.exists() and stamp.exists() and stamp.read_text() == dig:
@@ -68,15 +71,18 @@ def build_core(force: bool = False, verbose: bool = False) -> Path:
     objdir = LIBDIR / "obj"
     objdir.mkdir(exist_ok=True)
 
-    def compile_one(src):
-        obj = objdir / (Path(src).stem + ".o")
-        out = _run([nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", str(CSRC / src), "-o", str(obj)])
+    def compile_one(job):
+        src, defines, stem = job
+        obj = objdir / (stem + ".o")
+        out = _run([nvcc, *NVCC_FLAGS, *defines, *(["-Xptxas", "-v"] if verbose else []), "-c", str(CSRC / src), "-o", str(obj)])
         if verbose:
             print(out)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(CORE_SOURCES)) as ex:
-        objs = list(ex.map(compile_one, CORE_SOURCES))
+    jobs = [(s, [], Path(s).stem) for s in CORE_SOURCES]
+    jobs += [(KALMAN_INST, [f"-DGECON_KF_NP={np_}"], f"kalman_inst_np{np_}") for np_ in KALMAN_NPS]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, jobs))
     _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CORE_LIB), *map(str, objs), "-lcudart"])
     stamp.write_text(dig)
     return CORE_LIB
