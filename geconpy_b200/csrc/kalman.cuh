@@ -295,8 +295,37 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
             __syncthreads();
         }
 
-        double ll_acc = 0.0;  // meaningful in thread n only
-        bool notpd = false;   // thread n only
+        // The predicted mean rides along in the spare column n of the P / W tiles when there is one (n < NP): phase 2
+        // stores a+ in P[:, n], the W = T P+ product then leaves T a+ in W[:, n] -- no separate matrix-vector loop.
+        const bool aug = (n < NP);
+        const int wlo = aug ? min(ctlo, n >> 3) : ctlo, whi = aug ? max(cthi, (n >> 3) + 1) : cthi;
+        if (aug && tid < NP) W[tid * LD + n] = 0.0;  // a_0 = 0
+        // T's fragments are the same in all T_obs steps: keep them in registers (small NP only: register budget)
+        constexpr bool CACHE = (NP <= 24);
+        constexpr int KS = NP / 4, CTN = NP / 8;
+        double tA[CACHE ? KS : 1], tB[CACHE ? CTN : 1][CACHE ? KS : 1], rq[CACHE ? CTN : 1][2];
+        if constexpr (CACHE) {
+            const int g = (tid & 31) >> 2, q = tid & 3, r = (tid >> 5) * 8 + g;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                tA[ks] = Tm[r * LD + 4 * ks + q];
+#pragma unroll
+                for (int ct = 0; ct < CTN; ++ct) tB[ct][ks] = Tm[(ct * 8 + g) * LD + 4 * ks + q];
+            }
+#pragma unroll
+            for (int ct = 0; ct < CTN; ++ct) {
+                rq[ct][0] = RQ[r * LD + ct * 8 + 2 * q];
+                rq[ct][1] = RQ[r * LD + ct * 8 + 2 * q + 1];
+            }
+        }
+        __syncthreads();
+
+        // thread n accumulates sum_t (log det F_t + v' F^-1 v): the determinants are multiplied up (mantissa and
+        // exponent kept apart) and ONE logarithm is taken at the end, unless per-step values are requested
+        double ll_acc = 0.0, quad_acc = 0.0, detprod = 1.0;
+        long long det_exp = 0;
+        int n_ll_steps = 0;
+        bool notpd = false;
         for (int t = 0; t < Tobs; ++t) {
             const double* y = s_Y + (size_t)t * PT;
             const int wb = s_wb[t];
@@ -320,10 +349,10 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
                 const bool obs = (wb >> a) & 1;
                 double za;
                 if (sel) {
-                    za = s_a[s_obs[a]];
+                    za = aug ? W[s_obs[a] * LD + n] : s_a[s_obs[a]];
                 } else {
                     za = 0.0;
-                    for (int j = 0; j < n; ++j) za = fma(s_Z[a * NP + j], s_a[j], za);
+                    for (int j = 0; j < n; ++j) za = fma(s_Z[a * NP + j], aug ? W[j * LD + n] : s_a[j], za);
                 }
                 s_v[a] = (obs ? y[a] : 0.0) - (s_d[a] + (obs ? za : 0.0));
             }
@@ -396,10 +425,22 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
                     double quad = 0.0;
 #pragma unroll
                     for (int a = 0; a < PT; ++a) quad = fma(x[a] * dv[a], x[a], quad);
-                    const double llt = (wb == 0) ? 0.0 : -0.5 * (ll_const + log(s_sc[0]) + quad);
-                    ll_acc += llt;
                     if (s_sc[1] != 0.0) notpd = true;
-                    if (p.ll_t) p.ll_t[(size_t)draw * Tobs + t] = llt;
+                    if (p.ll_t) {
+                        const double llt = (wb == 0) ? 0.0 : -0.5 * (ll_const + log(s_sc[0]) + quad);
+                        ll_acc += llt;
+                        p.ll_t[(size_t)draw * Tobs + t] = llt;
+                    } else if (wb != 0) {
+                        int e;
+                        detprod *= frexp(s_sc[0], &e);
+                        det_exp += e;
+                        quad_acc += quad;
+                        ++n_ll_steps;
+                        if ((t & 31) == 31) {
+                            detprod = frexp(detprod, &e);
+                            det_exp += e;
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int a = 0; a < PT; ++a) x[a] *= dv[a];
@@ -408,10 +449,11 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
 #pragma unroll
                         for (int b = a + 1; b < PT; ++b) x[a] = fma(-s_F[b * PS + a], x[b], x[a]);
                     }
-                    double af = s_a[tid];
+                    double af = aug ? W[tid * LD + n] : s_a[tid];
 #pragma unroll
                     for (int a = 0; a < PT; ++a) af = fma(x[a], s_v[a], af);
-                    s_af[tid] = af;
+                    if (aug) P[tid * LD + n] = af;
+                    else s_af[tid] = af;
 #pragma unroll
                     for (int a = 0; a < PT; ++a) {
                         double kg = 0.0;
@@ -439,21 +481,52 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
                     P[j * LD + i] = acc;
                 }
             }
-            if (tid < n) {  // predicted mean a = T a+  (c = 0)
+            if (!aug && tid < n) {  // no spare column: predicted mean a = T a+ by a plain loop
                 double s = 0.0;
                 for (int j = lo; j < hi; ++j) s = fma(Tm[tid * LD + j], s_af[j], s);
                 s_a[tid] = s;
             }
             __syncthreads();
-            // ---- phases 4, 5: P = T P+ T' + R Q R'
-            {
+            // ---- phases 4, 5: W = T [P+ | a+],  P = T P+ T' + R Q R'
+            if constexpr (CACHE) {
+                const int g = (tid & 31) >> 2, q = tid & 3;
                 Acc<NP> w;
                 acc_zero(w);
-                gemm_acc<NP, false, false>(w, Tm, P, 1.0, klo, khi, ctlo, cthi);
-                acc_store<NP>(w, W, ctlo, cthi);
-            }
-            __syncthreads();
-            {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    if (4 * ks >= klo && 4 * ks < khi) {
+#pragma unroll
+                        for (int ct = 0; ct < CTN; ++ct) {
+                            if (ct >= wlo && ct < whi) dmma884(w.v[ct][0], w.v[ct][1], tA[ks], P[(4 * ks + q) * LD + ct * 8 + g]);
+                        }
+                    }
+                }
+                acc_store<NP>(w, W, wlo, whi);
+                __syncthreads();
+                const int r = (tid >> 5) * 8 + g;
+                Acc<NP> pn;
+#pragma unroll
+                for (int ct = 0; ct < CTN; ++ct) {
+                    pn.v[ct][0] = rq[ct][0];
+                    pn.v[ct][1] = rq[ct][1];
+                }
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    if (4 * ks >= klo && 4 * ks < khi) {
+                        const double a = W[r * LD + 4 * ks + q];
+#pragma unroll
+                        for (int ct = 0; ct < CTN; ++ct) dmma884(pn.v[ct][0], pn.v[ct][1], a, tB[ct][ks]);
+                    }
+                }
+                acc_store<NP>(pn, P);
+            } else {
+                {
+                    Acc<NP> w;
+                    acc_zero(w);
+                    gemm_acc<NP, false, false>(w, Tm, P, 1.0, klo, khi, wlo, whi);
+                    acc_store<NP>(w, W, wlo, whi);
+                }
+                __syncthreads();
                 Acc<NP> pn;
                 acc_load<NP>(pn, RQ);
                 gemm_acc<NP, false, true>(pn, W, Tm, 1.0, klo, khi);
@@ -462,6 +535,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
             __syncthreads();
         }
         if (tid == n) {
+            if (!p.ll_t) ll_acc = -0.5 * (n_ll_steps * ll_const + (log(detprod) + (double)det_exp * 0.6931471805599453) + quad_acc);
             if (notpd) status |= GECON_ST_NOT_PD;
             if (!(fabs(ll_acc) <= 1.7e308)) status |= GECON_ST_LL_NONFINITE;
             p.ll[draw] = ll_acc;

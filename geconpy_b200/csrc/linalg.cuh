@@ -164,6 +164,28 @@ __device__ bool gj_solve(double* M, double* R1, int lo1, int hi1, double* R2, in
     // R1 / R2 live in the same shared-memory array as M: address them as offsets from M so that one slot loop serves all
     const int off1 = (w1 > 0) ? (int)(R1 - M) + lo1 : 0;
     const int off2 = (w2 > 0) ? (int)(R2 - M) + lo2 : 0;
+    // ---- slots: lane q + 32 s of the concatenated columns [all of M | R1 range | R2 range], fixed for the whole solve.
+    // A lane without a column in a slot points at the tile's first padding column (index NP: never read as matrix data)
+    // with a zero pivot-row value, so that the update loop runs without per-element predicates.
+    const int ns = (n + w1 + w2 + 31) >> 5;
+    int coff[SL], cmin[SL];  // cmin: M column index (live once > j); RHS columns are always live (NP + 1)
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const int q = lane + 32 * s;
+        int c = NP, cm = -1;
+        if (q < n) {
+            c = q;
+            cm = q;
+        } else if (q < n + w1) {
+            c = off1 + (q - n);
+            cm = NP + 1;
+        } else if (q < n + w1 + w2) {
+            c = off2 + (q - n - w1);
+            cm = NP + 1;
+        }
+        coff[s] = c;
+        cmin[s] = cm;
+    }
     unsigned long long used = 0ull;
     bool ok = true;
     for (int j = 0; j < n; ++j) {
@@ -197,24 +219,11 @@ __device__ bool gj_solve(double* M, double* R1, int lo1, int hi1, double* R2, in
             s_piv[j] = r;
             s_inv[j] = inv;
         }
-        // ---- slots: lane q + 32 s of the live columns (columns right of j in M, then the R1 range, then the R2 range).
-        // A lane without a live column in a slot points at the tile's first padding column (index NP: never read as
-        // matrix data) with a zero pivot-row value, so that the update loop below runs without per-element predicates.
-        const int nM = n - 1 - j;
-        const int live = nM + w1 + w2;
-        const int ns = (live + 31) >> 5;
-        int coff[SL];
+        // ---- pivot-row values of this lane's slots; columns of M up to j are dead: a zero value makes their update an
+        // exact no-op (x - m * 0 = x, so the concurrent multiplier reads of column j by other warps see the same bits)
         double pv[SL];
 #pragma unroll
-        for (int s = 0; s < SL; ++s) {
-            const int q = lane + 32 * s;
-            int c = NP;
-            if (q < nM) c = j + 1 + q;
-            else if (q < nM + w1) c = off1 + (q - nM);
-            else if (q < live) c = off2 + (q - nM - w1);
-            coff[s] = c;
-            pv[s] = (c != NP) ? M[r * LD + c] : 0.0;
-        }
+        for (int s = 0; s < SL; ++s) pv[s] = (s < ns && cmin[s] > j) ? M[r * LD + coff[s]] : 0.0;
         // ---- eliminate column j from every other row; warps split rows (two at a time for ILP), lanes split columns.
         // Row r and rows with a zero multiplier get multiplier 0 (an exact no-op) instead of a branch.
         for (int i0 = warp; i0 < n; i0 += 2 * NW) {
