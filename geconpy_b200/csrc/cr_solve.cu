@@ -235,8 +235,11 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
                 const int k1 = (s1 + 3) & ~3, c1 = (s1 + 7) >> 3, k2 = (nl + 3) & ~3, c2 = (nl + 7) >> 3;
                 bool ok1 = (s1 == 0), ok2 = (nl == 0);
                 for (int sq = 0; sq <= 14; ++sq) {
-                    const double n1 = ok1 ? 0.0 : norm1<NP>(Z1, s1, s_red);
-                    const double n2 = ok2 ? 0.0 : norm1<NP>(Z2, nl, s_red);
+                    // the norms are only inspected after every second squaring (and at the start): a certificate
+                    // found one squaring late costs one small product, a norm costs two barriers
+                    const bool look = (sq == 0) || (sq & 1) == 0 || sq == 14;
+                    const double n1 = (ok1 || !look) ? (ok1 ? 0.0 : 2.0) : norm1<NP>(Z1, s1, s_red);
+                    const double n2 = (ok2 || !look) ? (ok2 ? 0.0 : 2.0) : norm1<NP>(Z2, nl, s_red);
                     ok1 = ok1 || (n1 < 1.0);
                     ok2 = ok2 || (n2 < 1.0);
                     if (ok1 && ok2) {

@@ -140,7 +140,7 @@ __device__ int dlyap_doubling(double* __restrict__ P, double* __restrict__ Aw, d
 // resident CTAs per SM the register allocator must leave room for (shared memory allows about this many)
 template <int NP>
 constexpr int kf_min_ctas() {
-    return NP <= 16 ? 8 : NP <= 24 ? 5 : NP <= 32 ? 3 : NP <= 40 ? 2 : 1;
+    return NP <= 16 ? 8 : NP <= 24 ? 4 : NP <= 32 ? 3 : NP <= 40 ? 2 : 1;
 }
 
 template <int NP, int PT>
