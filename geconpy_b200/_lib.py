@@ -77,6 +77,8 @@ class CrArgs(C.Structure):
         ("n_lead", C.c_int32),
         ("lead_idx", C.c_void_p),
         ("n_unstable", C.c_void_p),
+        ("solv_norms", C.c_void_p),
+        ("trunc_tol", C.c_double),
     ]
 
 

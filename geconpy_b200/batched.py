@@ -97,13 +97,15 @@ class CycleReductionResult:
     resid: object
     norms: object
     n_unstable: object = None
+    solv_norms: object = None
 
     @property
     def converged(self):
         return (self.status & L.ST_CR_NOT_CONVERGED) == 0
 
 
-def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None, subset=None, lead_idx=None) -> CycleReductionResult:
+def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None, subset=None, lead_idx=None,
+             solvability_norms=False, trunc_tol=1e-8) -> CycleReductionResult:
     """Batched cycle reduction + R + residual (``gecon_cr_solve_*``).
 
     Reference: ``_cycle_reduction_core`` (gEconpy/solvers/cycle_reduction.py:127-183), ``pt_compute_selection_matrix``
@@ -138,10 +140,12 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     lead = None if lead_idx is None else np.ascontiguousarray(lead_idx, dtype=np.int32)
     _, pL = m.inp(lead, np.int32)
     nu, pNu = m.out((N,), np.int32) if lead is not None else (None, None)
+    sn, pSn = m.out((N, 2)) if solvability_norms else (None, None)
     args = L.CrArgs(
         struct_size=C.sizeof(L.CrArgs), A=pA, B=pB, C=pC, D=pD, N=N, n=n, k=k, max_iter=int(max_iter), tol=float(tol),
         resid_tol=float(resid_tol), unperm=pU, T=pT, R=pR, status=pS, n_iter=pI, resid=pRes, norms=pNo, n_out=n_out,
         n_lead=(0 if lead is None else int(lead.size)), lead_idx=pL, n_unstable=pNu,
+        solv_norms=pSn, trunc_tol=float(trunc_tol),
     )  # fmt: skip
     lib = L.load_library()
     if m.device:
@@ -149,8 +153,9 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     else:
         L.check(lib.gecon_cr_solve_host(C.byref(args)), "gecon_cr_solve_host")
     if squeeze:
-        return CycleReductionResult(T[0], None if R is None else R[0], status[0], n_iter[0], resid[0], norms[0], None if nu is None else nu[0])
-    return CycleReductionResult(T, R, status, n_iter, resid, norms, nu)
+        return CycleReductionResult(T[0], None if R is None else R[0], status[0], n_iter[0], resid[0], norms[0], None if nu is None else nu[0],
+                                    None if sn is None else sn[0])
+    return CycleReductionResult(T, R, status, n_iter, resid, norms, nu, sn)
 
 
 def bk_count(A, B, C_, lead_idx, status=None, max_iter=0, skip_mask=0, n_unstable=None):

@@ -39,6 +39,8 @@ inline int sm_count() {
 template <typename K>
 inline int persistent_grid(K kernel, int threads, size_t smem, long long N, int* grid, int* ctas_per_sm) {
     GECON_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // these kernels live in shared memory and barely touch L1: ask for the largest shared-memory carve-out
+    GECON_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     GECON_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) {

@@ -28,8 +28,14 @@ struct CrSmem {
     static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (3 * NP + 4);
 };
 
+// resident CTAs per SM that shared memory allows (7 tiles per CTA): the register allocator must not get in the way
 template <int NP>
-__global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_args p) {
+constexpr int cr_min_ctas() {
+    return NP <= 8 ? 16 : NP <= 16 ? 10 : NP <= 24 ? 5 : NP <= 32 ? 3 : NP <= 40 ? 2 : 1;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kernel(const gecon_cr_args p) {
     using C = Cfg<NP>;
     constexpr int LD = C::LD;
     extern __shared__ __align__(16) double sm[];
@@ -274,6 +280,71 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) cr_solve_kernel(const gecon_cr_ar
             }
             __syncthreads();
         }
+
+        // ---- residual norms of gEcon's state/jumper representation (perturbation.py:287-380), as solvability_check
+        // reports them: entries of T, R below trunc_tol are zeroed first; state columns = columns of the truncated T
+        // with a surviving entry;  nd = ||(A + B T~ + C T~ T~)[:, states]||_F,  ns = ||B R~ + C T~ R~ + D||_F.
+        if (p.solv_norms) {
+            const double tt = p.trunc_tol;
+            for (int i = threadIdx.x; i < C::TILE; i += C::NT) {
+                const double v = Tt[i];
+                W[i] = (fabs(v) < tt) ? 0.0 : v;
+            }
+            if (gC) tile_load<NP>(A2, gC, n, n, n);
+            else tile_zero<NP>(A2);
+            tile_load<NP>(A1, gB, n, n, n);
+            tile_load<NP>(A1h, gA, n, n, n);
+            __syncthreads();
+            if ((int)threadIdx.x < NP) {  // state-column flags of the truncated T
+                int any = 0;
+                if ((int)threadIdx.x < n)
+                    for (int i = 0; i < n; ++i) any |= (W[i * LD + threadIdx.x] != 0.0);
+                s_piv[threadIdx.x] = any;
+            }
+            {
+                Acc<NP> ct;
+                acc_zero(ct);
+                gemm_acc<NP, false, false>(ct, A2, W, 1.0);
+                acc_store<NP>(ct, A0);
+            }
+            __syncthreads();
+            double nd, ns = 0.0;
+            {
+                Acc<NP> e;
+                acc_load<NP>(e, A1h);
+                gemm_acc<NP, false, false>(e, A1, W, 1.0);
+                gemm_acc<NP, false, false>(e, A0, W, 1.0);
+                const int q2 = 2 * (threadIdx.x & 3);
+                double ss = 0.0;
+#pragma unroll
+                for (int ct = 0; ct < C::CT; ++ct) {
+                    if (s_piv[ct * 8 + q2]) ss += e.v[ct][0] * e.v[ct][0];
+                    if (s_piv[ct * 8 + q2 + 1]) ss += e.v[ct][1] * e.v[ct][1];
+                }
+                nd = sqrt(block_sum<NP>(ss, s_red));
+            }
+            if (gD && p.R) {
+                for (int i = threadIdx.x; i < C::TILE; i += C::NT) {
+                    const double v = -X2[i];  // X2 holds -R
+                    A1h[i] = (fabs(v) < tt) ? 0.0 : v;
+                }
+                tile_load<NP>(A2, gD, n, k, k);
+                __syncthreads();
+                Acc<NP> e;
+                acc_load<NP>(e, A2);
+                gemm_acc<NP, false, false>(e, A1, A1h, 1.0);
+                gemm_acc<NP, false, false>(e, A0, A1h, 1.0);
+                double ss = 0.0;
+#pragma unroll
+                for (int ct = 0; ct < C::CT; ++ct) ss += e.v[ct][0] * e.v[ct][0] + e.v[ct][1] * e.v[ct][1];
+                ns = sqrt(block_sum<NP>(ss, s_red));
+            }
+            if (threadIdx.x == 0) {
+                p.solv_norms[2 * draw] = nd;
+                p.solv_norms[2 * draw + 1] = ns;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -346,7 +417,7 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
     const size_t no = (args->unperm && args->n_out > 0) ? (size_t)args->n_out : n;
     const size_t bm = N * n * n * sizeof(double), bd = N * n * k * sizeof(double);
     const size_t bmo = N * no * no * sizeof(double), bdo = N * no * k * sizeof(double);
-    DevBuf dA, dB, dC, dD, dT, dR, dSt, dIt, dRes, dNo, dPerm, dLead, dNu;
+    DevBuf dA, dB, dC, dD, dT, dR, dSt, dIt, dRes, dNo, dPerm, dLead, dNu, dSn;
     gecon_cr_args d = *args;
     GECON_CUDA(dA.alloc(bm));
     GECON_CUDA(dB.alloc(bm));
@@ -399,8 +470,13 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
         GECON_CUDA(dNu.alloc(N * sizeof(int32_t)));
         d.n_unstable = dNu.as<int32_t>();
     }
+    if (args->solv_norms) {
+        GECON_CUDA(dSn.alloc(2 * N * sizeof(double)));
+        d.solv_norms = dSn.as<double>();
+    }
     rc = gecon_cr_solve_batched(&d, nullptr);
     if (rc) return rc;
+    if (args->solv_norms) GECON_CUDA(cudaMemcpy(args->solv_norms, d.solv_norms, 2 * N * sizeof(double), cudaMemcpyDeviceToHost));
     if (args->n_unstable) GECON_CUDA(cudaMemcpy(args->n_unstable, d.n_unstable, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
     GECON_CUDA(cudaMemcpy(args->T, d.T, bmo, cudaMemcpyDeviceToHost));
     if (args->R) GECON_CUDA(cudaMemcpy(args->R, d.R, bdo, cudaMemcpyDeviceToHost));

@@ -93,6 +93,9 @@ typedef struct gecon_cr_args {
                                a power of the matrix having 1-norm < 1, repeated squaring) imply n_unstable == n_lead.
                                Certified draws get GECON_ST_BK_CERTIFIED; the others are left to gecon_bk_count_* */
     int32_t* n_unstable;    /* [N] out or NULL: n_lead for certified draws, -1 otherwise */
+    double* solv_norms;     /* [N][2] out or NULL: (norm_deterministic, norm_stochastic) of solvability_check
+                               (statistics/perturbation_diagnostics.py:105-161, model/perturbation.py:287-380) */
+    double trunc_tol;       /* entries of T, R below this are zeroed before the norms (the reference's `tol`) */
 } gecon_cr_args;
 
 int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream);

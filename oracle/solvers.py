@@ -299,3 +299,42 @@ def residual_norms_statespace(A, B, C, D, T, R, state_var_mask):
     nd = np.linalg.norm(A_p + B @ R_p + C @ R_p @ P)
     ns = np.linalg.norm(B @ R + C @ R_p @ Q + D)
     return float(nd), float(ns)
+
+
+def gecon_representation_norms(A, B, C, D, T, R, tol=1e-8):
+    """gEconpy/model/perturbation.py:321-380 (statespace_to_gEcon_representation) + :287-318 (residual_norms), the
+    quantities ``solvability_check`` reports (statistics/perturbation_diagnostics.py:141-153)."""
+    n = T.shape[1]
+    state_idx = np.where(np.abs(T[np.argmax(np.abs(T), axis=0), np.arange(n)]) >= tol)[0]
+    mask = np.isin(np.arange(n), state_idx)
+    PP = T.copy()
+    PP[np.abs(PP) < tol] = 0
+    QQ = R[:n].copy()
+    QQ[np.abs(QQ) < tol] = 0
+    P, Q = PP[mask][:, mask], QQ[mask]
+    A_prime, R_prime, S_prime = A[:, mask], PP[:, mask], QQ
+    nd = np.linalg.norm(A_prime + B @ R_prime + C @ R_prime @ P)
+    ns = np.linalg.norm(B @ S_prime + C @ R_prime @ Q + D)
+    return float(nd), float(ns)
+
+
+def solvability_one(model, theta, tol=1e-8, max_iter=100, norm_tol=1e-8):
+    """statistics/perturbation_diagnostics.py:105-161 ``_check_one_draw`` on an OracleModel:
+    (failure_step | None, norm_deterministic, norm_stochastic)."""
+    nd = ns = np.nan
+    A, B, C, D = model.jacobians(theta, mode="statespace")
+    if not all(np.isfinite(M).all() for M in (A, B, C, D)):
+        return "steady_state", nd, ns
+    T, conv, _ = cycle_reduction_core(A, B, C, max_iter=max_iter, tol=tol)
+    if not conv or not np.isfinite(T).all():
+        return "perturbation", nd, ns
+    R = selection_matrix(B, C, D, T)
+    ok, _, _ = bk_condition_pt(A, B, C, D, model.permuted_lead_var_idx)
+    if not ok:
+        return "blanchard-kahn", nd, ns
+    nd, ns = gecon_representation_norms(A, B, C, D, T, R, tol)
+    if nd > norm_tol:
+        return "deterministic_norm", nd, ns
+    if ns > norm_tol:
+        return "stochastic_norm", nd, ns
+    return None, nd, ns

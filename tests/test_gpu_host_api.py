@@ -156,3 +156,38 @@ def test_check_bk_condition_api():
     M = np.diag([0.5, 1.5, -2.0, 0.99, 0.0])
     M[0, 1] = 3.0
     assert int(count_outside_unit_circle(M)) == 2
+
+
+@pytest.mark.parametrize("name", ["rbc", "full_nk"])
+def test_solvability_check_matches_the_per_draw_pipeline(name):
+    """the reference's batch-over-draws driver (perturbation_diagnostics.py:362-450) as one GPU pass,
+    against the oracle's restatement of _check_one_draw (same labels, norms to 1e-9 relative + 1e-14)."""
+    import pandas as pd
+
+    from helpers import draws
+    from geconpy_b200.model.compiled import CompiledModel
+    from geconpy_b200.model.statistics import solvability_check
+
+    mod = model(name)
+    th = np.vstack([draws(mod, 20, seed=51, width=0.05, valid=True), draws(mod, 12, seed=52, width=0.08, valid=False)])
+    cols = mod.param_names[:4]
+    base = mod.theta_vector()
+    samples = pd.DataFrame({c: th[:, mod.param_names.index(c)] for c in cols})
+    out = solvability_check(CompiledModel(name), samples, tol=1e-8, max_iter=100, norm_tol=1e-8)
+    assert list(out.columns) == cols + ["failure_step", "norm_deterministic", "norm_stochastic"] and len(out) == len(samples)
+    seen = set()
+    for i in range(len(samples)):
+        t = base.copy()
+        for c in cols:
+            t[mod.param_names.index(c)] = samples[c][i]
+        step, nd, ns = osol.solvability_one(mod, t, tol=1e-8, max_iter=100, norm_tol=1e-8)
+        seen.add(step)
+        got = out["failure_step"][i]
+        assert (got is None and step is None) or got == step, (name, i, got, step)
+        if np.isnan(nd):
+            assert np.isnan(out["norm_deterministic"][i]) and np.isnan(out["norm_stochastic"][i])
+        else:
+            # converged draws leave rounding noise (1e-15..1e-13) unless the 1e-8 truncation of T, R bites
+            assert abs(out["norm_deterministic"][i] - nd) <= 1e-12 + 1e-6 * nd
+            assert abs(out["norm_stochastic"][i] - ns) <= 1e-12 + 1e-6 * ns
+    assert None in seen
