@@ -364,8 +364,15 @@ def main():
     units = n_eval_kf if dom == "kalman_ll" else draws_per_gpu
     launches_per_step = max(1, math.ceil(draws_per_gpu / ss.chunk))
     achieved = (fm.get(dom, 0.0) * units) / (kernel_ms[dom] * 1e-3) / 1e12 if dom in fm and kernel_ms.get(dom) else None
+    # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (per-draw figure x draws)
+    traffic = None
+    tfile = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if tfile.exists() and args.workload == "nk":
+        per_draw = {k.split("_kernel")[0]: v["dram_bytes_per_draw"] for k, v in json.loads(tfile.read_text()).items() if isinstance(v, dict)}
+        if dom in per_draw:
+            traffic = per_draw[dom] * min(draws_per_gpu, ss.chunk)
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": "measured DFMA burst on this pool's B200 (profiles/r01_fp64_peak_microbench.json); "
                                "MEASURED_PEAKS.json holds no fp64 figure",
                 "flops_per_eval": fm, "mean_cr_iterations": i_cr, "assumed_lyapunov_doublings": j_lyap,
