@@ -25,7 +25,7 @@ __device__ __forceinline__ void acc_sub(Acc<NP>& a, const Acc<NP>& b) {
 template <int NP>
 struct CrSmem {
     static constexpr int TILES = 7;
-    static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (3 * NP + 4);
+    static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 8 * NP) + sizeof(int) * (4 * NP + 8);
 };
 
 // resident CTAs per SM that shared memory allows (7 tiles per CTA): the register allocator must not get in the way
@@ -46,12 +46,13 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
     double* W = A1h + C::TILE;
     double* X0 = W + C::TILE;
     double* X2 = X0 + C::TILE;
-    double* s_inv = X2 + C::TILE;
-    double* s_red = s_inv + NP;
-    int* s_piv = reinterpret_cast<int*>(s_red + NP);
+    double* s_red = X2 + C::TILE;  // [8 NP]: two norm1_fast buffers
+    int* s_piv = reinterpret_cast<int*>(s_red + 8 * NP);
     int* s_perm = s_piv + NP;
     int* s_lead = s_perm + NP;
     int* s_i = s_lead + NP;
+    int* s_flag = s_i + 4;  // [NP + 1]
+    for (int i = threadIdx.x; i < NP; i += C::NT) s_piv[i] = 0;
 
     const int n = p.n, k = p.k;
     const int no = (p.unperm && p.n_out > 0) ? p.n_out : n;  // rows/cols written out (sub-block gather when < n)
@@ -90,11 +91,9 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
         if (gC) {
             while (it < p.max_iter) {
                 ++it;
-                tile_copy<NP>(W, A1);
-                tile_copy<NP>(X0, A0);
-                tile_copy<NP>(X2, A2);
-                __syncthreads();
-                const bool ok = gj_solve<NP>(W, X0, lo0, hi0, X2, lo2, hi2, n, s_piv, s_inv);
+                // [X0 | X2] = A1^-1 [A0 | A2], read from the live tiles, written to the scratch tiles; solution row j is
+                // left in row s_piv[j], which the four products below read through
+                const bool ok = gj_solve_blocked<NP>(A1, W, A0, X0, c0lo, c0hi, A2, X2, c2lo, c2hi, n, false, s_piv, s_flag);
                 if (!ok) {  // LAPACK: singular U -> inf/NaN in getrs; the norm test below then stops the loop
                     tile_nanfill<NP>(X0, n, n);
                     tile_nanfill<NP>(X2, n, n);
@@ -103,9 +102,9 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
                 {
                     Acc<NP> m20, t;
                     acc_zero(m20);
-                    gemm_acc<NP, false, false>(m20, A2, X0, 1.0, k2lo, k2hi, ok ? c0lo : 0, ok ? c0hi : C::CT);
+                    gemm_acc_bmap<NP>(m20, A2, X0, s_piv, 1.0, k2lo, k2hi, ok ? c0lo : 0, ok ? c0hi : C::CT);
                     acc_load<NP>(t, A1);
-                    gemm_acc<NP, false, false>(t, A0, X2, -1.0, k0lo, k0hi, ok ? c2lo : 0, ok ? c2hi : C::CT);
+                    gemm_acc_bmap<NP>(t, A0, X2, s_piv, -1.0, k0lo, k0hi, ok ? c2lo : 0, ok ? c2hi : C::CT);
                     acc_sub(t, m20);
                     acc_store<NP>(t, A1);
                     acc_load<NP>(t, A1h);
@@ -115,15 +114,15 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
                 Acc<NP> m00, m22;
                 acc_zero(m00);
                 acc_zero(m22);
-                gemm_acc<NP, false, false>(m00, A0, X0, -1.0, k0lo, k0hi, ok ? c0lo : 0, ok ? c0hi : C::CT);
-                gemm_acc<NP, false, false>(m22, A2, X2, -1.0, k2lo, k2hi, ok ? c2lo : 0, ok ? c2hi : C::CT);
+                gemm_acc_bmap<NP>(m00, A0, X0, s_piv, -1.0, k0lo, k0hi, ok ? c0lo : 0, ok ? c0hi : C::CT);
+                gemm_acc_bmap<NP>(m22, A2, X2, s_piv, -1.0, k2lo, k2hi, ok ? c2lo : 0, ok ? c2hi : C::CT);
                 __syncthreads();  // every warp is done reading A0, A2
                 acc_store<NP>(m00, A0);
                 acc_store<NP>(m22, A2);
                 __syncthreads();
-                a0n = norm1<NP>(A0, n, s_red);
+                a0n = norm1_fast<NP>(A0, s_red);
                 if (a0n < p.tol) {
-                    a2n = norm1<NP>(A2, n, s_red);
+                    a2n = norm1_fast<NP>(A2, s_red + 4 * NP);
                     if (a2n < p.tol) {
                         converged = true;
                         break;
@@ -136,40 +135,39 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
             if (!converged) {
                 status |= GECON_ST_CR_NOT_CONVERGED;
                 if (p.norms) {  // diagnostics of the numpy twin's failure tuple (cycle_reduction.py:101-109)
+                    __syncthreads();  // norm1_fast has no trailing barrier
                     a2n = norm1<NP>(A2, n, s_red);
                     a1n = norm1<NP>(A1, n, s_red);
                 }
             }
         }
 
-        // ---- T = -A1hat^-1 A (cycle_reduction.py:181), or T = -B^-1 A for backward-looking models; 0 if not converged
+        // ---- T = -A1hat^-1 A (cycle_reduction.py:181), or T = -B^-1 A for backward-looking models; 0 if not converged.
+        // The iterated A0, A1, A2 are dead from here on: the A0 tile takes A again, A1 takes B, A2 takes C.
+        tile_load<NP>(A0, gA, n, n, n);
+        tile_zero<NP>(X0);
+        __syncthreads();
         if (converged || !gC) {
-            tile_copy<NP>(W, A1h);  // backward looking: A1h == B
-            tile_load<NP>(X0, gA, n, n, n);
-            __syncthreads();
-            const bool ok = gj_solve<NP>(W, X0, lo0, hi0, nullptr, 0, 0, n, s_piv, s_inv);
+            const bool ok = gj_solve_blocked<NP>(A1h, W, A0, X0, c0lo, c0hi, nullptr, nullptr, 0, 0, n, true, s_piv, s_flag);  // backward looking: A1h == B
             if (!ok) {
                 status |= GECON_ST_SINGULAR;
                 tile_nanfill<NP>(X0, n, n);
             } else {
                 for (int i = threadIdx.x; i < C::TILE; i += C::NT) X0[i] = -X0[i];
             }
-        } else {
-            tile_zero<NP>(X0);
         }
         double* Tt = X0;
         __syncthreads();
 
-        // ---- CT = C T (A0 tile), W = B + CT, R = -W^-1 D (shared.py:74-75)
+        // ---- CT = C T (A1hat tile), W = B + CT, R = -W^-1 D (shared.py:74-75)
         if (gC) tile_load<NP>(A2, gC, n, n, n);
         tile_load<NP>(A1, gB, n, n, n);
-        tile_load<NP>(A1h, gA, n, n, n);
         __syncthreads();
         {
             Acc<NP> ct;
             acc_zero(ct);
             if (gC) gemm_acc<NP, false, false>(ct, A2, Tt, 1.0, (status & GECON_ST_SINGULAR) ? 0 : k2lo, (status & GECON_ST_SINGULAR) ? NP : k2hi);
-            acc_store<NP>(ct, A0);
+            acc_store<NP>(ct, A1h);
         }
         __syncthreads();
         // One solve with W for both right-hand sides: D (-> R) and, for the Blanchard-Kahn certificate, the non-zero
@@ -177,11 +175,11 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
         const bool want_cert = p.lead_idx && gC && converged && !(status & GECON_ST_SINGULAR);
         bool have_F = false;
         if ((gD && p.R) || want_cert) {
-            for (int i = threadIdx.x; i < C::TILE; i += C::NT) W[i] = A1[i] + A0[i];
+            for (int i = threadIdx.x; i < C::TILE; i += C::NT) W[i] = A1[i] + A1h[i];
             const int kd = (gD && p.R) ? k : 0;
             if (kd) tile_load<NP>(X2, gD, n, k, k);
             __syncthreads();
-            const bool ok = gj_solve<NP>(W, X2, 0, kd, A2, want_cert ? lo2 : 0, want_cert ? hi2 : 0, n, s_piv, s_inv);
+            const bool ok = gj_solve_blocked<NP>(W, W, X2, X2, 0, (kd + 7) >> 3, A2, A2, want_cert ? c2lo : 0, want_cert ? c2hi : 0, n, true, s_piv, s_flag);
             if (!ok) {
                 status |= GECON_ST_SINGULAR;
                 if (kd) tile_nanfill<NP>(X2, n, k);
@@ -194,9 +192,9 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
         // ---- residual sum((A + B T + (C T) T)^2) in solver order (statespace.py:213)
         {
             Acc<NP> e;
-            acc_load<NP>(e, A1h);
+            acc_load<NP>(e, A0);
             gemm_acc<NP, false, false>(e, A1, Tt, 1.0);
-            gemm_acc<NP, false, false>(e, A0, Tt, 1.0);
+            gemm_acc<NP, false, false>(e, A1h, Tt, 1.0);
             double ss = 0.0;
 #pragma unroll
             for (int ct = 0; ct < C::CT; ++ct) ss += e.v[ct][0] * e.v[ct][0] + e.v[ct][1] * e.v[ct][1];

@@ -145,6 +145,36 @@ __device__ double norm1(const double* __restrict__ M, int n, double* __restrict_
     return mx;
 }
 
+// norm1 for full tiles whose padding rows and columns are zero, all 4 NP threads busy: four partial column sums per
+// column, then an exact max of the (non-negative) sums through redux.sync on their bit patterns; NaN-propagating.
+// s_red: 4 NP doubles.  One barrier; NO trailing barrier: a barrier must separate two uses of the same s_red.
+template <int NP>
+__device__ __forceinline__ double norm1_fast(const double* __restrict__ M, double* __restrict__ s_red) {
+    constexpr int LD = Cfg<NP>::LD, RP = NP / 4, CH = Cfg<NP>::CH;
+    const int part = threadIdx.x / NP, c = threadIdx.x - part * NP;
+    const double* col = M + part * RP * LD + c;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < RP; ++i) s += fabs(col[i * LD]);
+    s_red[threadIdx.x] = s;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    unsigned long long key = 0ull;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        const int cc = lane + 32 * ch;
+        if (cc < NP) {
+            const double v = (s_red[cc] + s_red[NP + cc]) + (s_red[2 * NP + cc] + s_red[3 * NP + cc]);
+            const unsigned long long kk = (unsigned long long)__double_as_longlong(fabs(v));
+            key = kk > key ? kk : key;
+        }
+    }
+    const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, (khi == mhi) ? klo : 0u);
+    return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+}
+
 // ------------------------------------------------------------------------------------------------ linear solve
 // Gauss-Jordan elimination with implicit partial pivoting: X = M^{-1} [R1 | R2], in place in the column ranges
 // [lo1, hi1) of R1 and [lo2, hi2) of R2 (columns outside the ranges are not touched: callers pass the range that
@@ -289,6 +319,237 @@ __device__ bool gj_solve(double* M, double* R1, int lo1, int hi1, double* R2, in
         }
     }
     __syncthreads();
+    return true;
+}
+
+// acc += sign * A * B[bmap[.], :]: like gemm_acc<NP, false, false>, but row k of the B operand is read from row bmap[k]
+// of the tile.  Lets the products of the cycle-reduction step consume the row-permuted output of gj_solve_blocked
+// (solution row k lives in row piv[k]) without an un-permutation pass.
+template <int NP>
+__device__ __forceinline__ void gemm_acc_bmap(Acc<NP>& acc, const double* __restrict__ A, const double* __restrict__ B,
+                                              const int* __restrict__ bmap, double sign, int klo, int khi, int ct_lo, int ct_hi) {
+    constexpr int LD = Cfg<NP>::LD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int r = warp * 8 + g;
+    for (int k0 = klo; k0 < khi; k0 += 4) {
+        const double a = sign * A[r * LD + k0 + q];
+        const double* brow = B + bmap[k0 + q] * LD + g;
+#pragma unroll
+        for (int ct = 0; ct < NP / 8; ++ct) {
+            if (ct >= ct_lo && ct < ct_hi) dmma884(acc.v[ct][0], acc.v[ct][1], a, brow[ct * 8]);
+        }
+    }
+}
+
+// Blocked Gauss-Jordan elimination with partial pivoting, panels of 8 columns, trailing updates on the fp64 tensor
+// path:  X = M^-1 [R1 | R2] for the 8-column tiles [c1lo, c1hi) of R1 and [c2lo, c2hi) of R2.
+//
+// Block step kb (columns J = [8 kb, 8 kb + 8)):
+//   panel   warp 0, lane = row (two rows per lane for NP > 32), the row's 8 panel entries in registers.  In-place
+//           Gauss-Jordan inversion of the panel: for each column the pivot is the entry of largest magnitude among the
+//           rows not used yet (lowest row on ties: the row getrf picks), found with redux.sync; the pivot row travels
+//           by shuffles.  Rows are never swapped.  The panel ends up holding W (n x 8) with
+//               new_row_i = [i not a pivot row of this panel] old_row_i + sum_a W[i][a] old_row_{piv[8 kb + a]}
+//           (W = -multipliers for ordinary rows, the inverse of the 8 x 8 pivot block for the pivot rows).
+//   update  every warp, its 8-row strip: that formula as one DMMA product with k = 8 for every live column tile
+//           (tiles of M to the right of the panel, the right-hand-side tiles); pivot rows are gathered through piv[].
+// Three barriers per block step instead of one per column, and the O(n^3) work moves from load/DFMA/store triples to
+// mma.sync.  The first step may read from a different set of tiles than it writes (Ms/R1s/R2s -> Md/R1d/R2d: no
+// copy of the inputs is needed, and that step needs no barrier between reading and writing); the remaining steps work
+// in place in the destination tiles.  On exit M is destroyed and solution row j is in row piv[j] of the right-hand-
+// side tiles (piv -> s_piv); with `unpermute` the rows are moved to their natural positions.  Destination columns
+// outside the tile ranges are not written.  Returns false on a zero / non-finite pivot (caller NaN-fills, as the
+// reference's _solve_gen does).  Contains barriers: every thread of the CTA must call it with identical arguments.
+// s_piv: NP ints, s_flag: NP + 1 ints.
+// reciprocal to <= 1 ulp: MUFU.RCP64H seed + three Newton steps (the pivots only need a consistent, accurate 1/x;
+// IEEE division's special-case handling is not wanted inside the elimination's critical path)
+__device__ __forceinline__ double rcp_nr(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+template <int NP>
+__device__ __noinline__ bool gj_solve_blocked(const double* Ms, double* Md, const double* R1s, double* R1d, int c1lo, int c1hi,
+                                              const double* R2s, double* R2d, int c2lo, int c2hi, int n, bool unpermute,
+                                              int* __restrict__ s_piv, int* __restrict__ s_flag) {
+    constexpr int LD = Cfg<NP>::LD, CT = Cfg<NP>::CT, RPL = (NP + 31) / 32, NW = Cfg<NP>::NW;
+    constexpr unsigned IDXBITS = (RPL == 1) ? 5u : 6u, IDXMASK = (1u << IDXBITS) - 1u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int nblk = (n + 7) >> 3;
+    bool used[RPL];
+#pragma unroll
+    for (int h = 0; h < RPL; ++h) used[h] = (lane + 32 * h >= n);
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int c0 = 8 * kb;
+        const bool first = (kb == 0);
+        const double* Mc = first ? Ms : Md;
+        // ------------------------------------------------------------------------------------------ panel (warp 0)
+        if (warp == 0) {
+            const int jmax = min(8, n - c0);
+            double a[RPL][8];
+            bool inP[RPL];
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) {
+                const int i = lane + 32 * h;
+                inP[h] = false;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    double2 t = make_double2(0.0, 0.0);
+                    if (i < NP) t = *reinterpret_cast<const double2*>(Mc + i * LD + c0 + c);
+                    a[h][c] = t.x;
+                    a[h][c + 1] = t.y;
+                }
+            }
+            unsigned fail = 0u;
+            int myr = 0;  // lane jj keeps the pivot row of panel column jj (0 for padding columns: any valid row)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                if (jj < jmax) {  // warp-uniform
+                    // pivot = largest |.| among the rows not used yet, lowest row on ties.  One redux on a 32-bit key:
+                    // the high word of |x| (sign, exponent, 20 - IDXBITS leading mantissa bits: candidates closer than
+                    // ~2^-14 relative count as tied) above the complemented row index.
+                    unsigned key = 0u;
+                    double invo[RPL];
+#pragma unroll
+                    for (int h = 0; h < RPL; ++h) {
+                        const unsigned kk = ((unsigned)__double2hiint(fabs(a[h][jj])) & ~IDXMASK) | (IDXMASK - (unsigned)(lane + 32 * h));
+                        key = max(key, used[h] ? 0u : kk);
+                        invo[h] = rcp_nr(a[h][jj]);  // every row's own reciprocal, off the pivot search's critical path
+                    }
+                    const unsigned best = __reduce_max_sync(0xffffffffu, key);
+                    const int r = (int)(IDXMASK - (best & IDXMASK));
+                    fail |= ((best >> IDXBITS) == 0u || best >= 0x7ff00000u) ? 1u : 0u;  // zero / subnormal / inf / NaN pivot
+                    const int rl = r & 31;
+                    double inv = invo[0];
+                    if constexpr (RPL == 2) inv = (r >= 32) ? invo[1] : inv;
+                    inv = __shfl_sync(0xffffffffu, inv, rl);
+                    double pr[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c != jj) {
+                            double v = a[0][c];
+                            if constexpr (RPL == 2) v = (r >= 32) ? a[1][c] : v;
+                            pr[c] = __shfl_sync(0xffffffffu, v, rl);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < RPL; ++h) {
+                        const bool is_r = (lane + 32 * h == r);
+                        // pivot row: a[c] <- pr[c] * inv, a[jj] <- inv;  other rows: a[c] <- a[c] - m pr[c], a[jj] <- -m
+                        const double mm = is_r ? -inv : a[h][jj] * inv;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (c != jj) a[h][c] = fma(-mm, pr[c], is_r ? 0.0 : a[h][c]);
+                        }
+                        a[h][jj] = -mm;
+                        used[h] = used[h] || is_r;
+                        inP[h] = inP[h] || is_r;
+                    }
+                    if (lane == jj) myr = r;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) {
+                const int i = lane + 32 * h;
+                if (i < NP) {
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(Md + i * LD + c0 + c) = make_double2(a[h][c], a[h][c + 1]);
+                    s_flag[i] = inP[h] ? 1 : 0;
+                }
+            }
+            if (lane < 8) s_piv[c0 + lane] = myr;
+            if (lane == 0) s_flag[NP] = (int)fail;
+        }
+        __syncthreads();
+        if (s_flag[NP]) {
+            __syncthreads();
+            return false;
+        }
+        // ------------------------------------------------------------------------------------------ update (all warps)
+        const int r = warp * 8 + g;
+        const double a0 = Md[r * LD + c0 + q], a1 = Md[r * LD + c0 + 4 + q];
+        const int p0 = s_piv[c0 + q] * LD + g, p1 = s_piv[c0 + 4 + q] * LD + g;
+        const bool keep = (s_flag[r] == 0);
+        const int ro = r * LD + 2 * q;
+        const double* R1c = first ? R1s : R1d;
+        const double* R2c = first ? R2s : R2d;
+        double accM[CT][2], acc1[CT][2], acc2[CT][2];
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) {
+            if (ct > kb && ct < nblk) {
+                double2 o = make_double2(0.0, 0.0);
+                if (keep) o = *reinterpret_cast<const double2*>(Mc + ro + ct * 8);
+                accM[ct][0] = o.x;
+                accM[ct][1] = o.y;
+                dmma884(accM[ct][0], accM[ct][1], a0, Mc[p0 + ct * 8]);
+                dmma884(accM[ct][0], accM[ct][1], a1, Mc[p1 + ct * 8]);
+            }
+            if (ct >= c1lo && ct < c1hi) {
+                double2 o = make_double2(0.0, 0.0);
+                if (keep) o = *reinterpret_cast<const double2*>(R1c + ro + ct * 8);
+                acc1[ct][0] = o.x;
+                acc1[ct][1] = o.y;
+                dmma884(acc1[ct][0], acc1[ct][1], a0, R1c[p0 + ct * 8]);
+                dmma884(acc1[ct][0], acc1[ct][1], a1, R1c[p1 + ct * 8]);
+            }
+            if (ct >= c2lo && ct < c2hi) {
+                double2 o = make_double2(0.0, 0.0);
+                if (keep) o = *reinterpret_cast<const double2*>(R2c + ro + ct * 8);
+                acc2[ct][0] = o.x;
+                acc2[ct][1] = o.y;
+                dmma884(acc2[ct][0], acc2[ct][1], a0, R2c[p0 + ct * 8]);
+                dmma884(acc2[ct][0], acc2[ct][1], a1, R2c[p1 + ct * 8]);
+            }
+        }
+        // in place: every warp must have read the pivot rows before anybody overwrites them
+        const bool oop = first && Ms != Md && (c1lo >= c1hi || R1s != R1d) && (c2lo >= c2hi || R2s != R2d);
+        if (!oop) __syncthreads();
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) {
+            if (ct > kb && ct < nblk) *reinterpret_cast<double2*>(Md + ro + ct * 8) = make_double2(accM[ct][0], accM[ct][1]);
+            if (ct >= c1lo && ct < c1hi) *reinterpret_cast<double2*>(R1d + ro + ct * 8) = make_double2(acc1[ct][0], acc1[ct][1]);
+            if (ct >= c2lo && ct < c2hi) *reinterpret_cast<double2*>(R2d + ro + ct * 8) = make_double2(acc2[ct][0], acc2[ct][1]);
+        }
+        __syncthreads();
+    }
+    if (unpermute) {
+        // X[j] = rows[piv[j]]: rows j = warp + e * NW (e < 8 covers NP rows), through registers
+        constexpr int CH = Cfg<NP>::CH;
+        const int w1 = 8 * (c1hi - c1lo), w2 = 8 * (c2hi - c2lo);
+        double x1[8][CH], x2[8][CH];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = warp + e * NW;
+            const int pr = (j < n) ? s_piv[j] : 0;
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+                const int c = lane + 32 * ch;
+                x1[e][ch] = (j < n && c < w1) ? R1d[pr * LD + 8 * c1lo + c] : 0.0;
+                x2[e][ch] = (j < n && c < w2) ? R2d[pr * LD + 8 * c2lo + c] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = warp + e * NW;
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+                const int c = lane + 32 * ch;
+                if (j < NP && c < w1) R1d[j * LD + 8 * c1lo + c] = x1[e][ch];
+                if (j < NP && c < w2) R2d[j * LD + 8 * c2lo + c] = x2[e][ch];
+            }
+        }
+        __syncthreads();
+    }
     return true;
 }
 
