@@ -68,8 +68,23 @@ static int check_kf_args(const gecon_kalman_args* a) {
 #define GECON_KF_DECL(NPV) int launch_kf_##NPV(const gecon_kalman_args& a, cudaStream_t st, int* info);
 GECON_KF_DECL(8) GECON_KF_DECL(16) GECON_KF_DECL(24) GECON_KF_DECL(32) GECON_KF_DECL(40) GECON_KF_DECL(48) GECON_KF_DECL(56)
 #undef GECON_KF_DECL
+int launch_kw_8(const gecon_kalman_args& a, cudaStream_t st, int* info);
+int launch_kw_16(const gecon_kalman_args& a, cudaStream_t st, int* info);
+int launch_kw_24(const gecon_kalman_args& a, cudaStream_t st, int* info);
+
+// padded dimension of the warp-per-draw kernel (needs a spare column for the mean), or 0 when the CTA kernel must run
+static int warp_kernel_np(const gecon_kalman_args& a) {
+    if (!a.obs_idx || a.Z) return 0;  // dense design matrices stay on the CTA kernel
+    const int np = round_up8((a.n + 1) > a.k ? (a.n + 1) : a.k);
+    return np <= 24 ? np : 0;
+}
 
 static int launch_kf(int np, const gecon_kalman_args& a, cudaStream_t st, int* info) {
+    switch (warp_kernel_np(a)) {
+        case 8: return launch_kw_8(a, st, info);
+        case 16: return launch_kw_16(a, st, info);
+        case 24: return launch_kw_24(a, st, info);
+    }
     switch (np) {
         case 8: return launch_kf_8(a, st, info);
         case 16: return launch_kf_16(a, st, info);
@@ -105,6 +120,8 @@ int kf_kernel_info(int n, int p, int Tobs, int* ctas, int* smem, int* threads) {
     a.p = p;
     a.Tobs = Tobs;
     a.N = 1 << 30;
+    static const int32_t dummy_obs = 0;
+    a.obs_idx = &dummy_obs;  // info for the selector path (the one the pipeline uses)
     int info[3] = {0, 0, 0};
     int rc = launch_kf(round_up8(n), a, nullptr, info);
     if (rc) return rc;
