@@ -32,8 +32,8 @@ static int launch_one(const gecon_kalman_args& a, cudaStream_t st, int* info) {
 }
 
 // one warp per draw (kalman_warp.cuh): selector Z, n + 1 <= NP <= 24
-template <int NP, int PT>
-static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* info) {
+template <int NP, int PT, int MINB>
+static int launch_one_warp_b(const gecon_kalman_args& a, cudaStream_t st, int* info) {
     using S = KwSmem<NP, PT>;
     const size_t smem = S::bytes(a.Tobs);
     if (smem > 227 * 1024) {
@@ -41,7 +41,7 @@ static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* inf
         return GECON_E_UNSUPPORTED_SIZE;
     }
     int grid = 0, per_sm = 0;
-    int rc = persistent_grid(kalman_ll_warp_kernel<NP, PT>, S::WPC * 32, smem, (a.N + S::WPC - 1) / S::WPC, &grid, &per_sm);
+    int rc = persistent_grid(kalman_ll_warp_kernel<NP, PT, MINB>, S::WPC * 32, smem, (a.N + S::WPC - 1) / S::WPC, &grid, &per_sm);
     if (rc) return rc;
     if (info) {
         info[0] = per_sm;
@@ -49,10 +49,17 @@ static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* inf
         info[2] = S::WPC * 32;
         return 0;
     }
-    kalman_ll_warp_kernel<NP, PT><<<grid, S::WPC * 32, smem, st>>>(a);
+    kalman_ll_warp_kernel<NP, PT, MINB><<<grid, S::WPC * 32, smem, st>>>(a);
     g_launch_count++;
     GECON_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int NP, int PT>
+static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* info) {
+    // resident CTAs the register allocator must leave room for: 4 x 4 warps per SM up to NP = 16 (measured: 128 registers
+    // with the constant term in shared memory beats 168 registers and 3 CTAs), 2 CTAs at NP = 24
+    return launch_one_warp_b<NP, PT, (NP <= 16 ? 4 : 2)>(a, st, info);
 }
 
 #define GECON_CAT2(a, b) a##b

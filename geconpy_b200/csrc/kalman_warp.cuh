@@ -11,12 +11,13 @@
 //      form (p x p, registers);  lane i: row i of P Z', of K = P Z' F^-1, of M = K G / 2 - P Z', filtered mean a+_i
 //   2  P+ = P + [K | M | a+] [M | K | e_n]'  as ONE DMMA product with k = 2p + 1 on the accumulators that still hold P
 //      from the previous step (the expanded Joseph form P + K M' + M K'; the extra column drops a+ into the spare
-//      column n of P+, so the next product also propagates the mean);  + jitter on the diagonal
+//      column n of P+, so the next product also propagates the mean);  the jitter on the diagonal of P+ is carried
+//      by the constant term of phase 4 (R Q R' + jitter T T')
 //   3  W = T [P+ | a+]      (DMMA; T fragments live in registers for the whole draw)
 //   4  P = R Q R' + W T'    (DMMA; R Q R' in registers for NP <= 16)
 // P, W and the [K | M] panel go through the warp's private shared-memory tiles only to change fragment layout
-// (accumulator -> A/B operand), four __syncwarp per step.  P is symmetrised lazily: its readers in phase 1 average
-// P_ij and P_ji.
+// (accumulator -> A/B operand), four __syncwarp per step.  P is not symmetrised explicitly: the update term is
+// symmetric, and the rounding-level antisymmetric part of W T' is contracted by the next T . T' (rho(T) < 1).
 #pragma once
 #include "kalman.cuh"
 
@@ -25,17 +26,16 @@ namespace gecon {
 template <int PT>
 struct KmCfg {
     static constexpr int KS2 = (2 * PT + 1 + 3) / 4;            // k-steps of the rank-(2p+1) update
-    static constexpr int KMS = ((4 * KS2 + 3) / 8) * 8 + 4;     // row stride of the [K|M|a+] panel, = 4 (mod 8): conflict-free
+    static constexpr int KW = 4 * KS2;                          // rows of the (transposed) panels [K|M|a+]', [M|K|e_n]'
 };
 
 template <int NP, int PT>
 struct KwSmem {
     static constexpr int WPC = 4;  // warps (= draws in flight) per CTA
     static constexpr int TILE = Cfg<NP>::TILE;
-    static constexpr int KMS = KmCfg<PT>::KMS;
-    static constexpr int KM2 = 2 * NP * KMS;                       // KM and MK panels
+    static constexpr int KM2 = 2 * KmCfg<PT>::KW * Cfg<NP>::LD;    // KM and MK panels, stored transposed: [k][LD]
     static constexpr int ALIAS = KM2 > TILE ? KM2 : TILE;          // the Lyapunov scratch tile shares their storage
-    static constexpr bool C0_REGS = (NP <= 16);
+    static constexpr bool C0_REGS = (NP <= 8);   // R Q R' + jitter T T' in registers, else in a shared-memory tile
     static constexpr bool GM_REGS = (PT <= 4);                      // G = Z P Z' + H in registers, else in shared memory
     static constexpr int PER_WARP = 2 * TILE + ALIAS + (C0_REGS ? 0 : TILE) + NP + (GM_REGS ? 0 : PMAX * PMAX);  // doubles (even)
     static size_t bytes(int Tobs) {
@@ -117,16 +117,11 @@ __device__ __forceinline__ void warp_tile_load(double* __restrict__ dst, const d
     }
 }
 
-template <int NP, int PT>
-constexpr int kw_min_ctas() {
-    return NP <= 16 ? 4 : 2;
-}
-
-template <int NP, int PT>
-__global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>()) kalman_ll_warp_kernel(const gecon_kalman_args p) {
+template <int NP, int PT, int MINB>
+__global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, MINB) kalman_ll_warp_kernel(const gecon_kalman_args p) {
     using S = KwSmem<NP, PT>;
     constexpr int LD = Cfg<NP>::LD, TILE = Cfg<NP>::TILE, NS = NP / 8, KSN = NP / 4;
-    constexpr int KS2 = KmCfg<PT>::KS2, KMS = KmCfg<PT>::KMS, WPC = S::WPC;
+    constexpr int KS2 = KmCfg<PT>::KS2, KW = KmCfg<PT>::KW, WPC = S::WPC;
     constexpr bool C0_REGS = S::C0_REGS;
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -138,8 +133,8 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>(
     double* P = wb0;
     double* W = P + TILE;
     double* Aw = W + TILE;          // Lyapunov scratch; afterwards the same storage holds the two panels
-    double* KM = Aw;                // [NP][KMS]  K | M | a+
-    double* MK = KM + NP * KMS;     // [NP][KMS]  M | K | e_n
+    double* KM = Aw;                // [KW][LD]  rows: K' | M' | a+'   (transposed: lane i writes column i, conflict-free)
+    double* MK = KM + KW * LD;      // [KW][LD]  rows: M' | K' | e_n'
     double* C0t = Aw + S::ALIAS;    // R Q R' (only when it does not live in registers)
     double* s_q = C0t + (C0_REGS ? 0 : TILE);
     double* s_G = s_q + NP;         // [PT][PT] when it does not live in registers
@@ -219,12 +214,25 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>(
                 for (int c = 0; c < k; ++c) s = fma(W[lo * LD + c] * s_q[c], W[hi * LD + c], s);
             }
             P[idx] = s;
-            if constexpr (!C0_REGS) C0t[idx] = s;
         }
         __syncwarp();
+        // c0 = R Q R' + jitter T T': the jitter added to the diagonal of every filtered covariance, carried through the
+        // prediction once per draw instead of once per step  (T (P+ + jitter I) T' = T P+ T' + jitter T T')
         WAcc<NP> pacc, c0;
         wacc_load<NP>(pacc, P, lane);
-        if constexpr (C0_REGS) c0 = pacc;
+        {
+            WAcc<NP> tt;
+            wacc_zero(tt);
+            wgemm<NP, true>(tt, Aw, Aw, nks, lane);
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int ct = 0; ct < NS; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) tt.v[s][ct][e] = fma(jitter, tt.v[s][ct][e], pacc.v[s][ct][e]);
+            if constexpr (C0_REGS) c0 = tt;
+            else wacc_store<NP>(tt, C0t, lane);
+        }
 
         // ---- P0
         if (p.P0) {
@@ -283,10 +291,10 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>(
                 const int r = 8 * s + g, c = 4 * ks + q;
                 tA[s][ks] = (r < n && c < n) ? gT[(size_t)r * n + c] : 0.0;
             }
-        for (int i = lane; i < 2 * NP * KMS; i += 32) KM[i] = 0.0;
+        for (int i = lane; i < 2 * KW * LD; i += 32) KM[i] = 0.0;
         if (lane < NP) W[lane * LD + n] = 0.0;
         __syncwarp();
-        if (lane == 0) MK[n * KMS + 2 * PT] = 1.0;
+        if (lane == 0) MK[2 * PT * LD + n] = 1.0;
         __syncwarp();
 
         double ll_acc = 0.0, quad_acc = 0.0, detprod = 1.0;
@@ -301,13 +309,13 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>(
 #pragma unroll
             for (int a = 0; a < PT; ++a) {
                 const bool ob = (wb >> a) & 1;
-                const double s = 0.5 * (P[obs_r[a] * LD + il] + P[il * LD + obs_r[a]]);
+                const double s = P[obs_r[a] * LD + il];
                 pz[a] = ob ? s : 0.0;
                 const double za = W[obs_r[a] * LD + n];
                 v[a] = (ob ? y[a] : 0.0) - (dv0[a] + (ob ? za : 0.0));
 #pragma unroll
                 for (int b = 0; b <= a; ++b) {
-                    double x = 0.5 * (P[obs_r[a] * LD + obs_r[b]] + P[obs_r[b] * LD + obs_r[a]]);
+                    double x = P[obs_r[a] * LD + obs_r[b]];
                     x = (ob && ((wb >> b) & 1)) ? x : 0.0;
                     if (a == b) x += ob ? hv[a] : 0.0;
                     if constexpr (GM_REGS) {
@@ -360,12 +368,14 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>(
                     ll_acc += llt;
                     if (lane == 0) p.ll_t[(size_t)draw * Tobs + t] = llt;
                 } else if (wb != 0) {
-                    int e;
-                    detprod *= frexp(det, &e);
-                    det_exp += e;
+                    // det = m 2^e, m in [0.5, 1) (det > 0 and normal, else the draw is flagged not-PD anyway)
+                    const int hi = __double2hiint(det);
+                    det_exp += ((hi >> 20) & 0x7ff) - 1022;
+                    detprod *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(det));
                     quad_acc += quad;
                     ++n_ll_steps;
                     if ((t & 31) == 31) {
+                        int e;
                         detprod = frexp(detprod, &e);
                         det_exp += e;
                     }
@@ -390,20 +400,20 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>(
 #pragma unroll
                 for (int a = 0; a < PT; ++a) af = fma(x[a], v[a], af);
                 if (rowlane) {
-                    double* km = KM + lane * KMS;
-                    double* mk = MK + lane * KMS;
+                    double* km = KM + lane;
+                    double* mk = MK + lane;
 #pragma unroll
                     for (int a = 0; a < PT; ++a) {
                         double kg = 0.0;
 #pragma unroll
                         for (int b = 0; b < PT; ++b) kg = fma(x[b], GM_REGS ? gm[b][a] : s_G[b * PT + a], kg);
                         const double m = fma(0.5, kg, -pz[a]);
-                        km[a] = x[a];
-                        km[PT + a] = m;
-                        mk[a] = m;
-                        mk[PT + a] = x[a];
+                        km[a * LD] = x[a];
+                        km[(PT + a) * LD] = m;
+                        mk[a * LD] = m;
+                        mk[(PT + a) * LD] = x[a];
                     }
-                    km[2 * PT] = af;
+                    km[2 * PT * LD] = af;
                 }
             }
             __syncwarp();
@@ -413,20 +423,13 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, kw_min_ctas<NP, PT>(
                 double a[NS], b[NS];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    a[s] = KM[(8 * s + g) * KMS + 4 * ks + q];
-                    b[s] = MK[(8 * s + g) * KMS + 4 * ks + q];
+                    a[s] = KM[(4 * ks + q) * LD + 8 * s + g];
+                    b[s] = MK[(4 * ks + q) * LD + 8 * s + g];
                 }
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
 #pragma unroll
                     for (int ct = 0; ct < NS; ++ct) dmma884(pacc.v[s][ct][0], pacc.v[s][ct][1], a[s], b[ct]);
-            }
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                if (8 * s + g < n) {
-                    if (g == 2 * q) pacc.v[s][s][0] += jitter;
-                    if (g == 2 * q + 1) pacc.v[s][s][1] += jitter;
-                }
             }
             wacc_store<NP>(pacc, P, lane);
             __syncwarp();
