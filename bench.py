@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- fp64 likelihood evaluations / second (solve + Kalman) on B200, and the CPU reference arm.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload nk|rbc|large] [--draws D] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload nk|rbc|large|large45] [--draws D] [--impl reference]
 
 One "step" = one pass of the hot path (theta -> A,B,C,D -> cycle reduction -> R, residual -> Blanchard-Kahn count ->
 P0 -> Kalman log-likelihood over T_obs = 200 -> gating) over the whole population of draws of the workload.
 Workloads are BASELINE.json's configs: ``nk`` = medium New-Keynesian model (full_nk, n = 24, k = 4, p = 3) with
 262,144 draws per GPU -- the config the north-star target is quoted on and the default; ``rbc`` = RBC, 65,536 draws;
-``large`` = nk_complete_more_shocks (n = 31, k = 9, p = 7), 131,072 draws per GPU.  Draws shard across ranks with no
+``large`` = nk_complete_more_shocks (n = 31, k = 9, p = 7), 131,072 draws per GPU; ``large45`` = its synthetic 45-state
+composition with rbc_extended (config 4b).  Draws shard across ranks with no
 data-path collective; for N > 1 each step ends with the SMC-stage all-gather of the log-likelihoods (NCCL).
 
 Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU restatement of the reference path (oracle/, all
@@ -44,6 +45,9 @@ WORKLOADS = {
                desc="medium NK full_nk (n=24,k=4,p=3), Sobol draws in +-10% boxes around defaults, T_obs=200"),
     "large": dict(model="nk_complete_more_shocks", observed=["Y", "C", "I", "N", "pi", "i", "w"], meas=[], draws=131072, tobs=200,
                   width=0.05, desc="large NK nk_complete_more_shocks (n=31,k=9,p=7), Sobol draws in +-5% boxes, T_obs=200"),
+    "large45": dict(model="nk_rbc_composite", observed=["Y", "C", "I", "N", "pi", "i", "w"], meas=[], draws=131072, tobs=200,
+                    width=0.05, desc="synthetic 45-state composite nk_complete_more_shocks (+) rbc_extended (n=45,k=13,p=7; SURVEY 8d config 4b), "
+                                     "Sobol draws in +-5% boxes, T_obs=200"),
 }
 SIGMA_SHOCK = 0.01
 SIGMA_ERR = 1e-3

@@ -20,11 +20,11 @@ namespace gecon {
 
 template <int NP>
 struct BkSmem {
-    static constexpr size_t bytes = sizeof(double) * (3 * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (2 * NP + 4);
+    static constexpr size_t bytes = sizeof(double) * (3 * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (3 * NP + 8);
 };
 
 template <int NP>
-__global__ void __launch_bounds__(Cfg<NP>::NT) bk_count_kernel(const gecon_bk_args p) {
+__global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk_args p) {
     using C = Cfg<NP>;
     constexpr int LD = C::LD, NT = C::NT;
     extern __shared__ __align__(16) double sm[];
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) bk_count_kernel(const gecon_bk_ar
     double* s_red = s_inv + NP;
     int* s_piv = reinterpret_cast<int*>(s_red + NP);
     int* s_sel = s_piv + NP;
+    int* s_flag = s_sel + NP;  // [NP + 1]
 
     const int n = p.n, nl = p.n_lead, m = n + nl;
     const int cap = p.max_iter > 0 ? p.max_iter : 60;
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) bk_count_kernel(const gecon_bk_ar
             X[i] = xv;
         }
         __syncthreads();
-        bool ok = gj_solve<NP>(W, X, 0, m, nullptr, 0, 0, m, s_piv, s_inv);
+        const int mt = (m + 7) >> 3;
+        bool ok = gj_solve_blocked<NP>(W, W, X, X, 0, mt, nullptr, nullptr, 0, 0, m, true, s_piv, s_flag, s_inv);
         tile_copy<NP>(S, X);
         __syncthreads();
 
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) bk_count_kernel(const gecon_bk_ar
                 X[i] = (r == c && r < m) ? 1.0 : 0.0;
             }
             __syncthreads();
-            ok = gj_solve<NP>(W, X, 0, m, nullptr, 0, 0, m, s_piv, s_inv);
+            ok = gj_solve_blocked<NP>(W, W, X, X, 0, mt, nullptr, nullptr, 0, 0, m, true, s_piv, s_flag, s_inv);
             if (!ok) break;
             // determinant scaling: mu = |det S|^(-1/m) = exp(mean log |1/pivot|)
             double lg = ((int)threadIdx.x < m) ? log(fabs(s_inv[threadIdx.x])) : 0.0;
@@ -143,7 +145,7 @@ static int launch_bk(const gecon_bk_args& a, cudaStream_t st) {
 
 int bk_kernel_info(int m, int* ctas, int* smem, int* threads) {
     const int np = round_up8(m);
-    GECON_DISPATCH_NP(np, {
+    GECON_DISPATCH_NP_WIDE(np, {
         int grid = 0;
         int rc = persistent_grid(bk_count_kernel<NP_>, Cfg<NP_>::NT, BkSmem<NP_>::bytes, 1 << 30, &grid, ctas);
         if (rc) return rc;
@@ -174,7 +176,7 @@ extern "C" int gecon_bk_count_batched(const gecon_bk_args* args, void* stream) {
     if (rc) return rc;
     if (args->N == 0) return 0;
     const int np = round_up8(args->n + args->n_lead);
-    GECON_DISPATCH_NP(np, return launch_bk<NP_>(*args, (cudaStream_t)stream));
+    GECON_DISPATCH_NP_WIDE(np, return launch_bk<NP_>(*args, (cudaStream_t)stream));
     return 0;
 }
 

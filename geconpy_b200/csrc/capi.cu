@@ -27,11 +27,12 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) solve_kernel(const double* __rest
     double* Xt = W + C::TILE;
     double* s_inv = Xt + C::TILE;
     int* s_piv = reinterpret_cast<int*>(s_inv + NP);
+    int* s_flag = s_piv + NP;  // [NP + 1]
     for (long long draw = blockIdx.x; draw < N; draw += gridDim.x) {
         tile_load<NP>(W, M + (size_t)draw * n * n, n, n, n);
         tile_load<NP>(Xt, RHS + (size_t)draw * n * m, n, m, m);
         __syncthreads();
-        const bool ok = gj_solve<NP>(W, Xt, 0, m, nullptr, 0, 0, n, s_piv, s_inv);
+        const bool ok = gj_solve_blocked<NP>(W, W, Xt, Xt, 0, (m + 7) >> 3, nullptr, nullptr, 0, 0, n, true, s_piv, s_flag);
         if (!ok) {
             tile_nanfill<NP>(Xt, n, m);
             __syncthreads();
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT) solve_kernel(const double* __rest
 
 template <int NP>
 struct SolveSmem {
-    static constexpr size_t bytes = sizeof(double) * (2 * Cfg<NP>::TILE + NP) + sizeof(int) * NP;
+    static constexpr size_t bytes = sizeof(double) * (2 * Cfg<NP>::TILE + NP) + sizeof(int) * (2 * NP + 8);
 };
 
 // ------------------------------------------------------------------------------------------------ batched product
@@ -148,7 +149,7 @@ extern "C" int gecon_solve_batched(const double* M, const double* RHS, int64_t N
     }
     if (N == 0) return 0;
     const int np = round_up8(n);
-    GECON_DISPATCH_NP(np, return launch_solve<NP_>(M, RHS, N, n, m, X, status, (cudaStream_t)stream));
+    GECON_DISPATCH_NP_WIDE(np, return launch_solve<NP_>(M, RHS, N, n, m, X, status, (cudaStream_t)stream));
     return 0;
 }
 

@@ -78,8 +78,28 @@ struct DevBuf {
         case 40: { constexpr int NP_ = 40; __VA_ARGS__; } break; \
         case 48: { constexpr int NP_ = 48; __VA_ARGS__; } break; \
         case 56: { constexpr int NP_ = 56; __VA_ARGS__; } break; \
+        case 64: { constexpr int NP_ = 64; __VA_ARGS__; } break; \
         default:                                    \
-            set_last_error("unsupported matrix dimension (padded %d > 56)", np); \
+            set_last_error("unsupported matrix dimension (padded %d > 64)", np); \
+            return GECON_E_UNSUPPORTED_SIZE;        \
+    }
+
+// pencil dimensions of the Blanchard-Kahn count (n + n_lead) and the general solve: 3 / 2 tiles, up to 88
+#define GECON_DISPATCH_NP_WIDE(np, ...)             \
+    switch (np) {                                   \
+        case 8: { constexpr int NP_ = 8; __VA_ARGS__; } break;   \
+        case 16: { constexpr int NP_ = 16; __VA_ARGS__; } break; \
+        case 24: { constexpr int NP_ = 24; __VA_ARGS__; } break; \
+        case 32: { constexpr int NP_ = 32; __VA_ARGS__; } break; \
+        case 40: { constexpr int NP_ = 40; __VA_ARGS__; } break; \
+        case 48: { constexpr int NP_ = 48; __VA_ARGS__; } break; \
+        case 56: { constexpr int NP_ = 56; __VA_ARGS__; } break; \
+        case 64: { constexpr int NP_ = 64; __VA_ARGS__; } break; \
+        case 72: { constexpr int NP_ = 72; __VA_ARGS__; } break; \
+        case 80: { constexpr int NP_ = 80; __VA_ARGS__; } break; \
+        case 88: { constexpr int NP_ = 88; __VA_ARGS__; } break; \
+        default:                                    \
+            set_last_error("unsupported matrix dimension (padded %d > 88)", np); \
             return GECON_E_UNSUPPORTED_SIZE;        \
     }
 

@@ -22,9 +22,16 @@ __device__ __forceinline__ void acc_sub(Acc<NP>& a, const Acc<NP>& b) {
     }
 }
 
+// NP = 64: seven 34 KB tiles do not fit in 227 KB, so A1hat (touched once per iteration, by the warp that owns each
+// strip) lives in an L2-resident global workspace, one tile per CTA, allocated stream-ordered by the launcher.
+template <int NP>
+constexpr bool cr_a1h_global() {
+    return NP > 56;
+}
+
 template <int NP>
 struct CrSmem {
-    static constexpr int TILES = 7;
+    static constexpr int TILES = cr_a1h_global<NP>() ? 6 : 7;
     static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 8 * NP) + sizeof(int) * (4 * NP + 8);
 };
 
@@ -35,15 +42,15 @@ constexpr int cr_min_ctas() {
 }
 
 template <int NP>
-__global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kernel(const gecon_cr_args p) {
+__global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kernel(const gecon_cr_args p, double* __restrict__ ws) {
     using C = Cfg<NP>;
     constexpr int LD = C::LD;
     extern __shared__ __align__(16) double sm[];
     double* A0 = sm;
     double* A1 = A0 + C::TILE;
     double* A2 = A1 + C::TILE;
-    double* A1h = A2 + C::TILE;
-    double* W = A1h + C::TILE;
+    double* A1h = cr_a1h_global<NP>() ? ws + (size_t)blockIdx.x * C::TILE : A2 + C::TILE;
+    double* W = A2 + (cr_a1h_global<NP>() ? 1 : 2) * C::TILE;
     double* X0 = W + C::TILE;
     double* X2 = X0 + C::TILE;
     double* s_red = X2 + C::TILE;  // [8 NP]: two norm1_fast buffers
@@ -376,9 +383,13 @@ static int launch_cr(const gecon_cr_args& a, cudaStream_t st) {
     int grid = 0;
     int rc = persistent_grid(cr_solve_kernel<NP>, Cfg<NP>::NT, CrSmem<NP>::bytes, a.N, &grid, nullptr);
     if (rc) return rc;
-    cr_solve_kernel<NP><<<grid, Cfg<NP>::NT, CrSmem<NP>::bytes, st>>>(a);
+    double* ws = nullptr;
+    if (cr_a1h_global<NP>()) GECON_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)grid * Cfg<NP>::TILE, st));
+    cr_solve_kernel<NP><<<grid, Cfg<NP>::NT, CrSmem<NP>::bytes, st>>>(a, ws);
     g_launch_count++;
-    GECON_CUDA(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    if (ws) cudaFreeAsync(ws, st);
+    GECON_CUDA(le);
     return 0;
 }
 

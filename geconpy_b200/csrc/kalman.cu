@@ -66,7 +66,7 @@ static int check_kf_args(const gecon_kalman_args* a) {
 
 // defined in kalman_inst.cu (one translation unit per NP): launch, or only query occupancy when info != nullptr
 #define GECON_KF_DECL(NPV) int launch_kf_##NPV(const gecon_kalman_args& a, cudaStream_t st, int* info);
-GECON_KF_DECL(8) GECON_KF_DECL(16) GECON_KF_DECL(24) GECON_KF_DECL(32) GECON_KF_DECL(40) GECON_KF_DECL(48) GECON_KF_DECL(56)
+GECON_KF_DECL(8) GECON_KF_DECL(16) GECON_KF_DECL(24) GECON_KF_DECL(32) GECON_KF_DECL(40) GECON_KF_DECL(48) GECON_KF_DECL(56) GECON_KF_DECL(64)
 #undef GECON_KF_DECL
 int launch_kw_8(const gecon_kalman_args& a, cudaStream_t st, int* info);
 int launch_kw_16(const gecon_kalman_args& a, cudaStream_t st, int* info);
@@ -93,8 +93,9 @@ static int launch_kf(int np, const gecon_kalman_args& a, cudaStream_t st, int* i
         case 40: return launch_kf_40(a, st, info);
         case 48: return launch_kf_48(a, st, info);
         case 56: return launch_kf_56(a, st, info);
+        case 64: return launch_kf_64(a, st, info);
     }
-    set_last_error("unsupported matrix dimension (padded %d > 56)", np);
+    set_last_error("unsupported matrix dimension (padded %d > 64)", np);
     return GECON_E_UNSUPPORTED_SIZE;
 }
 

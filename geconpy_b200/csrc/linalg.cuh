@@ -20,7 +20,7 @@ namespace gecon {
 
 template <int NP>
 struct Cfg {
-    static_assert(NP % 8 == 0 && NP >= 8 && NP <= 64, "NP must be a multiple of 8 in [8, 64]");
+    static_assert(NP % 8 == 0 && NP >= 8 && NP <= 96, "NP must be a multiple of 8 in [8, 96]");
     static constexpr int LD = NP + 4;
     static constexpr int TILE = NP * LD;  // doubles per tile (even, so consecutive tiles stay 16-byte aligned)
     static constexpr int NW = NP / 8;     // warps per CTA
@@ -176,152 +176,6 @@ __device__ __forceinline__ double norm1_fast(const double* __restrict__ M, doubl
 }
 
 // ------------------------------------------------------------------------------------------------ linear solve
-// Gauss-Jordan elimination with implicit partial pivoting: X = M^{-1} [R1 | R2], in place in the column ranges
-// [lo1, hi1) of R1 and [lo2, hi2) of R2 (columns outside the ranges are not touched: callers pass the range that
-// holds the non-zero columns of the right-hand side, whose other solution columns are zero); M (n x n) is destroyed.  The pivot of column j is the entry of largest magnitude among the rows
-// not used yet (first index on ties) -- the row LAPACK's getrf picks -- so the result agrees with an LU solve to
-// rounding.  Rows are never swapped: the pivot row r_j and 1/pivot are recorded and the solution rows are
-// un-permuted and scaled at the end (X[j] = R[r_j] / pivot_j), through registers.
-// One barrier per column.  Returns false on a zero or non-finite pivot (caller NaN-fills, as the reference's
-// _solve_gen does).  Contains barriers: every thread of the CTA must call it with identical arguments.
-template <int NP>
-__device__ bool gj_solve(double* M, double* R1, int lo1, int hi1, double* R2, int lo2, int hi2, int n, int* __restrict__ s_piv,
-                         double* __restrict__ s_inv) {
-    constexpr int LD = Cfg<NP>::LD, NW = Cfg<NP>::NW, CH = Cfg<NP>::CH;
-    constexpr int SL = (3 * NP + 31) / 32;  // slots per lane over the concatenated live columns [M | R1 | R2]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w1 = hi1 - lo1, w2 = hi2 - lo2;
-    // R1 / R2 live in the same shared-memory array as M: address them as offsets from M so that one slot loop serves all
-    const int off1 = (w1 > 0) ? (int)(R1 - M) + lo1 : 0;
-    const int off2 = (w2 > 0) ? (int)(R2 - M) + lo2 : 0;
-    // ---- slots: lane q + 32 s of the concatenated columns [all of M | R1 range | R2 range], fixed for the whole solve.
-    // A lane without a column in a slot points at the tile's first padding column (index NP: never read as matrix data)
-    // with a zero pivot-row value, so that the update loop runs without per-element predicates.
-    const int ns = (n + w1 + w2 + 31) >> 5;
-    int coff[SL], cmin[SL];  // cmin: M column index (live once > j); RHS columns are always live (NP + 1)
-#pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        const int q = lane + 32 * s;
-        int c = NP, cm = -1;
-        if (q < n) {
-            c = q;
-            cm = q;
-        } else if (q < n + w1) {
-            c = off1 + (q - n);
-            cm = NP + 1;
-        } else if (q < n + w1 + w2) {
-            c = off2 + (q - n - w1);
-            cm = NP + 1;
-        }
-        coff[s] = c;
-        cmin[s] = cm;
-    }
-    unsigned long long used = 0ull;
-    bool ok = true;
-    for (int j = 0; j < n; ++j) {
-        // ---- pivot search, done redundantly by every warp on identical data (no barrier needed to share it).
-        // |x| as an orderable 64-bit key; max over the warp with two 32-bit redux.sync, lowest row index on ties.
-        unsigned long long key = 0ull;
-        int row = NP;
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-            const int i = lane + 32 * ch;
-            if (i < n && !((used >> i) & 1ull)) {
-                const unsigned long long kk = (unsigned long long)__double_as_longlong(fabs(M[i * LD + j]));
-                if (kk > key || row == NP) {
-                    key = kk;
-                    row = i;
-                }
-            }
-        }
-        const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
-        const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
-        const unsigned mlo = __reduce_max_sync(0xffffffffu, (khi == mhi) ? klo : 0u);
-        const int r = (int)__reduce_min_sync(0xffffffffu, (unsigned)((khi == mhi && klo == mlo) ? row : NP));
-        const double best = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-        if (r >= n || !(best > 0.0) || best > 1.7e308) {
-            ok = false;
-            break;  // uniform across the CTA
-        }
-        const double inv = 1.0 / M[r * LD + j];
-        used |= 1ull << r;
-        if (threadIdx.x == 0) {
-            s_piv[j] = r;
-            s_inv[j] = inv;
-        }
-        // ---- pivot-row values of this lane's slots; columns of M up to j are dead: a zero value makes their update an
-        // exact no-op (x - m * 0 = x, so the concurrent multiplier reads of column j by other warps see the same bits)
-        double pv[SL];
-#pragma unroll
-        for (int s = 0; s < SL; ++s) pv[s] = (s < ns && cmin[s] > j) ? M[r * LD + coff[s]] : 0.0;
-        // ---- eliminate column j from every other row; warps split rows (two at a time for ILP), lanes split columns.
-        // Row r and rows with a zero multiplier get multiplier 0 (an exact no-op) instead of a branch.
-        for (int i0 = warp; i0 < n; i0 += 2 * NW) {
-            const int i1 = i0 + NW;
-            double* row0 = M + i0 * LD;
-            const double m0 = (i0 == r) ? 0.0 : row0[j] * inv;
-            if (i1 < n) {
-                double* row1 = M + i1 * LD;
-                const double m1 = (i1 == r) ? 0.0 : row1[j] * inv;
-                if (m0 == 0.0 && m1 == 0.0) continue;  // structural zeros: nothing to do (reference BLAS skips them too)
-                double x0[SL], x1[SL];
-#pragma unroll
-                for (int s = 0; s < SL; ++s) {
-                    if (s < ns) {
-                        x0[s] = row0[coff[s]];
-                        x1[s] = row1[coff[s]];
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < SL; ++s) {
-                    if (s < ns) {
-                        row0[coff[s]] = fma(-m0, pv[s], x0[s]);
-                        row1[coff[s]] = fma(-m1, pv[s], x1[s]);
-                    }
-                }
-            } else {
-                if (m0 == 0.0) continue;
-#pragma unroll
-                for (int s = 0; s < SL; ++s) {
-                    if (s < ns) row0[coff[s]] = fma(-m0, pv[s], row0[coff[s]]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (!ok) {
-        __syncthreads();
-        return false;
-    }
-    // ---- un-permute and scale: X[j][c] = R[piv[j]][c] * inv[j]; rows j = warp + e*NW (e < 8 covers NP rows)
-    double x1[8][CH], x2[8][CH];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int j = warp + e * NW;
-        const int pr = (j < n) ? s_piv[j] : 0;
-        const double iv = (j < n) ? s_inv[j] : 0.0;
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-            const int c = lane + 32 * ch;
-            x1[e][ch] = (j < n && lo1 + c < hi1) ? R1[pr * LD + lo1 + c] * iv : 0.0;
-            x2[e][ch] = (j < n && lo2 + c < hi2) ? R2[pr * LD + lo2 + c] * iv : 0.0;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int j = warp + e * NW;
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-            const int c = lane + 32 * ch;
-            if (j < n && lo1 + c < hi1) R1[j * LD + lo1 + c] = x1[e][ch];
-            if (j < n && lo2 + c < hi2) R2[j * LD + lo2 + c] = x2[e][ch];
-        }
-    }
-    __syncthreads();
-    return true;
-}
-
 // acc += sign * A * B[bmap[.], :]: like gemm_acc<NP, false, false>, but row k of the B operand is read from row bmap[k]
 // of the tile.  Lets the products of the cycle-reduction step consume the row-permuted output of gj_solve_blocked
 // (solution row k lives in row piv[k]) without an un-permutation pass.
@@ -355,7 +209,8 @@ __device__ __forceinline__ void gemm_acc_bmap(Acc<NP>& acc, const double* __rest
 //   update  every warp, its 8-row strip: that formula as one DMMA product with k = 8 for every live column tile
 //           (tiles of M to the right of the panel, the right-hand-side tiles); pivot rows are gathered through piv[].
 // Three barriers per block step instead of one per column, and the O(n^3) work moves from load/DFMA/store triples to
-// mma.sync.  The first step may read from a different set of tiles than it writes (Ms/R1s/R2s -> Md/R1d/R2d: no
+// mma.sync.  The pivots are the ones of unblocked partial pivoting (1 / pivot_j -> s_pivinv[j] when given, so det M = +- prod
+// pivots).  The first step may read from a different set of tiles than it writes (Ms/R1s/R2s -> Md/R1d/R2d: no
 // copy of the inputs is needed, and that step needs no barrier between reading and writing); the remaining steps work
 // in place in the destination tiles.  On exit M is destroyed and solution row j is in row piv[j] of the right-hand-
 // side tiles (piv -> s_piv); with `unpermute` the rows are moved to their natural positions.  Destination columns
@@ -376,12 +231,19 @@ __device__ __forceinline__ double rcp_nr(double x) {
     return y;
 }
 
+// 64-bit shuffle as two explicit 32-bit shuffles (the double overload of __shfl_sync costs three extra LOP3 per value)
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    const int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src);
+    const int lo = __shfl_sync(0xffffffffu, __double2loint(v), src);
+    return __hiloint2double(hi, lo);
+}
+
 template <int NP>
 __device__ __noinline__ bool gj_solve_blocked(const double* Ms, double* Md, const double* R1s, double* R1d, int c1lo, int c1hi,
                                               const double* R2s, double* R2d, int c2lo, int c2hi, int n, bool unpermute,
-                                              int* __restrict__ s_piv, int* __restrict__ s_flag) {
+                                              int* __restrict__ s_piv, int* __restrict__ s_flag, double* __restrict__ s_pivinv = nullptr) {
     constexpr int LD = Cfg<NP>::LD, CT = Cfg<NP>::CT, RPL = (NP + 31) / 32, NW = Cfg<NP>::NW;
-    constexpr unsigned IDXBITS = (RPL == 1) ? 5u : 6u, IDXMASK = (1u << IDXBITS) - 1u;
+    constexpr unsigned IDXBITS = (RPL == 1) ? 5u : (RPL == 2) ? 6u : 7u, IDXMASK = (1u << IDXBITS) - 1u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int nblk = (n + 7) >> 3;
@@ -410,7 +272,11 @@ __device__ __noinline__ bool gj_solve_blocked(const double* Ms, double* Md, cons
                 }
             }
             unsigned fail = 0u;
-            int myr = 0;  // lane jj keeps the pivot row of panel column jj (0 for padding columns: any valid row)
+            int myr = 0;           // lane jj keeps the pivot row of panel column jj (0 for padding columns: any valid row)
+            double mypinv = 1.0;   // ... and 1 / pivot of that column (callers that want det M)
+            double myinv[RPL];     // 1 / pivot of the row(s) this lane holds, once they have been pivot rows
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) myinv[h] = 1.0;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 if (jj < jmax) {  // warp-uniform
@@ -429,37 +295,47 @@ __device__ __noinline__ bool gj_solve_blocked(const double* Ms, double* Md, cons
                     const int r = (int)(IDXMASK - (best & IDXMASK));
                     fail |= ((best >> IDXBITS) == 0u || best >= 0x7ff00000u) ? 1u : 0u;  // zero / subnormal / inf / NaN pivot
                     const int rl = r & 31;
+                    const int rh = r >> 5;
                     double inv = invo[0];
-                    if constexpr (RPL == 2) inv = (r >= 32) ? invo[1] : inv;
-                    inv = __shfl_sync(0xffffffffu, inv, rl);
+                    if constexpr (RPL >= 2) inv = (rh == 1) ? invo[1] : inv;
+                    if constexpr (RPL >= 3) inv = (rh == 2) ? invo[2] : inv;
+                    inv = shfl_f64(inv, rl);
                     double pr[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         if (c != jj) {
                             double v = a[0][c];
-                            if constexpr (RPL == 2) v = (r >= 32) ? a[1][c] : v;
-                            pr[c] = __shfl_sync(0xffffffffu, v, rl);
+                            if constexpr (RPL >= 2) v = (rh == 1) ? a[1][c] : v;
+                            if constexpr (RPL >= 3) v = (rh == 2) ? a[2][c] : v;
+                            pr[c] = shfl_f64(v, rl);
                         }
                     }
+                    // The pivot row is NOT scaled here (its slot takes the coefficient 1 of its own old row); it is
+                    // scaled by 1/pivot once, after the panel, which commutes with the later eliminations acting on it.
 #pragma unroll
                     for (int h = 0; h < RPL; ++h) {
                         const bool is_r = (lane + 32 * h == r);
-                        // pivot row: a[c] <- pr[c] * inv, a[jj] <- inv;  other rows: a[c] <- a[c] - m pr[c], a[jj] <- -m
-                        const double mm = is_r ? -inv : a[h][jj] * inv;
+                        const double m = is_r ? 0.0 : a[h][jj] * inv;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            if (c != jj) a[h][c] = fma(-mm, pr[c], is_r ? 0.0 : a[h][c]);
+                            if (c != jj) a[h][c] = fma(-m, pr[c], a[h][c]);
                         }
-                        a[h][jj] = -mm;
+                        a[h][jj] = is_r ? 1.0 : -m;
+                        myinv[h] = is_r ? inv : myinv[h];
                         used[h] = used[h] || is_r;
                         inP[h] = inP[h] || is_r;
                     }
-                    if (lane == jj) myr = r;
+                    if (lane == jj) {
+                        myr = r;
+                        mypinv = inv;
+                    }
                 }
             }
 #pragma unroll
             for (int h = 0; h < RPL; ++h) {
                 const int i = lane + 32 * h;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[h][c] *= myinv[h];  // 1 for the rows that were not pivot rows of this panel
                 if (i < NP) {
 #pragma unroll
                     for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(Md + i * LD + c0 + c) = make_double2(a[h][c], a[h][c + 1]);
@@ -467,6 +343,7 @@ __device__ __noinline__ bool gj_solve_blocked(const double* Ms, double* Md, cons
                 }
             }
             if (lane < 8) s_piv[c0 + lane] = myr;
+            if (s_pivinv && lane < 8) s_pivinv[c0 + lane] = mypinv;
             if (lane == 0) s_flag[NP] = (int)fail;
         }
         __syncthreads();

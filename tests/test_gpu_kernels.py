@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 TOL_TR = 1e-9
 TOL_LL = 1e-7
 
-MODELS = ["rbc", "one_block_1_ss", "rbc_extended", "full_nk", "new_keynesian", "nk_complete_more_shocks"]
+MODELS = ["rbc", "one_block_1_ss", "rbc_extended", "full_nk", "new_keynesian", "nk_complete_more_shocks", "nk_rbc_composite"]
 
 
 @pytest.fixture(scope="module")
@@ -29,7 +29,7 @@ def B():
 
 
 # ------------------------------------------------------------------------------------------- building blocks
-@pytest.mark.parametrize("n", [1, 3, 8, 9, 16, 17, 24, 31, 40, 45, 56])
+@pytest.mark.parametrize("n", [1, 3, 8, 9, 16, 17, 24, 31, 40, 45, 56, 64])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_gemm_matches_numpy(B, rng, n, ta, tb):
     A = rng.standard_normal((5, n, n))
@@ -39,7 +39,7 @@ def test_gemm_matches_numpy(B, rng, n, ta, tb):
     assert np.abs(out - ref).max() <= 1e-13 * n
 
 
-@pytest.mark.parametrize("n,m", [(1, 1), (5, 2), (9, 9), (24, 24), (24, 4), (31, 9), (45, 13), (56, 56)])
+@pytest.mark.parametrize("n,m", [(1, 1), (5, 2), (9, 9), (24, 24), (24, 4), (31, 9), (33, 33), (45, 13), (56, 56), (64, 64), (66, 5), (72, 72), (88, 88)])
 def test_solve_matches_lapack(B, rng, n, m):
     M = rng.standard_normal((7, n, n)) + 0.1 * np.eye(n)
     M[1, [0, -1]] = M[1, [-1, 0]]  # force pivoting
@@ -106,6 +106,25 @@ def test_cycle_reduction_unpermute_and_flags(B):
             assert rel_fro(short.R[i], Rref) <= TOL_TR
         else:
             assert np.isnan(short.R[i]).all()
+
+
+@pytest.mark.parametrize("n,k", [(57, 6), (60, 13), (64, 64)])
+def test_cycle_reduction_largest_size(B, rng, n, k):
+    """Padded dimension 64 (A1hat in the global workspace): synthetic well-conditioned systems against the oracle."""
+    N = 5
+    A = 0.3 * rng.standard_normal((N, n, n)) / np.sqrt(n)
+    C = 0.3 * rng.standard_normal((N, n, n)) / np.sqrt(n)
+    A[:, :, n // 2 :] = 0.0   # lag columns first, lead columns last, as in solver order
+    C[:, :, : n // 3] = 0.0
+    Bm = np.eye(n) + 0.2 * rng.standard_normal((N, n, n)) / np.sqrt(n)
+    D = rng.standard_normal((N, n, k))
+    res = B.cr_solve(A, Bm, C, D, max_iter=200, tol=1e-10, resid_tol=1e-8)
+    for i in range(N):
+        T, conv, n_iter = osol.cycle_reduction_core(A[i], Bm[i], C[i], max_iter=200, tol=1e-10)
+        assert conv and bool(res.converged[i]) and int(res.n_iter[i]) == n_iter
+        R = osol.selection_matrix(Bm[i], C[i], D[i], T)
+        assert rel_fro(res.T[i], T) <= TOL_TR and rel_fro(res.R[i], R) <= TOL_TR
+        assert res.status[i] == 0
 
 
 def test_backward_looking(B, rng):
@@ -211,7 +230,7 @@ def test_dlyap_parity(B, name):
         assert np.abs(P[i] - (T[i] @ P[i] @ T[i].T + R[i] @ np.diag(q) @ R[i].T)).max() <= 1e-13 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc", 200), ("full_nk", 200), ("nk_complete_more_shocks", 50)])
+@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc", 200), ("full_nk", 200), ("nk_complete_more_shocks", 50), ("nk_rbc_composite", 40)])
 @pytest.mark.parametrize("selector", [True, False])
 def test_kalman_parity(B, name, Tobs, selector):
     mod = model(name)
@@ -254,6 +273,48 @@ def test_kalman_missing_data_no_measurement_error_and_intercept(B):
             ref2 = oss.kalman_loglik(Yc, T[i], R[i], np.diag(q), Z, np.zeros((3, 3)), d=dd, mvn_const="bare")
             assert abs(ll[i] - ref) <= TOL_LL, (i, ll[i], ref)
             assert abs(ll2[i] - ref2) <= TOL_LL, (i, ll2[i], ref2)
+
+
+def _random_statespace(rng, N, n, k, rho=0.9):
+    T = rng.standard_normal((N, n, n))
+    if n > 1:
+        T[:, :, n - max(1, n // 4) :] = 0.0  # jumper columns, as a policy matrix has
+    for i in range(N):
+        T[i] *= rho / np.abs(np.linalg.eigvals(T[i])).max()
+    R = rng.standard_normal((N, n, k))
+    return T, R
+
+
+@pytest.mark.parametrize("n,k,p", [(1, 1, 1), (3, 2, 1), (5, 3, 2), (7, 2, 4), (12, 4, 3), (15, 6, 5), (15, 16, 8), (20, 7, 7), (23, 9, 6), (23, 3, 8),
+                                    (24, 5, 2), (40, 8, 8), (60, 10, 7), (63, 4, 3)])
+def test_kalman_synthetic_sizes(B, rng, n, k, p):
+    """Both filter kernels over their whole size range (one warp per draw up to n = 23, one CTA per draw above), every
+    number of observables, with measurement error, missing data, an intercept and per-step output."""
+    N, Tobs = 4, 45
+    T, R = _random_statespace(rng, N, n, k)
+    q = 0.5 + rng.random((N, k))
+    h = 0.1 + rng.random((N, p))
+    obs = np.sort(rng.choice(n, size=p, replace=False)).astype(np.int32)
+    Z = np.zeros((p, n))
+    Z[np.arange(p), obs] = 1.0
+    d = 0.1 * rng.standard_normal(p)
+    x = np.zeros(n)
+    Y = np.zeros((Tobs, p))
+    for t in range(Tobs):
+        x = T[0] @ x + R[0] @ (np.sqrt(q[0]) * rng.standard_normal(k))
+        Y[t] = x[obs] + d + np.sqrt(h[0]) * rng.standard_normal(p)
+    Ym = Y.copy()
+    Ym[rng.random(Y.shape) < 0.2] = np.nan
+    Ym[3] = np.nan
+    for Yc, dd in ((Y, None), (Ym, d)):
+        ll, st, llt = B.kalman_loglik(T, R, q, Yc, obs_idx=obs, hdiag=h, d=dd, return_per_step=True)
+        ll1, st1 = B.kalman_loglik(T, R, q, Yc, obs_idx=obs, hdiag=h, d=dd)
+        for i in range(N):
+            ref, ref_t = oss.kalman_loglik(Yc, T[i], R[i], np.diag(q[i]), Z, np.diag(h[i]), d=dd, return_all=True)
+            assert st[i] == 0 and st1[i] == 0
+            scale = max(1.0, abs(ref) * 1e-9)  # 1e-7 absolute on likelihoods of order 100
+            assert np.abs(llt[i] - ref_t).max() <= TOL_LL * scale, (n, p, i, np.abs(llt[i] - ref_t).max())
+            assert abs(ll[i] - ref) <= TOL_LL * scale and abs(ll1[i] - ref) <= TOL_LL * scale, (n, p, i, ll[i], ll1[i], ref)
 
 
 def test_kalman_gating_and_given_P0(B):

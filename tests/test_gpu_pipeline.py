@@ -10,7 +10,8 @@ from oracle import statespace as oss
 
 pytestmark = pytest.mark.gpu
 
-MODELS = ["rbc", "one_block_1_ss", "rbc_extended", "open_rbc", "full_nk", "new_keynesian", "nk_complete_more_shocks", "rbc_linearized"]
+MODELS = ["rbc", "one_block_1_ss", "rbc_extended", "open_rbc", "full_nk", "new_keynesian", "nk_complete_more_shocks", "rbc_linearized",
+          "nk_rbc_composite"]
 
 
 @pytest.fixture(scope="module")
@@ -58,7 +59,7 @@ def _configure(compiled, name, reduce_state=True, with_err=True):
     return cm, mod, ss, observed, meas
 
 
-@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc_extended", 80), ("full_nk", 200), ("nk_complete_more_shocks", 60)])
+@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc_extended", 80), ("full_nk", 200), ("nk_complete_more_shocks", 60), ("nk_rbc_composite", 40)])
 @pytest.mark.parametrize("reduce_state", [True, False])
 def test_pipeline_loglik_matches_oracle(compiled, name, Tobs, reduce_state):
     """North-star tolerances: flags exact, |ll - oracle| <= 1e-7, failures gated to -inf on both sides."""
@@ -79,6 +80,28 @@ def test_pipeline_loglik_matches_oracle(compiled, name, Tobs, reduce_state):
         else:
             assert np.isneginf(ll[i]) and st[i] != 0, (name, i, ll[i], st[i])
     assert n_ok >= len(th) // 3
+
+
+def test_composite_likelihood_equals_the_observed_block(compiled):
+    """Size-independent property of the 45-variable composite: its two economies do not
+    interact and only the first is observed, so the likelihood equals the one of the first model alone."""
+    _, moda, ssa, observed, meas = _configure(compiled, "nk_complete_more_shocks")
+    _, modc, ssc, observed_c, meas_c = _configure(compiled, "nk_rbc_composite")
+    assert observed == observed_c
+    rng = np.random.default_rng(41)
+    N = 16
+    tha = draws(moda, N, seed=41, width=0.02, valid=True)
+    modb = model("rbc_extended")
+    thb = draws(modb, N, seed=42, width=0.02, valid=True)
+    Y = simulate_obs(moda, 50, seed=6, sigma_err=SIGMA_ERR)
+    siga, sigb = np.full((N, moda.k), SIGMA_SHOCK), 0.01 + 0.02 * rng.random((N, modb.k))
+    err = np.full((N, len(meas)), SIGMA_ERR)
+    assert modc.param_names == moda.param_names + [p + "_2" for p in modb.param_names]
+    ll_a, st_a = ssa.loglik(np.hstack([tha, siga, err]), Y)
+    ll_c, st_c = ssc.loglik(np.hstack([tha, thb, siga, sigb, err]), Y)
+    ok = (st_a == 0) & (st_c == 0)
+    assert ok.sum() >= N // 2
+    assert np.abs(ll_a[ok] - ll_c[ok]).max() <= 1e-7
 
 
 def test_pipeline_reports_failures(compiled):

@@ -68,8 +68,8 @@ def test_bad_arguments_are_rejected_by_the_library():
     args = _lib.CrArgs(struct_size=3)
     assert lib.gecon_cr_solve_batched(C.byref(args), None) == -1
     assert b"struct_size" in lib.gecon_get_last_error()
-    big = _lib.CrArgs(struct_size=C.sizeof(_lib.CrArgs), A=1, B=1, T=1, status=1, N=1, n=57, k=0)
-    assert lib.gecon_cr_solve_batched(C.byref(big), None) == -2  # n > 56 unsupported
+    big = _lib.CrArgs(struct_size=C.sizeof(_lib.CrArgs), A=1, B=1, T=1, status=1, N=1, n=65, k=0)
+    assert lib.gecon_cr_solve_batched(C.byref(big), None) == -2  # n > 64 unsupported
 
 
 def test_product_never_imports_the_oracle_or_the_reference():
