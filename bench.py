@@ -199,13 +199,115 @@ def cpu_reference_rate(wl: dict, Y: np.ndarray, n_sample: int, cores: int, seed:
     return n_sample / dt, dt, int(np.isfinite(lls).sum())
 
 
+# --------------------------------------------------------------------------------------------------- SMC sweep (config 5)
+def prior_box(spec: dict, width):
+    """The box make_draws samples from (lo, hi per free parameter)."""
+    names = list(spec["free_params"])
+    th0 = np.array([spec["free_params"][p] for p in names], dtype=np.float64)
+    lo, hi = th0.copy(), th0.copy()
+    bounds = spec.get("bounds", {})
+    for j, p in enumerate(names):
+        lo[j], hi[j] = th0[j] - width * abs(th0[j]), th0[j] + width * abs(th0[j])
+        if p in bounds:
+            eps = 1e-6 * (bounds[p][1] - bounds[p][0])
+            lo[j], hi[j] = max(lo[j], bounds[p][0] + eps), min(hi[j], bounds[p][1] - eps)
+        if p in ("beta",):
+            lo[j], hi[j] = min(lo[j], 0.998), min(hi[j], 0.999)
+        elif p.startswith("rho_"):
+            lo[j], hi[j] = min(lo[j], 0.98), min(hi[j], 0.99)
+        elif p in ("pi_bar", "phi_pi_obj"):
+            lo[j] = hi[j] = th0[j]
+    return lo, hi
+
+
+def run_smc(args, rank, world, local_rank):
+    """BASELINE.json config 5: tempered SMC over `--particles` particles per GPU of the medium NK model; one timed
+    "step" = one tempering stage = Metropolis mutation (one batched likelihood evaluation of every particle) +
+    reweighting + ONE all-gather of (weight, ll, theta) + redundant systematic resampling on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    from geconpy_b200 import batched
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+    from geconpy_b200.smc import TemperedSMC
+
+    wl = WORKLOADS["nk"]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spec = json.loads((ROOT / "geconpy_b200" / "model" / "specs" / f"{wl['model']}.json").read_text())
+    n, k, p, tobs = len(spec["variables"]), len(spec["shocks"]), len(wl["observed"]), wl["tobs"]
+    cm = CompiledModel(wl["model"])
+    ss = BatchedStateSpace(cm).configure(observed_states=wl["observed"], measurement_error=wl["meas"], tol=1e-8, max_iter=100)
+    sol = ss.solve(cm.theta_vector()[None], device=str(dev))
+    Y = simulate_from_policy(sol["T"][0], sol["R"][0], k, tobs, [cm.var_names.index(v) for v in wl["observed"]])
+    Y_d = torch.as_tensor(Y, device=dev)
+    n_local = args.particles
+    theta0 = torch.as_tensor(make_draws(spec, n_local, wl["width"], seed=0, skip=rank * n_local), device=dev)
+    lo, hi = (torch.as_tensor(x, device=dev) for x in prior_box(spec, wl["width"]))
+    tail = torch.as_tensor(np.concatenate([np.full(k, SIGMA_SHOCK), np.full(len(wl["meas"]), SIGMA_ERR)]), device=dev)[None]
+    smc = TemperedSMC(ss, lo, hi, tail, Y_d, step_scale=0.02, seed=0).initialise(theta0)
+    n_stages = args.warmup + args.steps
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    launches0 = None
+    evs = []
+    with ClockSampler(local_rank) as clk:
+        for s in range(1, n_stages + 1):
+            if s == args.warmup + 1:
+                barrier()
+                launches0 = batched.launch_count() + cm.launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            smc.stage((s / n_stages) ** 2, s)
+            e1.record()
+            if s > args.warmup:
+                evs.append((e0, e1))
+        barrier()
+    launches = batched.launch_count() + cm.launches - launches0
+    ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n_local / (ms_per_step * 1e-3)
+    d = theta0.shape[1]
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"SMC sweep, medium NK full_nk (n={n},k={k},p={p}), T_obs={tobs}: {n_local} particles per GPU, "
+                                   f"{n_stages} tempering stages (first {args.warmup} untimed); one step = one stage = Metropolis mutation "
+                                   "(one likelihood evaluation per particle) + all-gather + systematic resampling",
+                       "n": n, "k": k, "p": p, "T_obs": tobs, "particles_per_gpu": n_local, "stages": n_stages,
+                       "l2": "working set of a stage (A,B,C,D,T,R of 65,536-draw chunks: >1 GB) exceeds L2"},
+            "clocks": clk.summary(),
+            # particles live on the device from stage to stage: the sweep has no per-step host traffic besides 3 scalars
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24, "ms_per_step": ms_per_step},
+            "gpu_launches": int(launches),
+            "smc": {"allgather_bytes_per_rank_per_stage": int(n_local * (2 + d) * 8), "collective": "nccl all_gather_into_tensor" if world > 1 else None,
+                    "stages": [dict(phi=round(st.phi, 4), ess=round(st.ess, 1), accept_rate=round(st.accept_rate, 4), mean_ll=round(st.mean_ll, 3),
+                                    failed=st.n_failed) for st in smc.stats]}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="nk", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="nk", choices=sorted(WORKLOADS) + ["smc"])
+    ap.add_argument("--particles", type=int, default=131072, help="smc workload: particles per GPU")
     ap.add_argument("--draws", type=int, default=0, help="draws per GPU (default: the workload's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="draws timed on the CPU (default: sized for ~20 s)")
@@ -216,6 +318,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "smc":
+        if args.impl == "reference":
+            args.workload = "nk"  # the CPU comparator of the sweep is the per-particle likelihood rate of the same model
+        else:
+            return run_smc(args, rank, world, local_rank)
     wl = WORKLOADS[args.workload]
     draws_per_gpu = args.draws or wl["draws"]
     spec = json.loads((ROOT / "geconpy_b200" / "model" / "specs" / f"{wl['model']}.json").read_text())

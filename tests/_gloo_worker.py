@@ -31,6 +31,13 @@ N2 = 64
 lo2, hi2 = shard_bounds(N2, rank, world)
 full2 = gather_loglik(torch.arange(lo2, hi2, dtype=torch.float64), N2)
 assert torch.equal(full2, torch.arange(N2, dtype=torch.float64))
+# the device-side resampler used by the SMC sweep (geconpy_b200/smc.py) is deterministic in (weights, seed) as well
+from geconpy_b200.smc import systematic_ancestors  # noqa: E402
+
+anc = systematic_ancestors(full, seed=11)
+gathered = [torch.empty_like(anc) for _ in range(world)]
+dist.all_gather(gathered, anc)
+assert all(torch.equal(g, anc) for g in gathered) and int(anc.max()) < N
 if rank == 0:
     print("gloo sharding ok")
 dist.destroy_process_group()
