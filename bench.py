@@ -479,9 +479,9 @@ def main():
     traffic = None
     tfile = ROOT / "profiles" / "r01_ncu_traffic.json"
     if tfile.exists() and args.workload == "nk":
-        per_draw = {k.split("_kernel")[0]: v["dram_bytes_per_draw"] for k, v in json.loads(tfile.read_text()).items() if isinstance(v, dict)}
-        if dom in per_draw:
-            traffic = per_draw[dom] * min(draws_per_gpu, ss.chunk)
+        for kname, v in json.loads(tfile.read_text()).items():
+            if isinstance(v, dict) and kname.startswith(dom):  # e.g. "kalman_ll_warp_kernel<16, 3, 4>" for dom = "kalman_ll"
+                traffic = v["dram_bytes_per_draw"] * min(draws_per_gpu, ss.chunk)
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": "measured DFMA burst on this pool's B200 (profiles/r01_fp64_peak_microbench.json); "
