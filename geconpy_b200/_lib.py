@@ -152,6 +152,25 @@ class KalmanArgs(C.Structure):
     ]
 
 
+class PropagateArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("T", C.c_void_p),
+        ("R", C.c_void_p),
+        ("X0", C.c_void_p),
+        ("E", C.c_void_p),
+        ("e_stride", C.c_int64),
+        ("N", C.c_int64),
+        ("n", C.c_int32),
+        ("k", C.c_int32),
+        ("m", C.c_int32),
+        ("L", C.c_int32),
+        ("start_at_x0", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("out", C.c_void_p),
+    ]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "gecon_abi_version": (C.c_int, []),
@@ -167,6 +186,8 @@ EXPORTS = {
     "gecon_dlyap_host": (C.c_int, [C.POINTER(DlyapArgs)]),
     "gecon_kalman_ll_batched": (C.c_int, [C.POINTER(KalmanArgs), C.c_void_p]),
     "gecon_kalman_ll_host": (C.c_int, [C.POINTER(KalmanArgs)]),
+    "gecon_propagate_batched": (C.c_int, [C.POINTER(PropagateArgs), C.c_void_p]),
+    "gecon_propagate_host": (C.c_int, [C.POINTER(PropagateArgs)]),
     "gecon_solve_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gecon_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "gecon_gemm_batched": (

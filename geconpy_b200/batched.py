@@ -222,6 +222,46 @@ def dlyap(T, R, qdiag, max_iter=0):
     return P, st, it
 
 
+def propagate(T, R=None, E=None, X0=None, n_steps=None, start_at_x0=False):
+    """Batched linear propagation ``X_t = T X_{t-1} + R E_t`` (``gecon_propagate_*``): returns ``out[N, L, n, m]``.
+
+    ``E``: shock panels ``[L, k, m]`` shared by all draws or ``[N, L, k, m]``; ``X0``: ``[N, n, m]`` state before t = 0.
+    Reference recursions: ``_simulate_linear_system`` (gEconpy/model/simulate.py:171-183), impulse responses
+    (simulate.py:201-318), ``_compute_autocovariance_matrix`` (model/statistics/covariance.py:133-161).
+    """
+    m_ = _marshal_for(T, R, E, X0)
+    T, pT = m_.inp(T)
+    T, squeeze = _batch3(T)
+    N, n = T.shape[0], T.shape[1]
+    pT = T.data_ptr() if m_.device else T.ctypes.data
+    R, pR = m_.inp(R)
+    k = 0 if R is None else R.shape[-1]
+    E, pE = m_.inp(E)
+    X0, pX = m_.inp(X0)
+    if E is not None:
+        if E.ndim not in (3, 4) or E.shape[-2] != k:
+            raise ValueError(f"E must be [L, k, m] or [N, L, k, m] with k = {k}; got {tuple(E.shape)}")
+        Lsteps, mm = E.shape[-3], E.shape[-1]
+        e_stride = Lsteps * k * mm if E.ndim == 4 else 0
+        if E.ndim == 4 and E.shape[0] != N:
+            raise ValueError("per-draw shocks need one panel per draw")
+    else:
+        if X0 is None or n_steps is None:
+            raise ValueError("without shocks give X0 and n_steps")
+        Lsteps, mm, e_stride = int(n_steps), X0.shape[-1], 0
+    if X0 is not None and tuple(X0.shape) != (N, n, mm):
+        raise ValueError(f"X0 must be [N, n, m] = {(N, n, mm)}; got {tuple(X0.shape)}")
+    out, pO = m_.out((N, Lsteps, n, mm))
+    args = L.PropagateArgs(struct_size=C.sizeof(L.PropagateArgs), T=pT, R=pR, X0=pX, E=pE, e_stride=e_stride, N=N, n=n, k=k, m=mm,
+                           L=Lsteps, start_at_x0=int(bool(start_at_x0)), reserved0=0, out=pO)  # fmt: skip
+    lib = L.load_library()
+    if m_.device:
+        L.check(lib.gecon_propagate_batched(C.byref(args), m_.stream()), "gecon_propagate_batched")
+    else:
+        L.check(lib.gecon_propagate_host(C.byref(args)), "gecon_propagate_host")
+    return out[0] if squeeze else out
+
+
 def kalman_loglik(
     T,
     R,

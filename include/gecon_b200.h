@@ -206,6 +206,34 @@ int gecon_gemm_batched(const double* A, const double* B, int64_t N, int32_t n, i
 int gecon_gemm_host(const double* A, const double* B, int64_t N, int32_t n, int32_t trans_a, int32_t trans_b, double alpha,
                     double* C);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched linear propagation X_t = T X_{t-1} + R E_t, t = 0..L-1, X an n x m panel per draw:
+ *   simulate            gEconpy/model/simulate.py:171-183 (_simulate_linear_system): X0 = NULL, E = shock trajectories,
+ *                       m = number of trajectories; out[0] = R e_0
+ *   impulse responses   gEconpy/model/simulate.py:201-318: m = k, E_0 = diag(shock sizes), E_t = 0 afterwards
+ *   autocovariances     gEconpy/model/statistics/covariance.py:133-161 (_compute_autocovariance_matrix):
+ *                       X0 = Sigma, start_at_x0 = 1, R = E = NULL; out[h] = T^h Sigma
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gecon_propagate_args {
+    size_t struct_size;
+    const double* T;   /* [N][n][n] */
+    const double* R;   /* [N][n][k] or NULL (no shocks) */
+    const double* X0;  /* [N][n][m] state before t = 0, or NULL (zero) */
+    const double* E;   /* shocks: [L][k][m] shared by all draws (e_stride = 0) or [N][L][k][m] (e_stride = L k m); NULL = none */
+    int64_t e_stride;
+    int64_t N;
+    int32_t n;
+    int32_t k;
+    int32_t m;
+    int32_t L;
+    int32_t start_at_x0; /* 1: out[0] = X0 (+ R E_0) instead of T X0 (+ R E_0) */
+    int32_t reserved0;
+    double* out;       /* [N][L][n][m] */
+} gecon_propagate_args;
+
+int gecon_propagate_batched(const gecon_propagate_args* args, void* stream);
+int gecon_propagate_host(const gecon_propagate_args* args);
+
 /* library / device information */
 int gecon_abi_version(void);
 int gecon_device_count(void);
