@@ -79,6 +79,10 @@ class CrArgs(C.Structure):
         ("n_unstable", C.c_void_p),
         ("solv_norms", C.c_void_p),
         ("trunc_tol", C.c_double),
+        ("t_stride", C.c_int64),
+        ("r_stride", C.c_int64),
+        ("t_ld", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -149,6 +153,7 @@ class KalmanArgs(C.Structure):
         ("ll", C.c_void_p),
         ("status", C.c_void_p),
         ("ll_t", C.c_void_p),
+        ("z_stride", C.c_int64),
     ]
 
 

@@ -284,6 +284,7 @@ def kalman_loglik(
 
     Reference call site: gEconpy/model/statespace.py:1151-1157 (pymc_extras StandardFilter); semantics in
     SURVEY.md Appendix A.5.  ``qdiag`` / ``hdiag`` are VARIANCES, per draw (N, k) / (N, p) or shared (k,) / (p,).
+    ``Z`` is (p, n) shared or (N, p, n), one design matrix per draw (parameter-dependent observation equations).
     """
     if (Z is None) == (obs_idx is None):
         raise ValueError("give exactly one of Z (dense design matrix) and obs_idx (selector)")
@@ -301,7 +302,7 @@ def kalman_loglik(
     q, pq = m.inp(qdiag)
     h, ph = m.inp(hdiag)
     dd, pd_ = m.inp(d)
-    _, pZ = m.inp(Z)
+    Za, pZ = m.inp(Z)
     _, pO = m.inp(None if obs_idx is None else np.ascontiguousarray(obs_idx, dtype=np.int32), np.int32)
     _, pP0 = m.inp(P0)
     _, pSin = m.inp(status_in, np.int32)
@@ -314,6 +315,7 @@ def kalman_loglik(
         d_stride=(p if (dd is not None and dd.ndim == 2) else 0), Y=pY, P0=pP0, N=N, n=n, k=k, p=p, Tobs=Tobs,
         jitter=float(jitter), missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1),
         lyap_max_iter=int(lyap_max_iter), status_in=pSin, gate_mask=int(gate_mask), ll=pll, status=pS, ll_t=pllt,
+        z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0),
     )  # fmt: skip
     lib = L.load_library()
     if m.device:

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
                 __syncthreads();
             }
             have_F = ok && want_cert;
-            if (kd) tile_store<NP>(p.R + (size_t)draw * no * k, X2, no, k, k, -1.0, perm, nullptr);
+            if (kd) tile_store<NP>(p.R + (size_t)draw * (p.r_stride ? (size_t)p.r_stride : (size_t)no * k), X2, no, k, k, -1.0, perm, nullptr);
         }
 
         // ---- residual sum((A + B T + (C T) T)^2) in solver order (statespace.py:213)
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
                 p.status[draw] = p.accumulate ? (p.status[draw] | status) : status;
             }
         }
-        tile_store<NP>(p.T + (size_t)draw * no * no, Tt, no, no, no, 1.0, perm, perm);
+        tile_store<NP>(p.T + (size_t)draw * (p.t_stride ? (size_t)p.t_stride : (size_t)no * no), Tt, no, no, p.t_ld ? p.t_ld : no, 1.0, perm, perm);
         __syncthreads();
 
         // ---- Blanchard-Kahn certificate (see gecon_cr_args.lead_idx): rho(T) < 1 and rho(F_LL) < 1 by repeated squaring.
@@ -367,6 +367,13 @@ static int check_cr_args(const gecon_cr_args* a) {
         set_last_error("gecon_cr_args: n_out = %d needs 0 <= n_out <= n and an index list in unperm", a->n_out);
         return GECON_E_BADARG;
     }
+    {
+        const int64_t no = (a->unperm && a->n_out > 0) ? a->n_out : a->n;
+        if ((a->t_ld && a->t_ld < no) || (a->t_stride && a->t_stride < no * (a->t_ld ? a->t_ld : no)) || (a->r_stride && a->r_stride < no * a->k)) {
+            set_last_error("gecon_cr_args: t_ld / t_stride / r_stride smaller than the block they hold");
+            return GECON_E_BADARG;
+        }
+    }
     if (a->lead_idx && (a->n_lead < 0 || a->n_lead > a->n)) {
         set_last_error("gecon_cr_args: n_lead = %d out of range", a->n_lead);
         return GECON_E_BADARG;
@@ -422,6 +429,10 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
     int rc = check_cr_args(args);
     if (rc) return rc;
     if (args->N == 0) return 0;
+    if (args->t_stride || args->r_stride || args->t_ld) {
+        set_last_error("gecon_cr_solve_host: strided outputs are a device-entry-point feature");
+        return GECON_E_BADARG;
+    }
     const size_t N = (size_t)args->N, n = args->n, k = args->k;
     const size_t no = (args->unperm && args->n_out > 0) ? (size_t)args->n_out : n;
     const size_t bm = N * n * n * sizeof(double), bd = N * n * k * sizeof(double);

@@ -57,6 +57,10 @@ static int check_kf_args(const gecon_kalman_args* a) {
         set_last_error("gecon_kalman_args: null pointer or bad dimension");
         return GECON_E_BADARG;
     }
+    if (a->Z && a->z_stride && a->z_stride != (int64_t)a->p * a->n) {
+        set_last_error("gecon_kalman_args: z_stride must be 0 (shared Z) or p * n");
+        return GECON_E_BADARG;
+    }
     if (a->p > PMAX || a->p > a->n) {
         set_last_error("gecon_kalman_args: unsupported p = %d (max %d, and p <= n)", a->p, PMAX);
         return GECON_E_UNSUPPORTED_SIZE;
@@ -221,7 +225,7 @@ extern "C" int gecon_kalman_ll_host(const gecon_kalman_args* a) {
     H2D(dR, R, double, N * n * k)
     H2D(dq, qdiag, double, (a->q_stride ? N * k : k))
     H2D(dh, hdiag, double, (a->h_stride ? N * p : p))
-    H2D(dZ, Z, double, p * n)
+    H2D(dZ, Z, double, (a->z_stride ? N * p * n : p * n))
     H2D(dobs, obs_idx, int32_t, p)
     H2D(dd, d, double, (a->d_stride ? N * p : p))
     H2D(dY, Y, double, Tobs * p)

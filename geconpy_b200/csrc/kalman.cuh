@@ -260,6 +260,13 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
             s_d[tid] = p.d ? p.d[(size_t)draw * p.d_stride + tid] : 0.0;
         }
         if (tid < NP) s_a[tid] = 0.0;
+        if (!sel && p.z_stride) {  // one design matrix per draw (the zero padding of s_Z is never overwritten)
+            const double* gZ = p.Z + (size_t)draw * (size_t)p.z_stride;
+            for (int i = tid; i < PT * n; i += NT) {
+                const int a = i / n, j = i - a * n;
+                s_Z[a * NP + j] = gZ[i];
+            }
+        }
         __syncthreads();
         rqr_fill<NP>(RQ, W, s_q, n, k);
         int lo, hi;

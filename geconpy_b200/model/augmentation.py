@@ -1,0 +1,153 @@
+"""State augmentation for temporally aggregated / mixed-frequency observations.
+
+Host-side bookkeeping of ``DSGEStateSpace`` (gEconpy/model/statespace.py:556-723, 260-296, 334-388), kept in the
+reference's vocabulary: *cumulator* states are deterministic lag copies of a "sum"/"mean"-aggregated variable, so that a
+low-frequency observation ``y = w (x_t + x_{t-1} + ... + x_{t-s+1})`` is a linear function of the augmented state;
+"first"/"last" aggregation needs no extra state, only missing values in the data (``prepare_mixed_frequency_data``).
+
+    T_aug = [[T, 0], [F, kron(I, shift)]]      R_aug = [[R], [0]]      Z[i] = w e_var + w sum(e_slots)
+
+Nothing here touches the device: the constant rows ``[F, kron(I, shift)]`` are written ONCE into the workspace the solver
+kernel fills (``gecon_cr_args.t_ld / t_stride / r_stride``), so augmentation adds no pass over HBM per draw.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+CUMULATOR_AGGREGATIONS = ("sum", "mean")  # statespace.py:48
+VALID_AGGREGATIONS = ("sum", "mean", "first", "last")
+
+
+@dataclass
+class StateAugmentation:
+    """Layout of the augmented state vector.
+
+    ``state_names``: names of the states the filter runs on, in filter order (the un-augmented part);
+    ``observed_states``: data-column order; ``temporal_aggregation``: {observed state: "sum"|"mean"|"first"|"last"}.
+    """
+
+    state_names: list
+    observed_states: list
+    temporal_aggregation: dict = field(default_factory=dict)
+    aggregation_period: int = 4
+
+    def __post_init__(self):
+        ta = dict(self.temporal_aggregation or {})
+        unknown = [v for v in ta if v not in self.observed_states]
+        if unknown:
+            raise ValueError(f"The following temporal_aggregation entries are not in observed_states: {', '.join(unknown)}")
+        bad = {v: m for v, m in ta.items() if m not in VALID_AGGREGATIONS}
+        if bad:
+            raise ValueError(f"Unknown temporal aggregation method(s) {bad}; expected one of {VALID_AGGREGATIONS}")
+        if any(m in CUMULATOR_AGGREGATIONS for m in ta.values()) and self.aggregation_period < 2:
+            raise ValueError(f"aggregation_period must be >= 2 for sum/mean aggregation, got {self.aggregation_period}")
+        missing = [v for v in self.observed_states if v not in self.state_names]
+        if missing:
+            raise ValueError(f"observed states {missing} are not among the filter states")
+        self.temporal_aggregation = ta
+
+    # ---- the reference's private properties, same names (statespace.py:556-584)
+    @property
+    def _cumulator_variables(self) -> list:
+        return [v for v, m in self.temporal_aggregation.items() if m in CUMULATOR_AGGREGATIONS]
+
+    @property
+    def _n_cumulator_states(self) -> int:
+        return len(self._cumulator_variables) * (self.aggregation_period - 1)
+
+    @property
+    def _cumulator_state_names(self) -> list:
+        return [f"{v}_cumulator_lag{lag}" for v in self._cumulator_variables for lag in range(1, self.aggregation_period)]
+
+    @property
+    def k_orig_states(self) -> int:
+        return len(self.state_names)
+
+    @property
+    def k_states(self) -> int:
+        return self.k_orig_states + self._n_cumulator_states
+
+    @property
+    def augmented_state_names(self) -> list:
+        return list(self.state_names) + self._cumulator_state_names
+
+    # ---- constant blocks
+    def transition_rows(self) -> np.ndarray:
+        """The rows appended below T: ``[F | kron(I, shift)]``, shape (n_cumulator, k_states) (statespace.py:629-650)."""
+        n_lags = self.aggregation_period - 1
+        n_cum = self._n_cumulator_states
+        rows = np.zeros((n_cum, self.k_states))
+        k0 = self.k_orig_states
+        for pos, name in enumerate(self._cumulator_variables):
+            rows[pos * n_lags, self.state_names.index(name)] = 1.0  # F: slot 1 copies the variable
+            for j in range(1, n_lags):  # shift companion: slot j+1 copies slot j
+                rows[pos * n_lags + j, k0 + pos * n_lags + j - 1] = 1.0
+        return rows
+
+    def augment_transition(self, T: np.ndarray) -> np.ndarray:
+        """numpy twin of ``_augment_transition`` for (..., k, k) arrays."""
+        n_cum = self._n_cumulator_states
+        if n_cum == 0:
+            return T
+        k0 = self.k_orig_states
+        out = np.zeros((*T.shape[:-2], k0 + n_cum, k0 + n_cum))
+        out[..., :k0, :k0] = T
+        out[..., k0:, :] = self.transition_rows()
+        return out
+
+    def augment_selection(self, R: np.ndarray) -> np.ndarray:
+        """numpy twin of ``_augment_selection`` (statespace.py:696-723)."""
+        n_cum = self._n_cumulator_states
+        if n_cum == 0:
+            return R
+        return np.concatenate([R, np.zeros((*R.shape[:-2], n_cum, R.shape[-1]))], axis=-2)
+
+    def design_matrix(self) -> np.ndarray:
+        """``_make_design_matrix`` on the selector path (statespace.py:279-296)."""
+        n_lags = self.aggregation_period - 1
+        Z = np.zeros((len(self.observed_states), self.k_states))
+        cum = self._cumulator_variables
+        for i, name in enumerate(self.observed_states):
+            j = self.state_names.index(name)
+            m = self.temporal_aggregation.get(name)
+            if m in CUMULATOR_AGGREGATIONS:
+                w = 1.0 / self.aggregation_period if m == "mean" else 1.0
+                start = self.k_orig_states + cum.index(name) * n_lags
+                Z[i, j] = w
+                Z[i, start : start + n_lags] = w
+            else:
+                Z[i, j] = 1.0
+        return Z
+
+    def is_selector(self) -> bool:
+        return self._n_cumulator_states == 0
+
+    def intercept_scale(self) -> np.ndarray:
+        """Per observed state: aggregation_period for "sum", 1 otherwise (statespace.py:382-386)."""
+        return np.array(
+            [float(self.aggregation_period) if self.temporal_aggregation.get(v) == "sum" else 1.0 for v in self.observed_states]
+        )
+
+
+def prepare_mixed_frequency_data(low_freq_data, high_freq: str, aggregation_period: int = 4, observation_position: str = "last"):
+    """Expand low-frequency data to the model's frequency with NaN at the unobserved periods (the filter masks them).
+    Same signature and placement rule as gEconpy/model/statespace.py:1432-1509."""
+    import pandas as pd
+
+    if observation_position not in ("first", "last"):
+        raise ValueError("observation_position must be 'first' or 'last'")
+    pos = 0 if observation_position == "first" else aggregation_period - 1
+    hf_index = pd.date_range(start=low_freq_data.index.min(), periods=len(low_freq_data) * aggregation_period, freq=high_freq)
+    out = pd.DataFrame(np.nan, index=hf_index, columns=list(low_freq_data.columns))
+    for lf_date, row in low_freq_data.iterrows():
+        window = hf_index[hf_index >= lf_date][:aggregation_period]
+        if len(window) > pos:
+            out.loc[window[pos]] = row
+    last = out.last_valid_index()
+    if last is not None:
+        out = out.loc[:last]
+    out.index.freq = out.index.inferred_freq
+    return out

@@ -17,6 +17,7 @@ import numpy as np
 
 from .. import _lib as L
 from ..build import build_model
+from .augmentation import StateAugmentation
 from .codegen import LinearizedModel, load_spec
 
 try:
@@ -126,7 +127,14 @@ class BatchedStateSpace:
         check_bk: bool = True,
         chunk: int = 65536,
         reduce_state: bool = True,
+        temporal_aggregation: dict | None = None,
+        aggregation_period: int = 4,
+        ss_obs_intercept: list | None = None,
     ):
+        """Same meaning as ``DSGEStateSpace.configure`` (gEconpy/model/statespace.py:822-1090) for the arguments it
+        shares: ``temporal_aggregation`` {"sum" | "mean" | "first" | "last"} with ``aggregation_period`` adds cumulator
+        states (statespace.py:598-650), ``ss_obs_intercept`` puts log x_ss(theta) / x_ss(theta) of the listed observed
+        states into the observation intercept d (statespace.py:363-388)."""
         m = self.model
         if solver not in ("cycle_reduction", "gensys"):
             raise NotImplementedError(f"solver={solver!r}: the B200 path solves by cycle reduction (gensys maps to CR + BK flag)")
@@ -148,7 +156,9 @@ class BatchedStateSpace:
         self.p = len(observed_states)
         # filter runs in solver order: observed variable -> permuted position (T, R are not un-permuted in between)
         self.obs_idx = m.inv_var_order[[m.var_names.index(v) for v in observed_states]].astype(np.int32)
-        self.err_pos = np.array([observed_states.index(v) for v in measurement_error], dtype=np.int64)
+        # the reference puts the error variances at positions 0..len(error_states)-1 of diag(H), whatever the position of
+        # those states among the observed ones (statespace.py:800-808, "mirror the previous semantics"): reproduced
+        self.err_pos = np.arange(len(measurement_error), dtype=np.int64)
         # The likelihood only depends on the lagged (state) variables and the observed variables: every other column of
         # T is identically zero, so those variables never feed back into the recursion.  With reduce_state the solver
         # kernel hands the filter the exact sub-blocks T[U][:, U], R[U] for U = states + observed (solver order).
@@ -157,6 +167,24 @@ class BatchedStateSpace:
         self.n_filter = int(self.filter_vars.size)
         self.obs_idx_filter = np.array([int(np.flatnonzero(self.filter_vars == o)[0]) for o in self.obs_idx], dtype=np.int32)
         self.reduce_state = bool(reduce_state)
+        # ---- state augmentation (cumulators) and the observation intercept
+        ss_obs_intercept = list(ss_obs_intercept or [])
+        unknown = [v for v in ss_obs_intercept if v not in observed_states]
+        if unknown:
+            raise ValueError(f"The following ss_obs_intercept entries are not in observed_states: {', '.join(unknown)}")
+        self.aug = StateAugmentation(
+            [m.lin.vars_perm[int(u)] for u in self.filter_vars], list(observed_states), dict(temporal_aggregation or {}), int(aggregation_period)
+        )
+        self.n_aug = self.aug.k_states
+        if self.n_aug > 64:
+            raise NotImplementedError(f"augmented state dimension {self.n_aug} > 64")
+        self.dense_Z = None if self.aug.is_selector() else np.ascontiguousarray(self.aug.design_matrix())
+        self.ss_obs_intercept = ss_obs_intercept
+        loglin = set(m.var_names) - set(m.lin.not_loglin_variables) if m.lin.log_linearize else set()
+        self._d_pos = np.array([observed_states.index(v) for v in ss_obs_intercept], dtype=np.int64)
+        self._d_var = np.array([m.var_names.index(v) for v in ss_obs_intercept], dtype=np.int64)
+        self._d_loglin = np.array([v in loglin for v in ss_obs_intercept], dtype=bool)
+        self._d_scale = self.aug.intercept_scale()[self._d_pos] if ss_obs_intercept else np.zeros(0)
         self.tol, self.max_iter, self.solver_tol = float(tol), int(max_iter), float(solver_tol)
         self.cov_jitter, self.missing_fill_value, self.mvn_const = float(cov_jitter), float(missing_fill_value), mvn_const
         self.check_bk = bool(check_bk)
@@ -180,12 +208,25 @@ class BatchedStateSpace:
             nc=nc, device=device,
             theta=torch.empty((nc, m.n_theta), **f64), sig=torch.empty((nc, m.k), **f64), herr=torch.zeros((nc, self.p), **f64),
             A=torch.empty((nc, m.n, m.n), **f64), B=torch.empty((nc, m.n, m.n), **f64), C=torch.empty((nc, m.n, m.n), **f64),
-            D=torch.empty((nc, m.n, m.k), **f64), T=torch.empty((nc, self.n_filter, self.n_filter), **f64),
-            R=torch.empty((nc, self.n_filter, m.k), **f64), subset=torch.as_tensor(self.filter_vars, **i32),
+            D=torch.empty((nc, m.n, m.k), **f64), T=torch.zeros((nc, self.n_aug, self.n_aug), **f64),
+            R=torch.zeros((nc, self.n_aug, m.k), **f64), subset=torch.as_tensor(self.filter_vars, **i32),
             status=torch.empty((nc,), **i32), n_iter=torch.empty((nc,), **i32), n_unstable=torch.empty((nc,), **i32),
             resid=torch.empty((nc,), **f64),
             lead=torch.as_tensor(m.permuted_lead_var_idx, **i32), obs=torch.as_tensor(self.obs_idx_filter, **i32),
         )  # fmt: skip
+        if self.n_aug > self.n_filter:
+            # constant rows [F | kron(I, shift)] of the augmented transition: written once, the solver kernel only ever
+            # writes the top-left n_filter x n_filter block (t_ld / t_stride) and the top n_filter rows of R
+            ws["T"][:, self.n_filter :, :] = torch.as_tensor(self.aug.transition_rows(), **f64)
+        if self.dense_Z is not None:
+            ws["Z"] = torch.as_tensor(self.dense_Z, **f64)
+        if self.ss_obs_intercept:
+            ws["xss"] = torch.empty((nc, m.n), **f64)
+            ws["d"] = torch.zeros((nc, self.p), **f64)
+            ws["d_var"] = torch.as_tensor(self._d_var, device=device)
+            ws["d_pos"] = torch.as_tensor(self._d_pos, device=device)
+            ws["d_loglin"] = torch.as_tensor(self._d_loglin, device=device)
+            ws["d_scale"] = torch.as_tensor(self._d_scale, **f64)
         self._ws = ws
         return ws
 
@@ -231,8 +272,11 @@ class BatchedStateSpace:
                 ws["herr"][:cnt, self.err_pos] = th[:, m.n_theta + m.k :]
             st = ws["status"][:cnt]
             e = mark("jacobian")
-            m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], None, st, stream)
+            m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
             e and e.record()
+            if self.ss_obs_intercept:  # d = log x_ss / x_ss of the listed observed states (x aggregation period for "sum")
+                xs = ws["xss"][:cnt].index_select(1, ws["d_var"])
+                ws["d"][:cnt].index_copy_(1, ws["d_pos"], torch.where(ws["d_loglin"], xs.log(), xs) * ws["d_scale"])
             cr = L.CrArgs(
                 struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
                 D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
@@ -240,6 +284,7 @@ class BatchedStateSpace:
                 status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
                 n_out=self.n_filter, n_lead=(int(ws["lead"].numel()) if self.check_bk else 0),
                 lead_idx=(ws["lead"].data_ptr() if self.check_bk else None), n_unstable=ws["n_unstable"].data_ptr(),
+                t_stride=self.n_aug * self.n_aug, r_stride=self.n_aug * m.k, t_ld=self.n_aug,
             )  # fmt: skip
             e = mark("cr_solve")
             L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
@@ -256,8 +301,11 @@ class BatchedStateSpace:
                 e and e.record()
             kf = L.KalmanArgs(
                 struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), qdiag=ws["sig"].data_ptr(),
-                q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p, Z=None,
-                obs_idx=ws["obs"].data_ptr(), d=None, d_stride=0, Y=Y.data_ptr(), P0=None, N=cnt, n=self.n_filter, k=m.k, p=self.p,
+                q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
+                Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None), z_stride=0,
+                obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
+                d=(ws["d"].data_ptr() if self.ss_obs_intercept else None), d_stride=(self.p if self.ss_obs_intercept else 0),
+                Y=Y.data_ptr(), P0=None, N=cnt, n=self.n_aug, k=m.k, p=self.p,
                 Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
                 mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
                 gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),

@@ -96,6 +96,14 @@ typedef struct gecon_cr_args {
     double* solv_norms;     /* [N][2] out or NULL: (norm_deterministic, norm_stochastic) of solvability_check
                                (statistics/perturbation_diagnostics.py:105-161, model/perturbation.py:287-380) */
     double trunc_tol;       /* entries of T, R below this are zeroed before the norms (the reference's `tol`) */
+    /* Strided outputs (device entry point only; 0 = dense).  They let the solver write T, R straight into the top-left
+     * block of a pre-initialised AUGMENTED transition / selection pair [[T, 0], [F, C]], [[R], [0]] (cumulator and
+     * observation-lag states of gEconpy/model/statespace.py:598-723): the constant rows are filled once and never
+     * touched, so augmentation costs no extra pass over HBM. */
+    int64_t t_stride;       /* doubles between consecutive draws of T (0: n_out * n_out) */
+    int64_t r_stride;       /* doubles between consecutive draws of R (0: n_out * k) */
+    int32_t t_ld;           /* leading dimension of a draw's T (0: n_out) */
+    int32_t reserved1;
 } gecon_cr_args;
 
 int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream);
@@ -156,7 +164,8 @@ int gecon_dlyap_host(const gecon_dlyap_args* args);
  * Kalman-filter log-likelihood (pymc_extras StandardFilter semantics: update -> jitter -> predict, Joseph form,
  * missing observations masked out of Z and H, a0 = 0, P0 = dlyap(T, R Q R') unless P0 is given):
  *   x_t = T x_{t-1} + R eps_t, eps ~ N(0, diag(q));   y_t = d + Z x_t + eta_t, eta ~ N(0, diag(h)).
- * Z is either dense (p x n, shared by all draws) or a selector given by obs_idx (Z[a][obs_idx[a]] = 1).
+ * Z is either dense (p x n, shared by all draws or one per draw: z_stride) or a selector given by obs_idx
+ * (Z[a][obs_idx[a]] = 1).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct gecon_kalman_args {
     size_t struct_size;
@@ -166,7 +175,7 @@ typedef struct gecon_kalman_args {
     int64_t q_stride;    /* k or 0 */
     const double* hdiag; /* measurement-error variances, [N][p] or shared [p]; NULL = 0 */
     int64_t h_stride;    /* p or 0 */
-    const double* Z;     /* [p][n] shared, or NULL when obs_idx is given */
+    const double* Z;     /* [p][n] shared or [N][p][n] (z_stride = p n), or NULL when obs_idx is given */
     const int32_t* obs_idx; /* [p] or NULL */
     const double* d;     /* observation intercept: [N][p] (d_stride = p), shared [p] (0), or NULL = 0 */
     int64_t d_stride;
@@ -189,6 +198,8 @@ typedef struct gecon_kalman_args {
     double* ll;           /* [N] out */
     int32_t* status;      /* [N] out: status_in | new bits (may alias status_in) */
     double* ll_t;         /* [N][Tobs] out or NULL: per-observation log-likelihood */
+    int64_t z_stride;     /* 0: Z is shared by all draws; p * n: Z is [N][p][n], one design matrix per draw (parameter-
+                             dependent observation equations, statespace.py:299-331) */
 } gecon_kalman_args;
 
 int gecon_kalman_ll_batched(const gecon_kalman_args* args, void* stream);

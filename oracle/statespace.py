@@ -187,6 +187,101 @@ def loglik_from_matrices(
     return out
 
 
+CUMULATOR_AGGREGATIONS = ("sum", "mean")  # gEconpy/model/statespace.py:48
+
+
+def cumulator_variables(temporal_aggregation):
+    """gEconpy/model/statespace.py:561-571 (no observation equations): insertion order of the dict."""
+    return [v for v, m in (temporal_aggregation or {}).items() if m in CUMULATOR_AGGREGATIONS]
+
+
+def augment_transition(T, var_names, temporal_aggregation, aggregation_period):
+    """gEconpy/model/statespace.py:598-650: T_aug = [[T, 0], [F, kron(I, shift)]]; F copies each aggregated variable
+    into the first slot of its chain, ``shift`` moves the chain down by one slot per period."""
+    cum = cumulator_variables(temporal_aggregation)
+    if not cum:
+        return T
+    k_orig = T.shape[0]
+    n_lags = aggregation_period - 1
+    n_cum = len(cum) * n_lags
+    shift = np.zeros((n_lags, n_lags))
+    if n_lags > 1:
+        shift[np.arange(1, n_lags), np.arange(n_lags - 1)] = 1.0
+    Cc = np.kron(np.eye(len(cum)), shift)
+    F = np.zeros((n_cum, k_orig))
+    for pos, name in enumerate(cum):
+        F[pos * n_lags, var_names.index(name)] = 1.0
+    return np.block([[T, np.zeros((k_orig, n_cum))], [F, Cc]])
+
+
+def augment_selection(R, n_extra):
+    """gEconpy/model/statespace.py:696-723: zero rows for the deterministic lag copies."""
+    return R if n_extra == 0 else np.vstack([R, np.zeros((n_extra, R.shape[1]))])
+
+
+def design_matrix(var_names, observed, temporal_aggregation, aggregation_period):
+    """gEconpy/model/statespace.py:279-296 (selector path): weight 1 (or 1/s for "mean") on the variable's column and
+    on its cumulator slots; "first"/"last"/unaggregated variables get a plain selector row."""
+    ta = temporal_aggregation or {}
+    cum = cumulator_variables(ta)
+    n_lags = aggregation_period - 1
+    k_orig = len(var_names)
+    Z = np.zeros((len(observed), k_orig + len(cum) * n_lags))
+    for i, name in enumerate(observed):
+        j = var_names.index(name)
+        m = ta.get(name)
+        if m in CUMULATOR_AGGREGATIONS:
+            w = 1.0 / aggregation_period if m == "mean" else 1.0
+            start = k_orig + cum.index(name) * n_lags
+            Z[i, j] = w
+            Z[i, start : start + n_lags] = w
+        else:
+            Z[i, j] = 1.0
+    return Z
+
+
+def obs_intercept(x_ss, var_names, observed, ss_obs_intercept, log_linearized, temporal_aggregation, aggregation_period):
+    """gEconpy/model/statespace.py:363-388: log x_ss (log-linearised) or x_ss (level) for the listed states, zero for the
+    others; "sum" aggregation multiplies the per-period intercept by the aggregation period."""
+    ta = temporal_aggregation or {}
+    d = np.zeros(len(observed))
+    for i, name in enumerate(observed):
+        if name not in (ss_obs_intercept or []):
+            continue
+        v = x_ss[var_names.index(name)]
+        base = np.log(v) if name in log_linearized else v
+        d[i] = aggregation_period * base if ta.get(name) == "sum" else base
+    return d
+
+
+def loglik_augmented(
+    model, theta, Y, observed, sigma_shock, sigma_err=None, temporal_aggregation=None, aggregation_period=4,
+    ss_obs_intercept=None, log_linearized=None, tol=1e-8, max_iter=1000, solver_tol=1e-8, jitter=JITTER_DEFAULT,
+    mvn_const="per_obs",
+):  # fmt: skip
+    """theta -> logp with temporal aggregation and steady-state intercepts: make_symbolic_graph's sequence
+    (gEconpy/model/statespace.py:769-820) -- solve, un-permute, augment T and R, build Z and d, P0 of the AUGMENTED
+    system, filter, gate."""
+    base = loglik(model, theta, np.zeros((1, len(observed))), observed, sigma_shock, None, tol=tol, max_iter=max_iter, solver_tol=solver_tol)
+    T, R = base["T"], base["R"]
+    names = model.var_names
+    ta = temporal_aggregation or {}
+    T_aug = augment_transition(T, names, ta, aggregation_period)
+    R_aug = augment_selection(R, T_aug.shape[0] - T.shape[0])
+    Z = design_matrix(names, observed, ta, aggregation_period)
+    loglin = set(names) if log_linearized is None else set(log_linearized)
+    d = obs_intercept(model.steady_state(theta), names, observed, ss_obs_intercept, loglin, ta, aggregation_period)
+    Q = np.diag(np.asarray(sigma_shock, dtype=np.float64) ** 2)
+    p = len(observed)
+    H = np.zeros((p, p)) if sigma_err is None else np.diag(np.asarray(sigma_err, dtype=np.float64) ** 2)
+    with np.errstate(all="ignore"):
+        P0 = dlyap(T_aug, R_aug @ Q @ R_aug.T)
+        ll_raw = kalman_loglik(Y, T_aug, R_aug, Q, Z, H, d=d, P0=P0, jitter=jitter, mvn_const=mvn_const) if np.all(np.isfinite(P0)) else np.nan
+    out = dict(base)
+    out.update(T_aug=T_aug, R_aug=R_aug, Z=Z, d=d, P0=P0, ll_raw=ll_raw, ll=ll_raw if base["ok"] else -np.inf)
+    return out
+
+
 def loglik(model, theta, Y, observed, sigma_shock, sigma_err=None, **kwargs):
     """theta -> logp for an ``oracle.model.OracleModel`` (the path of SURVEY.md section 3.3, without priors)."""
     A, B, C, D = model.jacobians(theta, mode="statespace")

@@ -1,0 +1,93 @@
+"""State-augmentation bookkeeping: host logic and oracle against golden vectors produced by the
+reference's own ``_make_design_matrix`` / ``prepare_mixed_frequency_data`` (tests/golden/make_augmentation_goldens.py)."""
+
+from __future__ import annotations
+
+import json
+
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import statespace as oss
+
+from geconpy_b200.model.augmentation import StateAugmentation, prepare_mixed_frequency_data
+
+GOLD = json.loads((Path(__file__).parent / "golden" / "ref_augmentation.json").read_text())
+
+
+@pytest.mark.parametrize("g", GOLD["design"], ids=lambda g: "-".join(f"{k}{v}" for k, v in g["case"]["ta"].items()) or "none")
+def test_design_matrix_and_names_match_the_reference(g):
+    c = g["case"]
+    aug = StateAugmentation(c["states"], c["observed"], c["ta"], c["period"])
+    Zref = np.array(g["Z"])
+    assert aug._cumulator_variables == g["cumulator_variables"]
+    assert aug._cumulator_state_names == g["cumulator_state_names"]
+    assert aug._n_cumulator_states == g["n_cumulator_states"]
+    assert np.array_equal(aug.design_matrix(), Zref)
+    # the oracle restatement agrees with the reference too
+    assert np.array_equal(oss.design_matrix(c["states"], c["observed"], c["ta"], c["period"]), Zref)
+
+
+@pytest.mark.parametrize("g", GOLD["design"], ids=lambda g: "-".join(f"{k}{v}" for k, v in g["case"]["ta"].items()) or "none")
+def test_augmented_transition_is_a_lag_chain(g):
+    """Known answer: with x_t = T x_{t-1}, the augmented state carries x_{t-1}, ..., x_{t-s+1} of each aggregated
+    variable, so Z s_t equals the windowed sum / mean of the un-augmented path (statespace.py:598-650)."""
+    c = g["case"]
+    rng = np.random.default_rng(0)
+    k = len(c["states"])
+    T = 0.4 * rng.standard_normal((k, k))
+    aug = StateAugmentation(c["states"], c["observed"], c["ta"], c["period"])
+    Ta = aug.augment_transition(T)
+    assert np.array_equal(Ta, oss.augment_transition(T, c["states"], c["ta"], c["period"]))
+    assert np.array_equal(aug.augment_selection(np.ones((k, 2)))[k:], np.zeros((aug._n_cumulator_states, 2)))
+    x = [rng.standard_normal(k)]
+    s = np.concatenate([x[0], np.zeros(aug._n_cumulator_states)])
+    Z = aug.design_matrix()
+    for t in range(1, 12):
+        x.append(T @ x[-1])
+        s = Ta @ s
+        if t >= c["period"]:
+            for i, name in enumerate(c["observed"]):
+                j = c["states"].index(name)
+                m = c["ta"].get(name)
+                if m in ("sum", "mean"):
+                    w = sum(x[t - d][j] for d in range(c["period"]))
+                    w = w / c["period"] if m == "mean" else w
+                else:
+                    w = x[t][j]
+                assert abs(Z[i] @ s - w) < 1e-12
+
+
+def test_batched_augment_matches_single():
+    aug = StateAugmentation(["a", "b", "c"], ["b"], {"b": "sum"}, 3)
+    T = np.random.default_rng(1).standard_normal((5, 3, 3))
+    Ta = aug.augment_transition(T)
+    assert Ta.shape == (5, 5, 5)
+    for i in range(5):
+        assert np.array_equal(Ta[i], oss.augment_transition(T[i], ["a", "b", "c"], {"b": "sum"}, 3))
+
+
+def test_validation_errors():
+    with pytest.raises(ValueError, match="not in observed_states"):
+        StateAugmentation(["a", "b"], ["a"], {"b": "sum"}, 4)
+    with pytest.raises(ValueError, match="aggregation_period"):
+        StateAugmentation(["a", "b"], ["a"], {"a": "sum"}, 1)
+    with pytest.raises(ValueError, match="Unknown temporal aggregation"):
+        StateAugmentation(["a", "b"], ["a"], {"a": "median"}, 4)
+
+
+@pytest.mark.parametrize("g", GOLD["mixed_frequency"], ids=lambda g: f"{g['position']}-{g['period']}")
+def test_prepare_mixed_frequency_data_matches_the_reference(g):
+    annual = pd.DataFrame({"GDP": [100.0, 110.0, 121.0], "R": [0.05, 0.04, 0.03]}, index=pd.to_datetime(["2020", "2021", "2022"]))
+    df = prepare_mixed_frequency_data(annual, high_freq=g["freq"], aggregation_period=g["period"], observation_position=g["position"])
+    assert [str(t.date()) for t in df.index] == g["index"]
+    ref = np.array([[np.nan if x is None else x for x in row] for row in g["values"]])
+    assert np.array_equal(df.to_numpy(), ref, equal_nan=True)
+
+
+def test_oracle_intercept_and_sum_rule():
+    d = oss.obs_intercept(np.array([2.0, 3.0, 4.0]), ["a", "b", "c"], ["c", "a", "b"], ["a", "c"], {"a"}, {"c": "sum", "a": "mean"}, 4)
+    assert np.allclose(d, [16.0, np.log(2.0), 0.0])
