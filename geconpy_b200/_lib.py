@@ -157,6 +157,51 @@ class KalmanArgs(C.Structure):
     ]
 
 
+class KalmanGradArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("T", C.c_void_p),
+        ("R", C.c_void_p),
+        ("qdiag", C.c_void_p),
+        ("q_stride", C.c_int64),
+        ("hdiag", C.c_void_p),
+        ("h_stride", C.c_int64),
+        ("Z", C.c_void_p),
+        ("obs_idx", C.c_void_p),
+        ("d", C.c_void_p),
+        ("d_stride", C.c_int64),
+        ("Y", C.c_void_p),
+        ("N", C.c_int64),
+        ("n", C.c_int32),
+        ("k", C.c_int32),
+        ("p", C.c_int32),
+        ("Tobs", C.c_int32),
+        ("jitter", C.c_double),
+        ("missing_fill", C.c_double),
+        ("mvn_const_mode", C.c_int32),
+        ("lyap_max_iter", C.c_int32),
+        ("status_in", C.c_void_p),
+        ("gate_mask", C.c_int32),
+        ("sigma_inputs", C.c_int32),
+        ("ll", C.c_void_p),
+        ("status", C.c_void_p),
+        ("T_bar", C.c_void_p),
+        ("R_bar", C.c_void_p),
+        ("q_bar", C.c_void_p),
+        ("h_bar", C.c_void_p),
+        ("d_bar", C.c_void_p),
+    ]
+
+
+class PolicyAdjointArgs(C.Structure):
+    _fields_ = (
+        [("struct_size", C.c_size_t)]
+        + [(f, C.c_void_p) for f in ("A", "B", "C", "D", "T", "R", "T_bar", "R_bar")]
+        + [("N", C.c_int64), ("n", C.c_int32), ("k", C.c_int32), ("max_iter", C.c_int32), ("reserved0", C.c_int32)]
+        + [(f, C.c_void_p) for f in ("A_bar", "B_bar", "C_bar", "D_bar", "status")]
+    )
+
+
 class PropagateArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_size_t),
@@ -193,6 +238,10 @@ EXPORTS = {
     "gecon_kalman_ll_host": (C.c_int, [C.POINTER(KalmanArgs)]),
     "gecon_propagate_batched": (C.c_int, [C.POINTER(PropagateArgs), C.c_void_p]),
     "gecon_propagate_host": (C.c_int, [C.POINTER(PropagateArgs)]),
+    "gecon_kalman_grad_batched": (C.c_int, [C.POINTER(KalmanGradArgs), C.c_void_p]),
+    "gecon_kalman_grad_host": (C.c_int, [C.POINTER(KalmanGradArgs)]),
+    "gecon_policy_adjoint_batched": (C.c_int, [C.POINTER(PolicyAdjointArgs), C.c_void_p]),
+    "gecon_policy_adjoint_host": (C.c_int, [C.POINTER(PolicyAdjointArgs)]),
     "gecon_solve_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gecon_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "gecon_gemm_batched": (

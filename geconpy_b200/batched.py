@@ -328,6 +328,93 @@ def kalman_loglik(
     return (ll, st, llt) if return_per_step else (ll, st)
 
 
+def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None, jitter=1e-8, missing_fill=-9999.0,
+                       mvn_const="per_obs", status_in=None, gate_mask=0, sigma_inputs=False, lyap_max_iter=0):
+    """Log-likelihood AND its gradient (``gecon_kalman_grad_*``): returns a dict with ``ll`` [N],
+    ``status`` [N], ``T`` [N,n,n], ``R`` [N,n,k], ``q`` [N,k], ``h`` [N,p], ``d`` [N,p] -- the derivatives of ll with
+    respect to the arguments of the same name (``q``/``h`` w.r.t. the standard deviations when ``sigma_inputs``).
+    What pytensor differentiates behind ``build_statespace_graph`` (gEconpy/model/statespace.py:812-820,1151-1157)."""
+    if (Z is None) == (obs_idx is None):
+        raise ValueError("give exactly one of Z (dense design matrix) and obs_idx (selector)")
+    m = _marshal_for(T, R)
+    T, pT = m.inp(T)
+    R, pR = m.inp(R)
+    T, squeeze = _batch3(T)
+    N, n = T.shape[0], T.shape[1]
+    k = R.shape[-1]
+    Ya, pY = m.inp(Y)
+    Tobs, p = (Ya.shape[0], 1) if Ya.ndim == 1 else Ya.shape
+    q, pq = m.inp(qdiag)
+    h, ph = m.inp(hdiag)
+    dd, pd_ = m.inp(d)
+    _, pZ = m.inp(Z)
+    _, pO = m.inp(None if obs_idx is None else np.ascontiguousarray(obs_idx, dtype=np.int32), np.int32)
+    _, pSin = m.inp(status_in, np.int32)
+    ll, pll = m.out((N,))
+    st, pS = m.out((N,), np.int32)
+    Tb, pTb = m.out((N, n, n))
+    Rb, pRb = m.out((N, n, k))
+    qb, pqb = m.out((N, k))
+    hb, phb = m.out((N, p))
+    db, pdb = m.out((N, p))
+    args = L.KalmanGradArgs(
+        struct_size=C.sizeof(L.KalmanGradArgs), T=pT, R=pR, qdiag=pq, q_stride=(k if q.ndim == 2 else 0), hdiag=ph,
+        h_stride=(p if (h is not None and h.ndim == 2) else 0), Z=pZ, obs_idx=pO, d=pd_,
+        d_stride=(p if (dd is not None and dd.ndim == 2) else 0), Y=pY, N=N, n=n, k=k, p=p, Tobs=Tobs, jitter=float(jitter),
+        missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1), lyap_max_iter=int(lyap_max_iter),
+        status_in=pSin, gate_mask=int(gate_mask), sigma_inputs=int(bool(sigma_inputs)), ll=pll, status=pS, T_bar=pTb, R_bar=pRb,
+        q_bar=pqb, h_bar=phb, d_bar=pdb,
+    )  # fmt: skip
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_kalman_grad_batched(C.byref(args), m.stream()), "gecon_kalman_grad_batched")
+    else:
+        L.check(lib.gecon_kalman_grad_host(C.byref(args)), "gecon_kalman_grad_host")
+    out = dict(ll=ll, status=st, T=Tb, R=Rb, q=qb, h=hb, d=db)
+    if squeeze:
+        out = {key: val[0] for key, val in out.items()}
+    return out
+
+
+def policy_adjoints(A, B, C_, T, T_bar, D=None, R=None, R_bar=None, max_iter=0):
+    """Reverse mode of the perturbation solution (``gecon_policy_adjoint_*``): returns (A_bar, B_bar, C_bar, D_bar, status).
+    ``o1_policy_function_adjoints`` (gEconpy/solvers/shared.py:12-71) when only ``T_bar`` is given; with ``D, R, R_bar``
+    the selection matrix ``R = -(C T + B)^-1 D`` (shared.py:74-75) is differentiated too (``D_bar`` is None otherwise)."""
+    with_r = R_bar is not None
+    if with_r and (D is None or R is None):
+        raise ValueError("R_bar needs D and R")
+    m = _marshal_for(A, B, C_, T, T_bar)
+    A, pA = m.inp(A)
+    B, pB = m.inp(B)
+    Cc, pC = m.inp(C_)
+    T, pT = m.inp(T)
+    Tb, pTb = m.inp(T_bar)
+    A, squeeze = _batch3(A)
+    N, n = A.shape[0], A.shape[1]
+    Dd, pD = m.inp(D if with_r else None)
+    Rr, pR = m.inp(R if with_r else None)
+    Rb, pRb = m.inp(R_bar)
+    k = Dd.shape[-1] if with_r else 0
+    Ab, pAb = m.out((N, n, n))
+    Bb, pBb = m.out((N, n, n))
+    Cb, pCb = m.out((N, n, n))
+    Db, pDb = m.out((N, n, k)) if with_r else (None, None)
+    st, pS = m.out((N,), np.int32)
+    args = L.PolicyAdjointArgs(
+        struct_size=C.sizeof(L.PolicyAdjointArgs), A=pA, B=pB, C=pC, D=pD, T=pT, R=pR, T_bar=pTb, R_bar=pRb, N=N, n=n, k=k,
+        max_iter=int(max_iter), A_bar=pAb, B_bar=pBb, C_bar=pCb, D_bar=pDb, status=pS,
+    )  # fmt: skip
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_policy_adjoint_batched(C.byref(args), m.stream()), "gecon_policy_adjoint_batched")
+    else:
+        L.check(lib.gecon_policy_adjoint_host(C.byref(args)), "gecon_policy_adjoint_host")
+    if squeeze:
+        Ab, Bb, Cb, st = Ab[0], Bb[0], Cb[0], st[0]
+        Db = None if Db is None else Db[0]
+    return Ab, Bb, Cb, Db, st
+
+
 def solve(M, RHS):
     """Batched general solve with partial pivoting (``gecon_solve_*``): returns (X, status)."""
     m = _marshal_for(M, RHS)

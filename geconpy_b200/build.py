@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 MODEL_LIBDIR = LIBDIR / "models"
 CORE_LIB = LIBDIR / "libgecon_b200.so"
-CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu"]
+CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu", "grad.cu"]
 # the Kalman kernel is instantiated for (NP, p) in 8 x 8 combinations: one object per padded dimension NP, built in parallel
 KALMAN_INST = "kalman_inst.cu"
 KALMAN_NPS = [8, 16, 24, 32, 40, 48, 56, 64]
@@ -62,7 +62,7 @@ def _run(cmd):
 def build_core(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu -> _lib/libgecon_b200.so (skipped when the sources are unchanged)."""
     LIBDIR.mkdir(exist_ok=True)
-    deps = [CSRC / s for s in CORE_SOURCES + [KALMAN_INST]] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "gecon_b200.h"]
+    deps = [CSRC / s for s in CORE_SOURCES + [KALMAN_INST]] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "gecon_b200.h"]
     stamp = LIBDIR / "libgecon_b200.stamp"
     dig = _digest(deps, NVCC_FLAGS)
     if not force and CORE_LIB.exists() and stamp.exists() and stamp.read_text() == dig:

@@ -1,0 +1,752 @@
+// Gradient path: reverse-mode kernels for the Kalman log-likelihood and for the policy function.
+//
+// What the reference differentiates with pytensor for NUTS (gEconpy/model/statespace.py:812-820,1151-1157 through the
+// solver Ops' pullbacks, gEconpy/solvers/cycle_reduction.py:212-213 -> gEconpy/solvers/shared.py:12-71) is done here as
+// two hand-written sweeps per draw, one CTA per draw:
+//
+//   kalman_grad_draw   forward filter storing the predicted moments (a_t, P_t) of every step in a per-CTA trajectory
+//                      buffer, then the reverse sweep:  ll,  dll/dT, dll/dR, dll/dq, dll/dh, dll/dd
+//                      (adjoint of P0 = dlyap(T, R Q R') by a second Smith doubling, S = T' S T + P0_bar)
+//   policy_adjoint_draw  R = -(C T + B)^-1 D and A + B T + C T T = 0 in reverse:  the multipliers of
+//                      o1_policy_function_adjoints solve W' S + C' S T' = -T_bar (W = C T + B); instead of the
+//                      reference's n^2 x n^2 Kronecker system this is the Stein equation S = Q + G S T',
+//                      G = -W^-T C', Q = -W^-T T_bar, solved by doubling (rho(G) rho(T) < 1 under Blanchard-Kahn)
+//
+// Every phase is a data-parallel loop over output elements (GFOR) separated by barriers (GSYNC), and nothing else:
+// the same source compiles as plain C++ with -DGECON_HOST_CHECK (one "thread", barriers vanish), which is how the
+// CPU test-suite checks the arithmetic against oracle/adjoints.py without a GPU (tests/test_adjoints_cpu.py).
+// Plain DFMA inner products on odd-leading-dimension shared tiles; these kernels are a first correct gradient path,
+// not yet tuned like the forward filter.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef GECON_HOST_CHECK
+#define GHD inline
+#define GHH inline
+#define G_TID 0
+#define G_NT 1
+#define GSYNC() \
+    do {        \
+    } while (0)
+#else
+#define GHD __device__ __forceinline__
+#define GHH __host__ __device__ __forceinline__
+#define G_TID ((int)threadIdx.x)
+#define G_NT ((int)blockDim.x)
+#define GSYNC() __syncthreads()
+#endif
+#define GFOR(i, count) for (int i = G_TID; i < (count); i += G_NT)
+
+namespace gecon_grad {
+
+constexpr int PMAXG = 8;
+constexpr int ST_SINGULAR = 0x004, ST_LYAP = 0x040, ST_NOT_PD = 0x080, ST_LL_NONFINITE = 0x100;
+
+GHH int ldim(int n) { return n | 1; }  // odd leading dimension: column walks hit distinct 8-byte banks
+
+// C (m x n, ldc) = alpha * op(A) * op(B) + beta * C;  op(A) is m x kk, op(B) is kk x n.  C must not alias A or B.
+template <bool TA, bool TB>
+GHD void mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n, int kk, double alpha, double beta) {
+    GFOR(idx, m * n) {
+        const int i = idx / n, j = idx - i * n;
+        double s = 0.0;
+        for (int k = 0; k < kk; ++k) s = fma(TA ? A[k * lda + i] : A[i * lda + k], TB ? B[j * ldb + k] : B[k * ldb + j], s);
+        C[i * ldc + j] = (beta != 0.0) ? fma(alpha, s, beta * C[i * ldc + j]) : alpha * s;
+    }
+}
+
+// max |x| over m x n (NaN-propagating: a NaN makes the result NaN); s_red: G_NT doubles.  Contains barriers.
+GHD double absmax(const double* X, int ldx, int m, int n, double* s_red) {
+    double mx = 0.0;
+    GFOR(idx, m * n) {
+        const int i = idx / n, j = idx - i * n;
+        const double a = fabs(X[i * ldx + j]);
+        if (a > mx || a != a) mx = a;
+    }
+    s_red[G_TID] = mx;
+    GSYNC();
+    double r = 0.0;
+    for (int t = 0; t < G_NT; ++t) {
+        const double a = s_red[t];
+        if (a > r || a != a) r = a;
+    }
+    GSYNC();
+    return r;
+}
+
+// In-place inverse of the SPD p x p matrix F (row-major, ld = PMAXG) by Gauss-Jordan without pivoting, executed by one
+// thread; returns log det F through *logdet and false if a pivot is not positive.
+GHD bool spd_inverse_small(double* F, int p, double* logdet) {
+    double ld = 0.0;
+    bool ok = true;
+    for (int c = 0; c < p; ++c) {
+        const double piv = F[c * PMAXG + c];
+        ok = ok && (piv > 0.0);
+        ld += log(piv);
+        const double inv = 1.0 / piv;
+        for (int j = 0; j < p; ++j) F[c * PMAXG + j] *= inv;
+        F[c * PMAXG + c] = inv;
+        for (int i = 0; i < p; ++i) {
+            if (i == c) continue;
+            const double f = F[i * PMAXG + c];
+            F[i * PMAXG + c] = 0.0;
+            for (int j = 0; j < p; ++j) F[i * PMAXG + j] = fma(-f, F[c * PMAXG + j], F[i * PMAXG + j]);
+        }
+    }
+    *logdet = ld;
+    return ok;
+}
+
+struct KalmanGradArgs {
+    const double* T;      // [N][n][n]
+    const double* R;      // [N][n][k]
+    const double* qdiag;  // [N][k] or [k]
+    long long q_stride;
+    const double* hdiag;  // [N][p], [p] or NULL
+    long long h_stride;
+    const double* Z;        // [p][n] shared, or NULL
+    const int32_t* obs_idx;  // [p] or NULL
+    const double* d;        // [N][p], [p] or NULL
+    long long d_stride;
+    const double* Y;  // [Tobs][p]
+    long long N;
+    int n, k, p, Tobs;
+    double jitter, missing_fill;
+    int mvn_const_mode, lyap_max_iter;
+    const int32_t* status_in;
+    int gate_mask, sigma_inputs;
+    double* ll;       // [N]
+    int32_t* status;  // [N]
+    double* T_bar;    // [N][n][n]
+    double* R_bar;    // [N][n][k]
+    double* q_bar;    // [N][k]   (w.r.t. sigma when sigma_inputs)
+    double* h_bar;    // [N][p]
+    double* d_bar;    // [N][p]
+    double* traj;     // workspace [n_cta][Tobs][n n + n]
+    double* c0bar_ws;  // workspace [n_cta][n n]
+};
+
+// doubles of shared memory needed by kalman_grad_draw
+GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
+    const int ld = ldim(n);
+    return (size_t)9 * n * ld + (size_t)5 * n * PMAXG + (size_t)p * n + 6 * (size_t)n + 4 * PMAXG * PMAXG + 12 * PMAXG + (size_t)n * (k > 0 ? k : 1) + k +
+           nt + 8;
+}
+
+// One draw.  sm: shared memory (kalman_grad_smem_doubles), cta: index of this CTA's workspace slot.
+GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, double* sm) {
+    const int n = g.n, k = g.k, p = g.p, Tobs = g.Tobs, ld = ldim(n);
+    const int tile = n * ld;
+    double* Tm = sm;
+    double* C0 = Tm + tile;
+    double* P = C0 + tile;
+    double* Pf = P + tile;
+    double* L = Pf + tile;
+    double* Pb = L + tile;   // adjoint of the predicted covariance
+    double* Pfb = Pb + tile;  // adjoint of the filtered covariance
+    double* W1 = Pfb + tile;
+    double* W2 = W1 + tile;
+    double* PZ = W2 + tile;       // [n][PMAXG]
+    double* K = PZ + n * PMAXG;   // [n][PMAXG]
+    double* Kb = K + n * PMAXG;   // [n][PMAXG]
+    double* PZb = Kb + n * PMAXG;  // [n][PMAXG]
+    double* PK = PZb + n * PMAXG;  // [n][PMAXG]
+    double* Zs = PK + n * PMAXG;  // [p][n]
+    double* a = Zs + p * n;
+    double* af = a + n;
+    double* ab = af + n;
+    double* afb = ab + n;
+    double* an = afb + n;
+    double* tmpn = an + n;
+    double* F = tmpn + n;             // [PMAXG][PMAXG]  F, then F^-1
+    double* Fb = F + PMAXG * PMAXG;   // adjoint of F
+    double* Gm = Fb + PMAXG * PMAXG;  // scratch
+    double* Gm2 = Gm + PMAXG * PMAXG;
+    double* v = Gm2 + PMAXG * PMAXG;
+    double* e = v + PMAXG;
+    double* vb = e + PMAXG;
+    double* w = vb + PMAXG;
+    double* ym = w + PMAXG;
+    double* hv = ym + PMAXG;
+    double* dv = hv + PMAXG;
+    double* hb = dv + PMAXG;
+    double* db = hb + PMAXG;
+    double* sc = db + PMAXG;  // [0] logdet, [1] ok flag, [2] ll, [3] all-missing flag
+    double* Rs = sc + 3 * PMAXG;  // [n][k]
+    double* qs = Rs + n * (k > 0 ? k : 1);
+    double* s_red = qs + k;
+
+    const double LOG2PI = 1.8378770664093453;
+    const double ll_const = (g.mvn_const_mode == 0) ? p * LOG2PI : LOG2PI;
+    const double jit = g.jitter;
+    int status = g.status_in ? (g.status_in[draw] & ~0x800) : 0;
+    double* gTb = g.T_bar + (size_t)draw * n * n;
+    double* gRb = g.R_bar + (size_t)draw * n * k;
+    if (status & g.gate_mask) {
+        GFOR(i, n * n) gTb[i] = 0.0;
+        GFOR(i, n * k) gRb[i] = 0.0;
+        GFOR(i, k) g.q_bar[(size_t)draw * k + i] = 0.0;
+        GFOR(i, p) {
+            if (g.h_bar) g.h_bar[(size_t)draw * p + i] = 0.0;
+            if (g.d_bar) g.d_bar[(size_t)draw * p + i] = 0.0;
+        }
+        if (G_TID == 0) {
+            g.ll[draw] = -INFINITY;
+            g.status[draw] = status | 0x400;
+        }
+        return;
+    }
+    double* traj = g.traj + (size_t)cta * Tobs * (size_t)(n * n + n);
+    double* gC0b = g.c0bar_ws + (size_t)cta * n * n;
+    const double* gT = g.T + (size_t)draw * n * n;
+    const double* gR = g.R + (size_t)draw * n * k;
+
+    // ---- load
+    GFOR(idx, n * n) {
+        const int i = idx / n, j = idx - i * n;
+        Tm[i * ld + j] = gT[idx];
+        gTb[idx] = 0.0;
+        gC0b[idx] = 0.0;
+    }
+    GFOR(idx, n * k) Rs[idx] = gR[idx];
+    GFOR(c, k) {
+        const double qv = g.qdiag[(size_t)draw * g.q_stride + c];
+        qs[c] = g.sigma_inputs ? qv * qv : qv;
+    }
+    GFOR(i, p) {
+        const double h = g.hdiag ? g.hdiag[(size_t)draw * g.h_stride + i] : 0.0;
+        hv[i] = g.sigma_inputs ? h * h : h;
+        dv[i] = g.d ? g.d[(size_t)draw * g.d_stride + i] : 0.0;
+        hb[i] = 0.0;
+        db[i] = 0.0;
+    }
+    GFOR(idx, p * n) {
+        const int i = idx / n, j = idx - i * n;
+        Zs[idx] = g.Z ? g.Z[idx] : ((g.obs_idx[i] == j) ? 1.0 : 0.0);
+    }
+    GFOR(i, n) {
+        a[i] = 0.0;
+        ab[i] = 0.0;
+    }
+    GSYNC();
+    // C0 = R Q R'
+    GFOR(idx, n * n) {
+        const int i = idx / n, j = idx - i * n;
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        double s = 0.0;
+        for (int c = 0; c < k; ++c) s = fma(Rs[lo * k + c] * qs[c], Rs[hi * k + c], s);
+        C0[i * ld + j] = s;
+        P[i * ld + j] = s;
+        L[i * ld + j] = Tm[i * ld + j];  // A_0 = T
+    }
+    GSYNC();
+    // ---- P0 by Smith doubling: P <- P + A P A', A <- A^2
+    {
+        const int cap = g.lyap_max_iter > 0 ? g.lyap_max_iter : 64;
+        bool done = false;
+        for (int it = 0; it < cap && !done; ++it) {
+            mm<false, false>(W1, ld, L, ld, P, ld, n, n, n, 1.0, 0.0);
+            GSYNC();
+            mm<false, true>(W2, ld, W1, ld, L, ld, n, n, n, 1.0, 0.0);
+            mm<false, false>(Pf, ld, L, ld, L, ld, n, n, n, 1.0, 0.0);
+            GSYNC();
+            GFOR(idx, n * n) {
+                const int i = idx / n, j = idx - i * n;
+                P[i * ld + j] += W2[i * ld + j];
+                L[i * ld + j] = Pf[i * ld + j];
+            }
+            GSYNC();
+            const double dmax = absmax(W2, ld, n, n, s_red), pmax = absmax(P, ld, n, n, s_red);
+            if (dmax != dmax || pmax != pmax) break;
+            if (dmax <= 1e-16 * pmax) done = true;
+        }
+        if (!done) status |= ST_LYAP;
+    }
+    if (G_TID == 0) {
+        sc[2] = 0.0;
+        sc[1] = 1.0;
+    }
+    GSYNC();
+
+    // One update step on the predicted (a, P): fills w, ym, v, PZ, F^-1 (in F), K, e, af, L, W1 = L P, Pf.
+    auto update = [&](int t, bool accumulate_ll) {
+        GFOR(i, p) {
+            const double yv = g.Y[(size_t)t * p + i];
+            const bool miss = (yv != yv) || (yv == g.missing_fill);
+            w[i] = miss ? 0.0 : 1.0;
+            ym[i] = miss ? 0.0 : yv;
+        }
+        GSYNC();
+        GFOR(idx, n * p) {
+            const int i = idx / p, c = idx - i * p;
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s = fma(P[i * ld + j], Zs[c * n + j], s);
+            PZ[i * PMAXG + c] = w[c] * s;
+        }
+        GFOR(c, p) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s = fma(Zs[c * n + j], a[j], s);
+            v[c] = ym[c] - (dv[c] + w[c] * s);
+        }
+        GSYNC();
+        GFOR(idx, p * p) {
+            const int c = idx / p, b = idx - c * p;
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s = fma(Zs[c * n + j], PZ[j * PMAXG + b], s);
+            s *= w[c];
+            if (c == b) s += w[c] * hv[c] + jit;
+            F[c * PMAXG + b] = s;
+        }
+        GSYNC();
+        if (G_TID == 0) {
+            // symmetrise (the two triangles differ by rounding), invert
+            for (int c = 0; c < p; ++c)
+                for (int b = 0; b < c; ++b) {
+                    const double s = 0.5 * (F[c * PMAXG + b] + F[b * PMAXG + c]);
+                    F[c * PMAXG + b] = F[b * PMAXG + c] = s;
+                }
+            double logdet;
+            const bool ok = spd_inverse_small(F, p, &logdet);
+            if (!ok) sc[1] = 0.0;
+            sc[0] = logdet;
+            double allmiss = 1.0;
+            for (int c = 0; c < p; ++c)
+                if (w[c] != 0.0) allmiss = 0.0;
+            sc[3] = allmiss;
+        }
+        GSYNC();
+        GFOR(idx, n * p) {
+            const int i = idx / p, c = idx - i * p;
+            double s = 0.0;
+            for (int b = 0; b < p; ++b) s = fma(PZ[i * PMAXG + b], F[b * PMAXG + c], s);
+            K[i * PMAXG + c] = s;
+        }
+        GFOR(c, p) {
+            double s = 0.0;
+            for (int b = 0; b < p; ++b) s = fma(F[c * PMAXG + b], v[b], s);
+            e[c] = s;
+        }
+        GSYNC();
+        GFOR(i, n) {
+            double s = a[i];
+            for (int c = 0; c < p; ++c) s = fma(K[i * PMAXG + c], v[c], s);
+            af[i] = s;
+        }
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            double s = (i == j) ? 1.0 : 0.0;
+            for (int c = 0; c < p; ++c) s = fma(-K[i * PMAXG + c] * w[c], Zs[c * n + j], s);
+            L[i * ld + j] = s;
+        }
+        if (accumulate_ll && G_TID == 0 && sc[3] == 0.0) {
+            double quad = 0.0;
+            for (int c = 0; c < p; ++c) quad = fma(v[c], e[c], quad);
+            sc[2] += -0.5 * (ll_const + sc[0] + quad);
+        }
+        GSYNC();
+        mm<false, false>(W1, ld, L, ld, P, ld, n, n, n, 1.0, 0.0);
+        GSYNC();
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            double s = (i == j) ? jit : 0.0;
+            for (int kk = 0; kk < n; ++kk) s = fma(W1[i * ld + kk], L[j * ld + kk], s);
+            for (int c = 0; c < p; ++c) s = fma(K[i * PMAXG + c] * (w[c] * hv[c]), K[j * PMAXG + c], s);
+            Pf[i * ld + j] = s;
+        }
+        GSYNC();
+    };
+
+    // ---- forward sweep: store the predicted moments, filter, predict
+    for (int t = 0; t < Tobs; ++t) {
+        double* tr = traj + (size_t)t * (n * n + n);
+        GFOR(idx, n * n) tr[idx] = P[(idx / n) * ld + (idx % n)];
+        GFOR(i, n) tr[n * n + i] = a[i];
+        update(t, true);
+        mm<false, false>(W2, ld, Tm, ld, Pf, ld, n, n, n, 1.0, 0.0);
+        GFOR(i, n) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s = fma(Tm[i * ld + j], af[j], s);
+            an[i] = s;
+        }
+        GSYNC();
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            double s = C0[i * ld + j];
+            for (int kk = 0; kk < n; ++kk) s = fma(W2[i * ld + kk], Tm[j * ld + kk], s);
+            P[i * ld + j] = s;
+        }
+        GFOR(i, n) a[i] = an[i];
+        GSYNC();
+    }
+    const double ll = sc[2];
+    if (sc[1] == 0.0) status |= ST_NOT_PD;
+    if (!(fabs(ll) <= 1.7e308)) status |= ST_LL_NONFINITE;
+
+    // ---- reverse sweep
+    GFOR(idx, n * ld) Pb[idx] = 0.0;
+    GSYNC();
+    for (int t = Tobs - 1; t >= 0; --t) {
+        const double* tr = traj + (size_t)t * (n * n + n);
+        GFOR(idx, n * n) P[(idx / n) * ld + (idx % n)] = tr[idx];
+        GFOR(i, n) a[i] = tr[n * n + i];
+        GSYNC();
+        update(t, false);
+        // predict:  P' = T Pf T' + C0,  a' = T af
+        mm<false, false>(W2, ld, Tm, ld, Pf, ld, n, n, n, 1.0, 0.0);
+        GSYNC();
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            double s = ab[i] * af[j];
+            for (int kk = 0; kk < n; ++kk) s = fma(Pb[i * ld + kk] + Pb[kk * ld + i], W2[kk * ld + j], s);
+            gTb[idx] += s;
+            gC0b[idx] += Pb[i * ld + j];
+        }
+        GSYNC();
+        mm<false, false>(W2, ld, Pb, ld, Tm, ld, n, n, n, 1.0, 0.0);
+        GFOR(i, n) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s = fma(Tm[j * ld + i], ab[j], s);
+            afb[i] = s;
+        }
+        GSYNC();
+        mm<true, false>(Pfb, ld, Tm, ld, W2, ld, n, n, n, 1.0, 0.0);
+        // log-likelihood term
+        GFOR(idx, p * p) {
+            const int c = idx / p, b = idx - c * p;
+            Fb[c * PMAXG + b] = (sc[3] == 0.0) ? -0.5 * (F[c * PMAXG + b] - e[c] * e[b]) : 0.0;
+        }
+        GFOR(c, p) vb[c] = (sc[3] == 0.0) ? -e[c] : 0.0;
+        GSYNC();
+        // update:  Pf = L P L' + K Hm K' + j I,  L = I - K Zm,  af = a + K v   (W1 = L P, P symmetric)
+        GFOR(idx, n * n) {  // L_bar -> W2
+            const int i = idx / n, j = idx - i * n;
+            double s = 0.0;
+            for (int kk = 0; kk < n; ++kk) s = fma(Pfb[i * ld + kk] + Pfb[kk * ld + i], W1[kk * ld + j], s);
+            W2[i * ld + j] = s;
+        }
+        mm<false, false>(Pf, ld, Pfb, ld, L, ld, n, n, n, 1.0, 0.0);  // Pf tile now holds Pfb L
+        GFOR(idx, n * p) {                                            // PK = Pfb K
+            const int i = idx / p, c = idx - i * p;
+            double s = 0.0;
+            for (int kk = 0; kk < n; ++kk) s = fma(Pfb[i * ld + kk], K[kk * PMAXG + c], s);
+            PK[i * PMAXG + c] = s;
+        }
+        GSYNC();
+        GFOR(idx, n * p) {  // K_bar
+            const int i = idx / p, c = idx - i * p;
+            double s = afb[i] * v[c];
+            double s1 = 0.0, s2 = 0.0;
+            for (int kk = 0; kk < n; ++kk) {
+                s1 = fma(Pfb[i * ld + kk] + Pfb[kk * ld + i], K[kk * PMAXG + c], s1);
+                s2 = fma(W2[i * ld + kk], Zs[c * n + kk], s2);
+            }
+            Kb[i * PMAXG + c] = s + s1 * (w[c] * hv[c]) - s2 * w[c];
+        }
+        GFOR(c, p) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s = fma(K[i * PMAXG + c], PK[i * PMAXG + c], s);
+            hb[c] += w[c] * s;
+            double u = vb[c];
+            for (int i = 0; i < n; ++i) u = fma(K[i * PMAXG + c], afb[i], u);
+            vb[c] = u;
+        }
+        GSYNC();
+        GFOR(idx, n * p) {  // PZ_bar = K_bar F^-1
+            const int i = idx / p, c = idx - i * p;
+            double s = 0.0;
+            for (int b = 0; b < p; ++b) s = fma(Kb[i * PMAXG + b], F[b * PMAXG + c], s);
+            PZb[i * PMAXG + c] = s;
+        }
+        GSYNC();
+        GFOR(idx, p * p) {  // F_bar -= K' PZ_bar
+            const int c = idx / p, b = idx - c * p;
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s = fma(K[i * PMAXG + c], PZb[i * PMAXG + b], s);
+            Fb[c * PMAXG + b] -= s;
+        }
+        GSYNC();
+        GFOR(idx, n * p) {  // PZ_bar += Zm' F_bar
+            const int i = idx / p, b = idx - i * p;
+            double s = PZb[i * PMAXG + b];
+            for (int c = 0; c < p; ++c) s = fma(w[c] * Zs[c * n + i], Fb[c * PMAXG + b], s);
+            PZb[i * PMAXG + b] = s;
+        }
+        GFOR(c, p) {
+            hb[c] += w[c] * Fb[c * PMAXG + c];
+            db[c] -= vb[c];
+        }
+        GSYNC();
+        GFOR(idx, n * n) {  // P_bar = L' (Pfb L) + PZ_bar Zm
+            const int i = idx / n, j = idx - i * n;
+            double s = 0.0;
+            for (int kk = 0; kk < n; ++kk) s = fma(L[kk * ld + i], Pf[kk * ld + j], s);
+            for (int c = 0; c < p; ++c) s = fma(PZb[i * PMAXG + c] * w[c], Zs[c * n + j], s);
+            Pb[i * ld + j] = s;
+        }
+        GFOR(j, n) {
+            double s = afb[j];
+            for (int c = 0; c < p; ++c) s = fma(-w[c] * Zs[c * n + j], vb[c], s);
+            ab[j] = s;
+        }
+        GSYNC();
+    }
+    // ---- P0 = dlyap(T, C0): S = T' S T + P0_bar by doubling (S in Pb, A in L);  P still holds P0
+    GFOR(idx, n * ld) L[idx] = Tm[idx];
+    GSYNC();
+    {
+        const int cap = g.lyap_max_iter > 0 ? g.lyap_max_iter : 64;
+        for (int it = 0; it < cap; ++it) {
+            mm<false, false>(W1, ld, Pb, ld, L, ld, n, n, n, 1.0, 0.0);
+            GSYNC();
+            mm<true, false>(W2, ld, L, ld, W1, ld, n, n, n, 1.0, 0.0);
+            mm<false, false>(Pf, ld, L, ld, L, ld, n, n, n, 1.0, 0.0);
+            GSYNC();
+            GFOR(idx, n * n) {
+                const int i = idx / n, j = idx - i * n;
+                Pb[i * ld + j] += W2[i * ld + j];
+                L[i * ld + j] = Pf[i * ld + j];
+            }
+            GSYNC();
+            const double dmax = absmax(W2, ld, n, n, s_red), smax = absmax(Pb, ld, n, n, s_red);
+            if (!(dmax > 1e-17 * smax)) break;
+        }
+    }
+    // C0_bar += S;  T_bar += (S + S') T P0
+    mm<false, false>(W1, ld, Tm, ld, P, ld, n, n, n, 1.0, 0.0);
+    GFOR(idx, n * n) gC0b[idx] += Pb[(idx / n) * ld + (idx % n)];
+    GSYNC();
+    GFOR(idx, n * n) {
+        const int i = idx / n, j = idx - i * n;
+        double s = 0.0;
+        for (int kk = 0; kk < n; ++kk) s = fma(Pb[i * ld + kk] + Pb[kk * ld + i], W1[kk * ld + j], s);
+        gTb[idx] += s;
+        W2[i * ld + j] = gC0b[idx] + gC0b[j * n + i];  // C0_bar + C0_bar'
+    }
+    GSYNC();
+    // R_bar = (C0_bar + C0_bar') R Q;  q_bar_c = sum_ij R_ic C0_bar_ij R_jc = (1/2) sum_i R_ic ((C0_bar + C0_bar') R)_ic
+    GFOR(idx, n * k) {
+        const int i = idx / k, c = idx - i * k;
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = fma(W2[i * ld + j], Rs[j * k + c], s);
+        W1[i * ld + c] = s;
+        gRb[idx] = s * qs[c];
+    }
+    GSYNC();
+    GFOR(c, k) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s = fma(Rs[i * k + c], W1[i * ld + c], s);
+        s *= 0.5;
+        if (g.sigma_inputs) s *= 2.0 * g.qdiag[(size_t)draw * g.q_stride + c];
+        g.q_bar[(size_t)draw * k + c] = s;
+    }
+    GFOR(c, p) {
+        if (g.h_bar) {
+            double s = hb[c];
+            if (g.sigma_inputs) s *= 2.0 * (g.hdiag ? g.hdiag[(size_t)draw * g.h_stride + c] : 0.0);
+            g.h_bar[(size_t)draw * p + c] = s;
+        }
+        if (g.d_bar) g.d_bar[(size_t)draw * p + c] = db[c];
+    }
+    if (G_TID == 0) {
+        g.ll[draw] = ll;
+        g.status[draw] = status;
+    }
+    GSYNC();
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+struct PolicyAdjointArgs {
+    const double* A;  // [N][n][n]  (unused by the arithmetic: A_bar = S does not depend on A; kept for the reference's signature)
+    const double* B;
+    const double* C;
+    const double* D;      // [N][n][k] or NULL
+    const double* T;      // [N][n][n]
+    const double* R;      // [N][n][k] or NULL
+    const double* T_bar;  // [N][n][n]
+    const double* R_bar;  // [N][n][k] or NULL
+    long long N;
+    int n, k, max_iter;
+    double* A_bar;    // [N][n][n]
+    double* B_bar;    // [N][n][n]
+    double* C_bar;    // [N][n][n]
+    double* D_bar;    // [N][n][k] or NULL
+    int32_t* status;  // [N] or NULL: GECON_ST_SINGULAR when C T + B is singular (outputs NaN)
+};
+
+GHH size_t policy_adjoint_smem_doubles(int n, int nt) { return (size_t)6 * n * ldim(n) + nt + 8; }
+
+GHD void policy_adjoint_draw(const PolicyAdjointArgs& g, long long draw, double* sm, int* s_int) {
+    const int n = g.n, k = (g.R_bar && g.D && g.R) ? g.k : 0, ld = ldim(n);
+    const int tile = n * ld;
+    double* X0 = sm;  // W -> W^-1
+    double* X1 = X0 + tile;
+    double* X2 = X1 + tile;
+    double* X3 = X2 + tile;
+    double* X4 = X3 + tile;  // S
+    double* X5 = X4 + tile;  // G
+    double* s_red = X5 + tile;
+    const size_t o = (size_t)draw * n * n;
+    const double *gB = g.B + o, *gC = g.C + o, *gT = g.T + o, *gTb = g.T_bar + o;
+    double *oA = g.A_bar + o, *oB = g.B_bar + o, *oC = g.C_bar + o;
+    // W = C T + B  (X1), identity (X0)
+    GFOR(idx, n * n) {
+        const int i = idx / n, j = idx - i * n;
+        double s = gB[idx];
+        for (int kk = 0; kk < n; ++kk) s = fma(gC[i * n + kk], gT[kk * n + j], s);
+        X1[i * ld + j] = s;
+        X0[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    }
+    GSYNC();
+    // Gauss-Jordan with partial pivoting on [X1 | X0] -> X0 = W^-1
+    bool singular = false;
+    for (int c = 0; c < n; ++c) {
+        if (G_TID == 0) {
+            int piv = c;
+            double best = fabs(X1[c * ld + c]);
+            for (int i = c + 1; i < n; ++i) {
+                const double x = fabs(X1[i * ld + c]);
+                if (x > best) {
+                    best = x;
+                    piv = i;
+                }
+            }
+            s_int[0] = piv;
+            s_int[1] = (best > 0.0 && best <= 1.7e308) ? 1 : 0;
+        }
+        GSYNC();
+        const int piv = s_int[0];
+        if (!s_int[1]) {
+            singular = true;
+            break;
+        }
+        if (piv != c) {
+            GFOR(j, n) {
+                double t = X1[c * ld + j];
+                X1[c * ld + j] = X1[piv * ld + j];
+                X1[piv * ld + j] = t;
+                t = X0[c * ld + j];
+                X0[c * ld + j] = X0[piv * ld + j];
+                X0[piv * ld + j] = t;
+            }
+            GSYNC();
+        }
+        const double inv = 1.0 / X1[c * ld + c];
+        GSYNC();
+        GFOR(j, n) {
+            X1[c * ld + j] *= inv;
+            X0[c * ld + j] *= inv;
+        }
+        GSYNC();
+        GFOR(i, n) X2[i * ld] = (i == c) ? 0.0 : X1[i * ld + c];  // multipliers out of the way of the row updates below
+        GSYNC();
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            const double f = X2[i * ld];
+            X1[i * ld + j] = fma(-f, X1[c * ld + j], X1[i * ld + j]);
+            X0[i * ld + j] = fma(-f, X0[c * ld + j], X0[i * ld + j]);
+        }
+        GSYNC();
+    }
+    if (singular) {
+        const double nanv = NAN;
+        GFOR(idx, n * n) oA[idx] = oB[idx] = oC[idx] = nanv;
+        if (g.D_bar) GFOR(idx, n * g.k) g.D_bar[(size_t)draw * n * g.k + idx] = nanv;
+        if (G_TID == 0 && g.status) g.status[draw] = ST_SINGULAR;
+        GSYNC();
+        return;
+    }
+    // selection matrix in reverse: D_bar = -W^-T R_bar, W_bar = D_bar R', B_bar = W_bar, C_bar = W_bar T', T_bar += C' W_bar
+    if (k > 0) {
+        const double* gRb = g.R_bar + (size_t)draw * n * k;
+        const double* gR = g.R + (size_t)draw * n * k;
+        GFOR(idx, n * k) {
+            const int i = idx / k, c = idx - i * k;
+            double s = 0.0;
+            for (int kk = 0; kk < n; ++kk) s = fma(X0[kk * ld + i], gRb[kk * k + c], s);
+            X1[i * ld + c] = -s;
+            if (g.D_bar) g.D_bar[(size_t)draw * n * k + idx] = -s;
+        }
+        GSYNC();
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            double s = 0.0;
+            for (int c = 0; c < k; ++c) s = fma(X1[i * ld + c], gR[j * k + c], s);
+            X2[i * ld + j] = s;  // W_bar
+        }
+        GSYNC();
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            double s = 0.0, u = gTb[idx];
+            for (int kk = 0; kk < n; ++kk) {
+                s = fma(X2[i * ld + kk], gT[j * n + kk], s);   // W_bar T'
+                u = fma(gC[kk * n + i], X2[kk * ld + j], u);  // T_bar + C' W_bar
+            }
+            oB[idx] = X2[i * ld + j];
+            oC[idx] = s;
+            X3[i * ld + j] = u;
+        }
+    } else {
+        if (g.D_bar) GFOR(idx, n * g.k) g.D_bar[(size_t)draw * n * g.k + idx] = 0.0;
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            oB[idx] = 0.0;
+            oC[idx] = 0.0;
+            X3[i * ld + j] = gTb[idx];
+        }
+    }
+    GSYNC();
+    // S = Q = -W^-T T_bar_total (X4),  G = -W^-T C' (X5),  T_k = T' (X1)
+    GFOR(idx, n * n) {
+        const int i = idx / n, j = idx - i * n;
+        double s = 0.0, u = 0.0;
+        for (int kk = 0; kk < n; ++kk) {
+            s = fma(X0[kk * ld + i], X3[kk * ld + j], s);
+            u = fma(X0[kk * ld + i], gC[j * n + kk], u);
+        }
+        X4[i * ld + j] = -s;
+        X5[i * ld + j] = -u;
+        X1[i * ld + j] = gT[j * n + i];
+    }
+    GSYNC();
+    const int cap = g.max_iter > 0 ? g.max_iter : 64;
+    for (int it = 0; it < cap; ++it) {
+        mm<false, false>(X2, ld, X5, ld, X4, ld, n, n, n, 1.0, 0.0);  // G S
+        GSYNC();
+        mm<false, false>(X3, ld, X2, ld, X1, ld, n, n, n, 1.0, 0.0);  // (G S) T_k
+        mm<false, false>(X0, ld, X5, ld, X5, ld, n, n, n, 1.0, 0.0);  // G^2
+        GSYNC();
+        mm<false, false>(X2, ld, X1, ld, X1, ld, n, n, n, 1.0, 0.0);  // T_k^2
+        GFOR(idx, n * n) {
+            const int i = idx / n, j = idx - i * n;
+            X4[i * ld + j] += X3[i * ld + j];
+            X5[i * ld + j] = X0[i * ld + j];
+        }
+        GSYNC();
+        GFOR(idx, n * n) X1[(idx / n) * ld + (idx % n)] = X2[(idx / n) * ld + (idx % n)];
+        const double dmax = absmax(X3, ld, n, n, s_red), smax = absmax(X4, ld, n, n, s_red);
+        if (!(dmax > 1e-17 * smax)) break;
+    }
+    GSYNC();
+    // A_bar = S, B_bar += S T', C_bar += S T' T'
+    GFOR(idx, n * n) {
+        const int i = idx / n, j = idx - i * n;
+        double s = 0.0;
+        for (int kk = 0; kk < n; ++kk) s = fma(X4[i * ld + kk], gT[j * n + kk], s);
+        X2[i * ld + j] = s;
+        oA[idx] = X4[i * ld + j];
+        oB[idx] += s;
+    }
+    GSYNC();
+    GFOR(idx, n * n) {
+        const int i = idx / n, j = idx - i * n;
+        double s = 0.0;
+        for (int kk = 0; kk < n; ++kk) s = fma(X2[i * ld + kk], gT[j * n + kk], s);
+        oC[idx] += s;
+    }
+    if (G_TID == 0 && g.status) g.status[draw] = 0;
+    GSYNC();
+}
+
+}  // namespace gecon_grad

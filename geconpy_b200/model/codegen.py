@@ -169,6 +169,86 @@ class LinearizedModel:
             "ops": int(sum(sp.count_ops(r) for _, r in subs) + sum(sp.count_ops(r) for r in red)),
         }
 
+    # ------------------------------------------------------------------------------------------------ reverse mode
+    def vjp_body(self) -> str:
+        """Device code of the vector-Jacobian product  theta_bar = sum_M <M_bar, dM/dtheta> (+ <xss_bar, dxss/dtheta>):
+        source-to-source reverse mode over the SAME straight-line program the forward kernel evaluates (deterministic
+        parameters -> steady state -> scales -> shared-CSE temporaries -> entries).  Every statement ``s = f(operands)``
+        contributes ``b_operand += b_s * df/doperand`` in reverse order; the partial derivatives are taken symbolically
+        per statement (the statements are CSE-sized, so they stay small).  The last stage of the gradient path
+        (SURVEY 8f rank 3): what pytensor's autodiff does to the compiled [A, B, C, D] graph in the reference."""
+        n, k = self.n, self.k
+        cc = lambda e: sp.ccode(e, strict=True)  # noqa: E731
+        fwd, stmts = [], []  # forward text; (symbol name, expr) in evaluation order
+        for i, p in enumerate(self.param_names):
+            fwd.append(f"    const double {self.p_sym[p].name} = th[{i}];")
+        for d, e in zip(self.det_names, self.det_exprs):
+            stmts.append((self.p_sym[d], e))
+        ss_subs, ss_red = sp.cse(self.ss_exprs, symbols=sp.numbered_symbols("s_tmp_"), optimizations="basic")
+        stmts += list(ss_subs)
+        stmts += [(self.ss_sym[v], e) for v, e in zip(self.var_names, ss_red)]
+        for sym, e in stmts:
+            fwd.append(f"    const double {sym.name} = {cc(e)};")
+        for j, (v, kind) in enumerate(zip(self.vars_perm, self.scale_kind)):
+            ss = self.ss_sym[v].name
+            rhs = {"one": "1.0", "ss": ss, "switch": f"(({ss} > 0.0) ? {ss} : 1.0)"}[kind]
+            fwd.append(f"    const double sc{j} = {rhs};")
+        sym_entries, where, const_entries = [], [], []
+        for m in "ABCD":
+            for i, row in enumerate(self.entries[m]):
+                for j, e in enumerate(row):
+                    if e.is_number:
+                        if e != 0:
+                            const_entries.append((m, i, j, float(e)))
+                    else:
+                        sym_entries.append(e)
+                        where.append((m, i, j))
+        subs, red = sp.cse(sym_entries, symbols=sp.numbered_symbols("j_tmp_"), optimizations="basic") if sym_entries else ([], [])
+        for sym, e in subs:
+            fwd.append(f"    const double {sym.name} = {cc(e)};")
+        stmts_all = stmts + list(subs)
+        rev = []
+        names = [self.p_sym[p].name for p in self.param_names] + [sym.name for sym, _ in stmts_all]
+        for nm in names:
+            rev.append(f"    double b_{nm} = 0.0;")
+        for j, kind in enumerate(self.scale_kind):
+            if kind != "one":
+                rev.append(f"    double b_sc{j} = 0.0;")
+        rev.append("    double g;")
+        width = {"A": n, "B": n, "C": n, "D": k}
+
+        def push(target_expr, seed):
+            """b_s += seed * d target / d s for every operand s"""
+            for sv in sorted(target_expr.free_symbols, key=lambda x: x.name):
+                dv = sp.diff(target_expr, sv)
+                if dv != 0:
+                    rev.append(f"    b_{sv.name} += {seed} * ({cc(dv)});")
+
+        for (m, i, j), e in zip(where, red):
+            scaled = m != "D" and self.scale_kind[j] != "one"
+            rev.append(f"    g = {m}b[{i * width[m] + j}];")
+            push(e, f"g * sc{j}" if scaled else "g")
+            if scaled:
+                rev.append(f"    b_sc{j} += g * ({cc(e)});")
+        for m, i, j, val in const_entries:
+            if m != "D" and self.scale_kind[j] != "one":
+                rev.append(f"    b_sc{j} += {m}b[{i * width[m] + j}] * {val!r};")
+        rev.append("    if (xssb) {")
+        for i, v in enumerate(self.var_names):
+            rev.append(f"        b_{self.ss_sym[v].name} += xssb[{i}];")
+        rev.append("    }")
+        for j, (v, kind) in enumerate(zip(self.vars_perm, self.scale_kind)):
+            ss = self.ss_sym[v].name
+            if kind == "ss":
+                rev.append(f"    b_{ss} += b_sc{j};")
+            elif kind == "switch":
+                rev.append(f"    b_{ss} += ({ss} > 0.0) ? b_sc{j} : 0.0;")
+        for sym, e in reversed(stmts_all):
+            push(e, f"b_{sym.name}")
+        for i, p in enumerate(self.param_names):
+            rev.append(f"    thb[{i}] = b_{self.p_sym[p].name};")
+        return "\n".join(fwd + rev)
+
     # ------------------------------------------------------------------------------------------------ code
     def cuda_source(self) -> str:
         """One translation unit: the per-draw device function, the batched kernel and the C-ABI launchers."""
@@ -230,7 +310,7 @@ class LinearizedModel:
                 emit(f"    {m}[{i * width[m] + j}] = {val!r};")
         body = "\n".join(lines)
         ident = re.sub(r"[^0-9A-Za-z_]", "_", self.name)
-        return _TEMPLATE.format(name=ident, n=n, k=k, n_theta=self.n_theta, body=body)
+        return _TEMPLATE.format(name=ident, n=n, k=k, n_theta=self.n_theta, body=body, vjp_body=self.vjp_body())
 
 
 _TEMPLATE = r"""// GENERATED by geconpy_b200/model/codegen.py for model "{name}" -- do not edit.
@@ -260,7 +340,25 @@ __device__ __forceinline__ bool gecon_model_eval(const double* __restrict__ th, 
     return fin;
 }}
 
+// theta_bar = sum over the entries of <M_bar, dM/dtheta> (+ <xss_bar, dx_ss/dtheta>): reverse mode over the same program
+__device__ __forceinline__ void gecon_model_vjp(const double* __restrict__ th, const double* __restrict__ Ab,
+                                                const double* __restrict__ Bb, const double* __restrict__ Cb,
+                                                const double* __restrict__ Db, const double* __restrict__ xssb,
+                                                double* __restrict__ thb) {{
+{vjp_body}
+}}
+
 #ifdef GECON_HOST_CHECK
+extern "C" int gecon_model_vjp_host_check(const double* theta, int64_t N, const double* Ab, const double* Bb, const double* Cb,
+                                          const double* Db, const double* xssb, double* theta_bar) {{
+    const size_t nn = (size_t)GECON_MODEL_N * GECON_MODEL_N;
+    for (int64_t i = 0; i < N; ++i)
+        gecon_model_vjp(theta + (size_t)i * GECON_MODEL_NTHETA, Ab + i * nn, Bb + i * nn, Cb + i * nn,
+                        Db + (size_t)i * GECON_MODEL_N * GECON_MODEL_K, xssb ? xssb + (size_t)i * GECON_MODEL_N : nullptr,
+                        theta_bar + (size_t)i * GECON_MODEL_NTHETA);
+    return 0;
+}}
+
 extern "C" int gecon_model_eval_host_check(const double* theta, int64_t N, double* A, double* B, double* C, double* D, double* xss,
                                            int32_t* status) {{
     const size_t nn = (size_t)GECON_MODEL_N * GECON_MODEL_N;
@@ -282,6 +380,31 @@ __global__ void __launch_bounds__(128) gecon_model_jacobian_kernel(const double*
                                           D + (size_t)i * GECON_MODEL_N * GECON_MODEL_K, xss ? xss + (size_t)i * GECON_MODEL_N : nullptr);
         if (status) status[i] = fin ? 0 : GECON_ST_JAC_NONFINITE;
     }}
+}}
+
+__global__ void __launch_bounds__(128) gecon_model_vjp_kernel(const double* __restrict__ theta, long long N, const double* __restrict__ Ab,
+                                                              const double* __restrict__ Bb, const double* __restrict__ Cb,
+                                                              const double* __restrict__ Db, const double* __restrict__ xssb,
+                                                              double* __restrict__ theta_bar) {{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {{
+        const size_t nn = (size_t)GECON_MODEL_N * GECON_MODEL_N;
+        gecon_model_vjp(theta + (size_t)i * GECON_MODEL_NTHETA, Ab + i * nn, Bb + i * nn, Cb + i * nn,
+                        Db + (size_t)i * GECON_MODEL_N * GECON_MODEL_K, xssb ? xssb + (size_t)i * GECON_MODEL_N : nullptr,
+                        theta_bar + (size_t)i * GECON_MODEL_NTHETA);
+    }}
+}}
+
+// DEVICE pointers: theta_bar[N][n_theta] = vector-Jacobian product of (A_bar, B_bar, C_bar, D_bar, xss_bar or NULL)
+extern "C" int gecon_model_vjp_batched(const double* theta, int64_t N, const double* Ab, const double* Bb, const double* Cb,
+                                       const double* Db, const double* xssb, double* theta_bar, void* stream) {{
+    if (N <= 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (N + 127) / 128;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    gecon_model_vjp_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(theta, N, Ab, Bb, Cb, Db, xssb, theta_bar);
+    return (int)cudaGetLastError();
 }}
 
 extern "C" int gecon_model_info(int32_t* n, int32_t* k, int32_t* n_theta) {{

@@ -47,6 +47,9 @@ class CompiledModel:
         self._jac_host = self._lib.gecon_model_jacobian_host
         self._jac_host.restype = C.c_int
         self._jac_host.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        self._vjp_dev = self._lib.gecon_model_vjp_batched
+        self._vjp_dev.restype = C.c_int
+        self._vjp_dev.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         n, k, nt = C.c_int32(), C.c_int32(), C.c_int32()
         self.launches = 0  # kernel launches made through this model library (bench.py's gpu_launches)
         self._lib.gecon_model_info(C.byref(n), C.byref(k), C.byref(nt))
@@ -80,6 +83,17 @@ class CompiledModel:
         if rc != 0:
             raise L.GeconLibraryError(f"gecon_model_jacobian_batched({self.name}) failed with CUDA error {rc}")
 
+    def vjp_device(self, theta, A_bar, B_bar, C_bar, D_bar, xss_bar, theta_bar, stream) -> None:
+        """theta_bar[N, n_theta] = <(A_bar, B_bar, C_bar, D_bar[, xss_bar]), d(A, B, C, D[, x_ss])/dtheta> on device pointers: the
+        generated reverse-mode kernel (codegen.vjp_body), last stage of the gradient path."""
+        rc = self._vjp_dev(
+            theta.data_ptr(), theta.shape[0], A_bar.data_ptr(), B_bar.data_ptr(), C_bar.data_ptr(), D_bar.data_ptr(),
+            xss_bar.data_ptr() if xss_bar is not None else None, theta_bar.data_ptr(), C.c_void_p(stream),
+        )  # fmt: skip
+        self.launches += 1
+        if rc != 0:
+            raise L.GeconLibraryError(f"gecon_model_vjp_batched({self.name}) failed with CUDA error {rc}")
+
     def jacobian(self, theta):
         """theta[N, n_theta] (numpy, host path) -> A, B, C, D, xss, status in the reference's permuted solver order
         (rows eq_order, columns var_order; gEconpy/model/perturbation.py:130-158)."""
@@ -112,6 +126,7 @@ class BatchedStateSpace:
     def __init__(self, model: CompiledModel):
         self.model = model
         self.configured = False
+        self._grad_ws = None
 
     def configure(
         self,
@@ -195,6 +210,7 @@ class BatchedStateSpace:
         self.n_param = len(self.param_names)
         self.configured = True
         self._ws = None
+        self._grad_ws = None
         return self
 
     # ------------------------------------------------------------------------------------------------ workspace
@@ -317,6 +333,149 @@ class BatchedStateSpace:
             if out_n_iter is not None:
                 out_n_iter[lo : lo + cnt].copy_(ws["n_iter"][:cnt])
         return ll, status
+
+    # ------------------------------------------------------------------------------------------------ gradient
+    def loglik_and_grad_device(self, theta_full, Y, events=None):
+        """theta_full [N, n_param] (CUDA) -> (ll [N], grad [N, n_param], status [N]): the log-likelihood and its gradient
+        with respect to every entry of the parameter vector (free parameters, sigma_<shock>, error_sigma_<state>) --
+        what ``pm.Model.dlogp`` delivers to NUTS in the reference, as seven launches per chunk:
+        Jacobian -> cycle reduction (full T, R) -> BK count -> Kalman forward + reverse sweep -> policy / selection
+        adjoint -> generated vector-Jacobian product.  Gated draws (ll = -inf) get a zero gradient."""
+        if not self.configured:
+            raise RuntimeError("call configure(...) first")
+        if not (torch is not None and isinstance(theta_full, torch.Tensor) and theta_full.is_cuda):
+            raise TypeError("loglik_and_grad_device needs CUDA tensors; use loglik_and_grad() for host arrays")
+        m = self.model
+        lib = L.load_library()
+        dev = theta_full.device
+        N = theta_full.shape[0]
+        if theta_full.shape[1] != self.n_param:
+            raise ValueError(f"theta has {theta_full.shape[1]} columns, expected {self.n_param}: {self.param_names}")
+        Y = Y.to(torch.float64).contiguous().reshape(-1, self.p)
+        Tobs = Y.shape[0]
+        f64 = dict(dtype=torch.float64, device=dev)
+        ll = torch.empty((N,), **f64)
+        status = torch.empty((N,), dtype=torch.int32, device=dev)
+        grad = torch.zeros((N, self.n_param), **f64)
+        nc = min(self.chunk, N, 16384)  # the gradient path keeps full-size adjoints per draw: smaller chunks
+        ws = self._workspace(dev, nc)
+        g = self._grad_ws
+        if g is None or g["nc"] < nc or g["device"] != dev:
+            na, n, k, p = self.n_aug, m.n, m.k, self.p
+            g = self._grad_ws = dict(
+                nc=nc, device=dev, Tfull=torch.empty((nc, n, n), **f64), Rfull=torch.empty((nc, n, k), **f64),
+                Tb_f=torch.empty((nc, na, na), **f64), Rb_f=torch.empty((nc, na, k), **f64), qb=torch.empty((nc, k), **f64),
+                hb=torch.empty((nc, p), **f64), db=torch.empty((nc, p), **f64), Tb=torch.zeros((nc, n, n), **f64),
+                Rb=torch.zeros((nc, n, k), **f64), Ab=torch.empty((nc, n, n), **f64), Bb=torch.empty((nc, n, n), **f64),
+                Cb=torch.empty((nc, n, n), **f64), Db=torch.empty((nc, n, k), **f64), thb=torch.empty((nc, m.n_theta), **f64),
+                xssb=torch.zeros((nc, n), **f64), U=torch.as_tensor(self.filter_vars.astype(np.int64), device=dev),
+                ll=torch.empty((nc,), **f64), st2=torch.empty((nc,), dtype=torch.int32, device=dev),
+            )  # fmt: skip
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        n_err, nf, U = len(self.measurement_error), self.n_filter, g["U"]
+
+        def mark(name):
+            if events is None:
+                return None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            events.append((name, e0, e1))
+            return e1
+
+        for lo in range(0, N, nc):
+            cnt = min(nc, N - lo)
+            th = theta_full[lo : lo + cnt]
+            ws["theta"][:cnt].copy_(th[:, : m.n_theta])
+            ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
+            if n_err:
+                ws["herr"][:cnt, self.err_pos] = th[:, m.n_theta + m.k :]
+            st = ws["status"][:cnt]
+            e = mark("jacobian")
+            m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
+            e and e.record()
+            if self.ss_obs_intercept:
+                xs = ws["xss"][:cnt].index_select(1, ws["d_var"])
+                ws["d"][:cnt].index_copy_(1, ws["d_pos"], torch.where(ws["d_loglin"], xs.log(), xs) * ws["d_scale"])
+            cr = L.CrArgs(
+                struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
+                D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
+                resid_tol=self.solver_tol, unperm=None, T=g["Tfull"].data_ptr(), R=g["Rfull"].data_ptr(),
+                status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
+                n_out=0, n_lead=(int(ws["lead"].numel()) if self.check_bk else 0),
+                lead_idx=(ws["lead"].data_ptr() if self.check_bk else None), n_unstable=ws["n_unstable"].data_ptr(),
+            )  # fmt: skip
+            e = mark("cr_solve")
+            L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
+            e and e.record()
+            if self.check_bk:
+                bk = L.BkArgs(
+                    struct_size=C.sizeof(L.BkArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(), N=cnt,
+                    n=m.n, n_lead=int(ws["lead"].numel()), lead_idx=ws["lead"].data_ptr(), accumulate=1, max_iter=0,
+                    n_unstable=ws["n_unstable"].data_ptr(), status=st.data_ptr(),
+                    skip_mask=L.ST_BK_CERTIFIED | L.ST_JAC_NONFINITE,
+                )  # fmt: skip
+                L.check(lib.gecon_bk_count_batched(C.byref(bk), C.c_void_p(stream)), "gecon_bk_count_batched")
+            # the filter's (exactly reduced, possibly augmented) transition and selection blocks
+            ws["T"][:cnt, :nf, :nf] = g["Tfull"][:cnt].index_select(1, U).index_select(2, U)
+            ws["R"][:cnt, :nf] = g["Rfull"][:cnt].index_select(1, U)
+            kg = L.KalmanGradArgs(
+                struct_size=C.sizeof(L.KalmanGradArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), qdiag=ws["sig"].data_ptr(),
+                q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
+                Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None),
+                obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
+                d=(ws["d"].data_ptr() if self.ss_obs_intercept else None), d_stride=(self.p if self.ss_obs_intercept else 0),
+                Y=Y.data_ptr(), N=cnt, n=self.n_aug, k=m.k, p=self.p, Tobs=Tobs, jitter=self.cov_jitter,
+                missing_fill=self.missing_fill_value, mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0,
+                status_in=st.data_ptr(), gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(),
+                status=status[lo : lo + cnt].data_ptr(), T_bar=g["Tb_f"].data_ptr(), R_bar=g["Rb_f"].data_ptr(),
+                q_bar=g["qb"].data_ptr(), h_bar=g["hb"].data_ptr(), d_bar=g["db"].data_ptr(),
+            )  # fmt: skip
+            e = mark("kalman_grad")
+            L.check(lib.gecon_kalman_grad_batched(C.byref(kg), C.c_void_p(stream)), "gecon_kalman_grad_batched")
+            e and e.record()
+            # scatter the filter-block adjoints back into solver order (the augmentation rows are constants)
+            Tb, Rb = g["Tb"][:cnt], g["Rb"][:cnt]
+            Tb.zero_()
+            Rb.zero_()
+            Tb[:, U[:, None], U[None, :]] = g["Tb_f"][:cnt, :nf, :nf]
+            Rb[:, U] = g["Rb_f"][:cnt, :nf]
+            pa = L.PolicyAdjointArgs(
+                struct_size=C.sizeof(L.PolicyAdjointArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
+                D=ws["D"].data_ptr(), T=g["Tfull"].data_ptr(), R=g["Rfull"].data_ptr(), T_bar=Tb.data_ptr(), R_bar=Rb.data_ptr(),
+                N=cnt, n=m.n, k=m.k, max_iter=0, A_bar=g["Ab"].data_ptr(), B_bar=g["Bb"].data_ptr(), C_bar=g["Cb"].data_ptr(),
+                D_bar=g["Db"].data_ptr(), status=g["st2"].data_ptr(),
+            )  # fmt: skip
+            e = mark("policy_adjoint")
+            L.check(lib.gecon_policy_adjoint_batched(C.byref(pa), C.c_void_p(stream)), "gecon_policy_adjoint_batched")
+            e and e.record()
+            xssb = None
+            if self.ss_obs_intercept:  # d = scale * log x_ss (or scale * x_ss): adjoint of the steady state
+                xssb = g["xssb"][:cnt]
+                xssb.zero_()
+                xs = ws["xss"][:cnt].index_select(1, ws["d_var"])
+                dbar = g["db"][:cnt].index_select(1, ws["d_pos"]) * ws["d_scale"]
+                xssb.index_add_(1, ws["d_var"], torch.where(ws["d_loglin"], dbar / xs, dbar))
+            e = mark("jacobian_vjp")
+            m.vjp_device(ws["theta"][:cnt], g["Ab"], g["Bb"], g["Cb"], g["Db"], xssb, g["thb"], stream)
+            e and e.record()
+            out = grad[lo : lo + cnt]
+            out[:, : m.n_theta] = g["thb"][:cnt]
+            out[:, m.n_theta : m.n_theta + m.k] = g["qb"][:cnt]
+            if n_err:
+                out[:, m.n_theta + m.k :] = g["hb"][:cnt][:, self.err_pos]
+            bad = (status[lo : lo + cnt] != 0) | (g["st2"][:cnt] != 0)
+            out[bad] = 0.0
+        return ll, grad, status
+
+    def loglik_and_grad(self, theta_full, Y, device="cuda:0"):
+        """HOST arrays in, HOST arrays out: (ll, grad, status)."""
+        L.require_device()
+        th = np.ascontiguousarray(np.atleast_2d(theta_full), dtype=np.float64)
+        dev = torch.device(device)
+        th_d = torch.from_numpy(th).pin_memory().to(dev, non_blocking=True)
+        Y_d = torch.as_tensor(np.ascontiguousarray(Y, dtype=np.float64).reshape(-1, self.p)).to(dev)
+        ll, grad, st = self.loglik_and_grad_device(th_d, Y_d)
+        return ll.cpu().numpy(), grad.cpu().numpy(), st.cpu().numpy()
 
     def loglik(self, theta_full, Y, device="cuda:0"):
         """HOST arrays in, HOST arrays out (the end-to-end call a sampler makes): pinned staging, one H2D copy of the

@@ -245,6 +245,85 @@ typedef struct gecon_propagate_args {
 int gecon_propagate_batched(const gecon_propagate_args* args, void* stream);
 int gecon_propagate_host(const gecon_propagate_args* args);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Gradient path.
+ *
+ * gecon_kalman_grad_*: the log-likelihood of gecon_kalman_ll_* (same arguments, Z shared or a selector) AND its gradient
+ * with respect to T, R, the shock / measurement-error scales and the observation intercept, by a reverse sweep over the
+ * stored predicted moments (P0 = dlyap(T, R Q R') is differentiated through a second doubling).  Replaces the graph
+ * pytensor differentiates behind PyMCStateSpace.build_statespace_graph (gEconpy/model/statespace.py:812-820,1151-1157).
+ * With sigma_inputs != 0, q_bar / h_bar are derivatives with respect to the standard deviations.
+ * Sizes: n <= 48, k <= n, p <= 8.  Gated draws (status_in & gate_mask) get ll = -inf and zero gradients.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gecon_kalman_grad_args {
+    size_t struct_size;
+    const double* T;
+    const double* R;
+    const double* qdiag;
+    int64_t q_stride;
+    const double* hdiag;
+    int64_t h_stride;
+    const double* Z;         /* [p][n] shared, or NULL when obs_idx is given */
+    const int32_t* obs_idx;
+    const double* d;
+    int64_t d_stride;
+    const double* Y;
+    int64_t N;
+    int32_t n;
+    int32_t k;
+    int32_t p;
+    int32_t Tobs;
+    double jitter;
+    double missing_fill;
+    int32_t mvn_const_mode;
+    int32_t lyap_max_iter;
+    const int32_t* status_in;
+    int32_t gate_mask;
+    int32_t sigma_inputs;
+    double* ll;       /* [N] out */
+    int32_t* status;  /* [N] out */
+    double* T_bar;    /* [N][n][n] out: dll/dT */
+    double* R_bar;    /* [N][n][k] out: dll/dR */
+    double* q_bar;    /* [N][k] out: dll/dq (variances) or dll/dsigma */
+    double* h_bar;    /* [N][p] out or NULL */
+    double* d_bar;    /* [N][p] out or NULL */
+} gecon_kalman_grad_args;
+
+int gecon_kalman_grad_batched(const gecon_kalman_grad_args* args, void* stream);
+int gecon_kalman_grad_host(const gecon_kalman_grad_args* args);
+
+/* gecon_policy_adjoint_*: reverse mode of the perturbation solution.  Given T_bar (and optionally R_bar) returns the
+ * adjoints of A, B, C (and D):
+ *   o1_policy_function_adjoints(A, B, C, T, T_bar) -> [A_bar, B_bar, C_bar]   gEconpy/solvers/shared.py:12-71
+ *   (the pullback of CycleReductionWrapper / GensysWrapper / scan_cycle_reduction, cycle_reduction.py:212-213,
+ *   gensys.py:668-676), plus R = -(C T + B)^-1 D (shared.py:74-75) in reverse when R_bar, R and D are given.
+ * The reference solves an n^2 x n^2 Kronecker system for the multipliers S; here W' S + C' S T' = -T_bar (W = C T + B)
+ * is solved as the Stein equation S = Q + G S T' by doubling.  Singular W: NaN outputs + GECON_ST_SINGULAR.  n <= 64. */
+typedef struct gecon_policy_adjoint_args {
+    size_t struct_size;
+    const double* A;      /* [N][n][n] (not read: A_bar = S does not depend on A; kept for the reference's signature) */
+    const double* B;
+    const double* C;
+    const double* D;      /* [N][n][k] or NULL */
+    const double* T;
+    const double* R;      /* [N][n][k] or NULL */
+    const double* T_bar;  /* [N][n][n] */
+    const double* R_bar;  /* [N][n][k] or NULL */
+    int64_t N;
+    int32_t n;
+    int32_t k;
+    int32_t max_iter;     /* doubling steps, <= 0: 64 */
+    int32_t reserved0;
+    double* A_bar;
+    double* B_bar;
+    double* C_bar;
+    double* D_bar;        /* [N][n][k] or NULL */
+    int32_t* status;      /* [N] or NULL */
+} gecon_policy_adjoint_args;
+
+int gecon_policy_adjoint_batched(const gecon_policy_adjoint_args* args, void* stream);
+int gecon_policy_adjoint_host(const gecon_policy_adjoint_args* args);
+
 /* library / device information */
 int gecon_abi_version(void);
 int gecon_device_count(void);

@@ -1,0 +1,167 @@
+"""GPU parity of the gradient path through the C ABI: Kalman reverse sweep, policy / selection
+adjoints (o1_policy_function_adjoints), generated vector-Jacobian product and the whole theta -> (ll, dll/dtheta) chain,
+against oracle/adjoints.py (itself pinned against finite differences in tests/test_adjoints_cpu.py)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from helpers import SIGMA_ERR, SIGMA_SHOCK, draws, jacobian_batch, model, simulate_obs
+from oracle import adjoints as oad
+from oracle import solvers as osol
+from oracle import statespace as oss
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8  # relative to the largest entry of each gradient block
+
+
+@pytest.fixture(scope="module")
+def B():
+    from geconpy_b200 import batched
+
+    return batched
+
+
+def _close(got, ref, rtol=RTOL):
+    return np.abs(np.asarray(got) - ref).max() <= rtol * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n,k,p,Tobs,missing,selector", [(1, 1, 1, 10, False, True), (5, 2, 2, 25, False, False), (5, 2, 2, 25, True, False),
+                                                          (10, 4, 3, 60, True, True), (13, 3, 8, 20, True, False), (19, 9, 7, 30, False, True),
+                                                          (33, 5, 4, 15, True, True), (48, 6, 3, 8, False, False)])
+@pytest.mark.parametrize("device_path", [False, True])
+def test_kalman_grad_matches_oracle(B, n, k, p, Tobs, missing, selector, device_path):
+    import torch
+
+    rng = np.random.default_rng(n * 7 + p)
+    N = 3
+    T = rng.standard_normal((N, n, n))
+    for i in range(N):
+        T[i] *= 0.8 / np.abs(np.linalg.eigvals(T[i])).max()
+    R = rng.standard_normal((N, n, k))
+    q, h = 0.5 + rng.random((N, k)), 0.1 + rng.random((N, p))
+    obs = np.sort(rng.choice(n, size=p, replace=False)).astype(np.int32)
+    Z = rng.standard_normal((p, n))
+    if selector:
+        Z = np.zeros((p, n))
+        Z[np.arange(p), obs] = 1.0
+    Y = rng.standard_normal((Tobs, p))
+    d = 0.1 * rng.standard_normal((N, p))
+    if missing:
+        Y[3, 0], Y[5, p - 1] = np.nan, -9999.0
+        Y[7] = np.nan
+        d[:] = 0.0
+    kw = dict(obs_idx=obs) if selector else dict(Z=Z)
+    args = [T, R, np.sqrt(q), Y]
+    if device_path:
+        args = [torch.as_tensor(x, device="cuda") for x in args]
+    out = B.kalman_loglik_grad(*args, hdiag=np.sqrt(h), d=d, sigma_inputs=True, **kw)
+    out = {key: (v.cpu().numpy() if hasattr(v, "cpu") else v) for key, v in out.items()}
+    ll_fwd, _ = B.kalman_loglik(T, R, q, Y, hdiag=h, d=d, **kw)
+    for i in range(N):
+        g = oad.kalman_loglik_adjoints(Y, T[i], R[i], q[i], Z, h[i], d[i])
+        assert out["status"][i] == 0
+        assert abs(out["ll"][i] - g["ll"]) <= 1e-7 and abs(out["ll"][i] - ll_fwd[i]) <= 1e-7
+        assert _close(out["T"][i], g["T"]) and _close(out["R"][i], g["R"]) and _close(out["d"][i], g["d"])
+        assert _close(out["q"][i], 2 * np.sqrt(q[i]) * g["q"]) and _close(out["h"][i], 2 * np.sqrt(h[i]) * g["h"])
+
+
+@pytest.mark.parametrize("name", ["rbc", "rbc_extended", "full_nk", "nk_complete_more_shocks", "nk_rbc_composite"])
+@pytest.mark.parametrize("with_R", [False, True])
+def test_policy_adjoints_match_the_kronecker_restatement(B, name, with_R):
+    mod = model(name)
+    th = draws(mod, 4, seed=2, width=0.02, valid=True)
+    A, Bm, Cm, D = jacobian_batch(mod, th)
+    N, n, k = len(th), mod.n, mod.k
+    res = B.cr_solve(A, Bm, Cm, D, max_iter=1000, tol=1e-13)
+    T, R = res.T, res.R
+    rng = np.random.default_rng(1)
+    Tb, Rb = rng.standard_normal((N, n, n)), rng.standard_normal((N, n, k))
+    Ab, Bb, Cb, Db, st = B.policy_adjoints(A, Bm, Cm, T, Tb, **(dict(D=D, R=R, R_bar=Rb) if with_R else {}))
+    for i in range(N):
+        tb, b0, c0 = Tb[i], 0.0, 0.0
+        if with_R:
+            b0, c0, d0, tadd = oad.selection_adjoints(Bm[i], Cm[i], D[i], T[i], R[i], Rb[i])
+            tb = tb + tadd
+            assert _close(Db[i], d0)
+        S, SB, SC = oad.policy_adjoints_kron(A[i], Bm[i], Cm[i], T[i], tb)
+        assert st[i] == 0
+        assert _close(Ab[i], S) and _close(Bb[i], SB + b0) and _close(Cb[i], SC + c0)
+
+
+def test_o1_policy_function_adjoints_keeps_the_reference_signature(B):
+    from geconpy_b200.solvers.shared import o1_policy_function_adjoints
+
+    mod = model("rbc")
+    A, Bm, Cm, D = mod.jacobians(mod.theta_vector(), mode="statespace")
+    T = osol.cycle_reduction_core(A, Bm, Cm, max_iter=1000, tol=1e-13)[0]
+    Tb = np.random.default_rng(0).standard_normal(T.shape)
+    out = o1_policy_function_adjoints(A, Bm, Cm, T, Tb)
+    assert isinstance(out, list) and len(out) == 3
+    for got, ref in zip(out, oad.policy_adjoints_kron(A, Bm, Cm, T, Tb)):
+        assert got.shape == T.shape and _close(got, ref)
+    # singular C T + B -> NaN + status, never an exception
+    Ab, _, _, _, st = B.policy_adjoints(np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 4)), np.ones((4, 4)))
+    assert st != 0 and np.isnan(Ab).all()
+
+
+@pytest.mark.parametrize("name,Tobs", [("rbc", 60), ("full_nk", 50), ("nk_complete_more_shocks", 30)])
+def test_pipeline_gradient_matches_oracle(name, Tobs):
+    """theta -> (ll, dll/d[theta, sigma_shock, error_sigma]) through all seven launches."""
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    mod = model(name)
+    observed = mod.spec["observed_default"]
+    cm = CompiledModel(name)
+    ss = BatchedStateSpace(cm).configure(observed_states=observed, measurement_error=observed, tol=1e-13, max_iter=1000, chunk=8)
+    N = 10
+    th = draws(mod, N, seed=31, width=0.02, valid=True)
+    Y = simulate_obs(mod, Tobs, seed=3, sigma_err=SIGMA_ERR)
+    sig = np.full((N, mod.k), SIGMA_SHOCK) * (1.0 + 0.1 * np.arange(N))[:, None]
+    err = np.full((N, len(observed)), SIGMA_ERR)
+    full = np.hstack([th, sig, err])
+    ll, grad, st = ss.loglik_and_grad(full, Y)
+    ll_fwd, st_fwd = ss.loglik(full, Y)
+    assert np.array_equal(st, st_fwd)
+    n_ok = 0
+    for i in range(N):
+        ref = oss.loglik(mod, th[i], Y, observed, sig[i], err[i], tol=1e-13, max_iter=1000)
+        if not (ref["ok"] and np.isfinite(ref["ll"])):
+            assert st[i] != 0 and np.isneginf(ll[i]) and not grad[i].any()
+            continue
+        n_ok += 1
+        g = oad.loglik_grad(mod, th[i], Y, observed, sig[i], err[i])
+        assert st[i] == 0 and abs(ll[i] - g["ll"]) <= 1e-7 and abs(ll[i] - ll_fwd[i]) <= 1e-7
+        nt, k = mod.theta_vector().size, mod.k
+        # the oracle's last stage is a central difference (1e-9 relative): compare at 1e-6 of the largest component
+        assert _close(grad[i, :nt], g["theta"], rtol=1e-6), (i, np.abs(grad[i, :nt] - g["theta"]).max())
+        assert _close(grad[i, nt : nt + k], g["sigma_shock"], rtol=1e-7) and _close(grad[i, nt + k :], g["sigma_err"], rtol=1e-7)
+    assert n_ok >= N // 2
+
+
+def test_pipeline_gradient_with_aggregation_and_intercept():
+    """Augmented states and a steady-state intercept flow through the gradient: checked against central differences of
+    the GPU log-likelihood itself (loose tolerance: ll ~ 1e3, step 1e-6)."""
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    from test_gpu_augmentation import _aggregated_data
+
+    mod = model("rbc")
+    observed, ta = ["Y", "C"], {"Y": "sum"}
+    ss = BatchedStateSpace(CompiledModel("rbc")).configure(
+        observed_states=observed, measurement_error=observed, tol=1e-13, max_iter=1000, temporal_aggregation=ta, aggregation_period=4,
+        ss_obs_intercept=["Y", "C"],
+    )  # fmt: skip
+    Y = _aggregated_data(mod, observed, ta, 4, ["Y", "C"], 40, seed=8, dense=True)
+    th = draws(mod, 3, seed=5, width=0.002, valid=True)
+    full = np.hstack([th, np.full((3, mod.k), SIGMA_SHOCK), np.full((3, 2), SIGMA_ERR)])
+    ll, grad, st = ss.loglik_and_grad(full, Y)
+    assert (st == 0).all()
+    for j in range(full.shape[1]):
+        h = 1e-6 * np.maximum(1.0, np.abs(full[:, j])) if j < th.shape[1] else 1e-8
+        fp, fm = full.copy(), full.copy()
+        fp[:, j] += h
+        fm[:, j] -= h
+        num = (ss.loglik(fp, Y)[0] - ss.loglik(fm, Y)[0]) / (2 * h)
+        assert np.abs(num - grad[:, j]).max() <= 2e-4 * max(1.0, np.abs(num).max()), (j, num, grad[:, j])

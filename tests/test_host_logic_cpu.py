@@ -41,12 +41,14 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     exe = tmp_path / "abi_sizes"
     src.write_text(
         f'#include <stdio.h>\n#include "{ROOT}/include/gecon_b200.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(gecon_cr_args), sizeof(gecon_bk_args), '
-        "sizeof(gecon_dlyap_args), sizeof(gecon_kalman_args));return 0;}\n"
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gecon_cr_args), sizeof(gecon_bk_args), '
+        "sizeof(gecon_dlyap_args), sizeof(gecon_kalman_args), sizeof(gecon_kalman_grad_args), sizeof(gecon_policy_adjoint_args), "
+        "sizeof(gecon_propagate_args));return 0;}\n"
     )
     subprocess.run(["gcc", "-o", str(exe), str(src)], check=True, capture_output=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    assert sizes == [C.sizeof(_lib.CrArgs), C.sizeof(_lib.BkArgs), C.sizeof(_lib.DlyapArgs), C.sizeof(_lib.KalmanArgs)]
+    mirrors = [_lib.CrArgs, _lib.BkArgs, _lib.DlyapArgs, _lib.KalmanArgs, _lib.KalmanGradArgs, _lib.PolicyAdjointArgs, _lib.PropagateArgs]
+    assert sizes == [C.sizeof(m) for m in mirrors]
 
 
 def test_no_device_is_a_loud_error_not_a_fallback():
