@@ -229,6 +229,7 @@ class BatchedStateSpace:
             status=torch.empty((nc,), **i32), n_iter=torch.empty((nc,), **i32), n_unstable=torch.empty((nc,), **i32),
             resid=torch.empty((nc,), **f64),
             lead=torch.as_tensor(m.permuted_lead_var_idx, **i32), obs=torch.as_tensor(self.obs_idx_filter, **i32),
+            err_pos=torch.as_tensor(self.err_pos, device=device),
         )  # fmt: skip
         if self.n_aug > self.n_filter:
             # constant rows [F | kron(I, shift)] of the augmented transition: written once, the solver kernel only ever
@@ -285,7 +286,7 @@ class BatchedStateSpace:
             ws["theta"][:cnt].copy_(th[:, : m.n_theta])
             ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
             if n_err:
-                ws["herr"][:cnt, self.err_pos] = th[:, m.n_theta + m.k :]
+                ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + m.k :])
             st = ws["status"][:cnt]
             e = mark("jacobian")
             m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
@@ -370,6 +371,7 @@ class BatchedStateSpace:
                 Cb=torch.empty((nc, n, n), **f64), Db=torch.empty((nc, n, k), **f64), thb=torch.empty((nc, m.n_theta), **f64),
                 xssb=torch.zeros((nc, n), **f64), U=torch.as_tensor(self.filter_vars.astype(np.int64), device=dev),
                 ll=torch.empty((nc,), **f64), st2=torch.empty((nc,), dtype=torch.int32, device=dev),
+                rows=torch.empty((nc, self.n_filter, n), **f64), err_pos=torch.as_tensor(self.err_pos, device=dev),
             )  # fmt: skip
         stream = torch.cuda.current_stream(dev).cuda_stream
         n_err, nf, U = len(self.measurement_error), self.n_filter, g["U"]
@@ -388,7 +390,7 @@ class BatchedStateSpace:
             ws["theta"][:cnt].copy_(th[:, : m.n_theta])
             ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
             if n_err:
-                ws["herr"][:cnt, self.err_pos] = th[:, m.n_theta + m.k :]
+                ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + m.k :])
             st = ws["status"][:cnt]
             e = mark("jacobian")
             m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
@@ -437,8 +439,11 @@ class BatchedStateSpace:
             Tb, Rb = g["Tb"][:cnt], g["Rb"][:cnt]
             Tb.zero_()
             Rb.zero_()
-            Tb[:, U[:, None], U[None, :]] = g["Tb_f"][:cnt, :nf, :nf]
-            Rb[:, U] = g["Rb_f"][:cnt, :nf]
+            rows = g["rows"][:cnt]
+            rows.zero_()
+            rows.index_copy_(2, U, g["Tb_f"][:cnt, :nf, :nf])
+            Tb.index_copy_(1, U, rows)
+            Rb.index_copy_(1, U, g["Rb_f"][:cnt, :nf])
             pa = L.PolicyAdjointArgs(
                 struct_size=C.sizeof(L.PolicyAdjointArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
                 D=ws["D"].data_ptr(), T=g["Tfull"].data_ptr(), R=g["Rfull"].data_ptr(), T_bar=Tb.data_ptr(), R_bar=Rb.data_ptr(),
@@ -462,9 +467,9 @@ class BatchedStateSpace:
             out[:, : m.n_theta] = g["thb"][:cnt]
             out[:, m.n_theta : m.n_theta + m.k] = g["qb"][:cnt]
             if n_err:
-                out[:, m.n_theta + m.k :] = g["hb"][:cnt][:, self.err_pos]
+                out[:, m.n_theta + m.k :] = g["hb"][:cnt].index_select(1, g["err_pos"])
             bad = (status[lo : lo + cnt] != 0) | (g["st2"][:cnt] != 0)
-            out[bad] = 0.0
+            out.masked_fill_(bad[:, None], 0.0)
         return ll, grad, status
 
     def loglik_and_grad(self, theta_full, Y, device="cuda:0"):
