@@ -15,6 +15,8 @@
 //      by the constant term of phase 4 (R Q R' + jitter T T')
 //   3  W = T [P+ | a+]      (DMMA; T fragments live in registers for the whole draw)
 //   4  P = R Q R' + W T'    (DMMA; R Q R' in registers for NP <= 16)
+// P is symmetric, so phases 2 and 4 only compute and store the tiles on or above the block diagonal (3 of 4 tiles at NP = 16,
+// 6 of 9 at NP = 24) and the readers of phases 1 and 3 take mirror images for the rest.
 // P, W and the [K | M] panel go through the warp's private shared-memory tiles only to change fragment layout
 // (accumulator -> A/B operand), four __syncwarp per step.  P is not symmetrised explicitly: the update term is
 // symmetric, and the rounding-level antisymmetric part of W T' is contracted by the next T . T' (rho(T) < 1).
@@ -87,6 +89,38 @@ __device__ __forceinline__ void wacc_store(const WAcc<NP>& a, double* __restrict
 #pragma unroll
         for (int ct = 0; ct < NP / 8; ++ct)
             *reinterpret_cast<double2*>(base + s * 8 * LD + ct * 8) = make_double2(a.v[s][ct][0], a.v[s][ct][1]);
+}
+
+// The covariance is symmetric: inside the filter loop only the tiles on or above the block diagonal (ct >= s) are computed
+// and stored; a reader that needs an element of a lower tile takes its mirror image from the upper one.
+template <int NP>
+__device__ __forceinline__ void wacc_load_upper(WAcc<NP>& a, const double* __restrict__ M, int lane) {
+    constexpr int LD = Cfg<NP>::LD;
+    const double* base = M + (lane >> 2) * LD + 2 * (lane & 3);
+#pragma unroll
+    for (int s = 0; s < NP / 8; ++s)
+#pragma unroll
+        for (int ct = s; ct < NP / 8; ++ct) {
+            const double2 t = *reinterpret_cast<const double2*>(base + s * 8 * LD + ct * 8);
+            a.v[s][ct][0] = t.x;
+            a.v[s][ct][1] = t.y;
+        }
+}
+template <int NP>
+__device__ __forceinline__ void wacc_store_upper(const WAcc<NP>& a, double* __restrict__ M, int lane) {
+    constexpr int LD = Cfg<NP>::LD;
+    double* base = M + (lane >> 2) * LD + 2 * (lane & 3);
+#pragma unroll
+    for (int s = 0; s < NP / 8; ++s)
+#pragma unroll
+        for (int ct = s; ct < NP / 8; ++ct)
+            *reinterpret_cast<double2*>(base + s * 8 * LD + ct * 8) = make_double2(a.v[s][ct][0], a.v[s][ct][1]);
+}
+// offset of element (r, c) of a symmetric tile whose lower block triangle is not maintained
+template <int NP>
+__device__ __forceinline__ int sym_off(int r, int c) {
+    constexpr int LD = Cfg<NP>::LD;
+    return ((r >> 3) > (c >> 3)) ? c * LD + r : r * LD + c;
 }
 
 // acc += A * op(B) for one warp, operands in shared-memory tiles; k-steps [0, nks).  TB: acc += A * B_s'.
@@ -309,13 +343,13 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, MINB) kalman_ll_warp
 #pragma unroll
             for (int a = 0; a < PT; ++a) {
                 const bool ob = (wb >> a) & 1;
-                const double s = P[obs_r[a] * LD + il];
+                const double s = P[sym_off<NP>(obs_r[a], il)];
                 pz[a] = ob ? s : 0.0;
                 const double za = W[obs_r[a] * LD + n];
                 v[a] = (ob ? y[a] : 0.0) - (dv0[a] + (ob ? za : 0.0));
 #pragma unroll
                 for (int b = 0; b <= a; ++b) {
-                    double x = P[obs_r[a] * LD + obs_r[b]];
+                    double x = P[sym_off<NP>(obs_r[a], obs_r[b])];
                     x = (ob && ((wb >> b) & 1)) ? x : 0.0;
                     if (a == b) x += ob ? hv[a] : 0.0;
                     if constexpr (GM_REGS) {
@@ -429,11 +463,11 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, MINB) kalman_ll_warp
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
 #pragma unroll
-                    for (int ct = 0; ct < NS; ++ct) dmma884(pacc.v[s][ct][0], pacc.v[s][ct][1], a[s], b[ct]);
+                    for (int ct = s; ct < NS; ++ct) dmma884(pacc.v[s][ct][0], pacc.v[s][ct][1], a[s], b[ct]);
             }
-            wacc_store<NP>(pacc, P, lane);
+            wacc_store_upper<NP>(pacc, P, lane);
             __syncwarp();
-            // ---- phase 4: W = T [P+ | a+]
+            // ---- phase 4: W = T [P+ | a+]   (rows of P+ below the block diagonal are read as mirror images)
             WAcc<NP> w;
             wacc_zero(w);
 #pragma unroll
@@ -441,7 +475,7 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, MINB) kalman_ll_warp
                 if (ks < nks) {
                     double b[NS];
 #pragma unroll
-                    for (int ct = 0; ct < NS; ++ct) b[ct] = P[(4 * ks + q) * LD + 8 * ct + g];
+                    for (int ct = 0; ct < NS; ++ct) b[ct] = ((ks >> 1) > ct) ? P[(8 * ct + g) * LD + 4 * ks + q] : P[(4 * ks + q) * LD + 8 * ct + g];
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -452,7 +486,7 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, MINB) kalman_ll_warp
             __syncwarp();
             // ---- phase 5: P = R Q R' + W T'
             if constexpr (C0_REGS) pacc = c0;
-            else wacc_load<NP>(pacc, C0t, lane);
+            else wacc_load_upper<NP>(pacc, C0t, lane);
 #pragma unroll
             for (int ks = 0; ks < KSN; ++ks) {
                 if (ks < nks) {
@@ -462,10 +496,10 @@ __global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, MINB) kalman_ll_warp
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
 #pragma unroll
-                        for (int ct = 0; ct < NS; ++ct) dmma884(pacc.v[s][ct][0], pacc.v[s][ct][1], a[s], tA[ct][ks]);
+                        for (int ct = s; ct < NS; ++ct) dmma884(pacc.v[s][ct][0], pacc.v[s][ct][1], a[s], tA[ct][ks]);
                 }
             }
-            wacc_store<NP>(pacc, P, lane);
+            wacc_store_upper<NP>(pacc, P, lane);
             __syncwarp();
         }
         if (!p.ll_t) ll_acc = -0.5 * (n_ll_steps * ll_const + (log(detprod) + (double)det_exp * 0.6931471805599453) + quad_acc);
