@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -37,7 +38,7 @@ inline int sm_count() {
 // Persistent-grid launch helper: sets the dynamic shared memory attribute, asks the occupancy calculator for the
 // resident CTAs per SM and returns grid = min(N, SMs * CTAs/SM).
 template <typename K>
-inline int persistent_grid(K kernel, int threads, size_t smem, long long N, int* grid, int* ctas_per_sm) {
+inline int persistent_grid(K kernel, int threads, size_t smem, long long N, int* grid, int* ctas_per_sm, const char* cap_env = nullptr) {
     GECON_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // these kernels live in shared memory and barely touch L1: ask for the largest shared-memory carve-out
     GECON_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -46,6 +47,12 @@ inline int persistent_grid(K kernel, int threads, size_t smem, long long N, int*
     if (per_sm < 1) {
         set_last_error("kernel does not fit on an SM (threads=%d, smem=%zu)", threads, smem);
         return GECON_E_UNSUPPORTED_SIZE;
+    }
+    if (cap_env) {  // resident CTAs per SM capped from the environment: lets two kernels of different chunks share the SMs
+        if (const char* e = getenv(cap_env)) {
+            const int cap = atoi(e);
+            if (cap > 0 && cap < per_sm) per_sm = cap;
+        }
     }
     const int sms = sm_count();
     long long g = (long long)sms * per_sm;

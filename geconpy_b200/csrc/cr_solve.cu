@@ -388,7 +388,7 @@ static int check_cr_args(const gecon_cr_args* a) {
 template <int NP>
 static int launch_cr(const gecon_cr_args& a, cudaStream_t st) {
     int grid = 0;
-    int rc = persistent_grid(cr_solve_kernel<NP>, Cfg<NP>::NT, CrSmem<NP>::bytes, a.N, &grid, nullptr);
+    int rc = persistent_grid(cr_solve_kernel<NP>, Cfg<NP>::NT, CrSmem<NP>::bytes, a.N, &grid, nullptr, "GECON_CR_CTAS_PER_SM");
     if (rc) return rc;
     double* ws = nullptr;
     if (cr_a1h_global<NP>()) GECON_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)grid * Cfg<NP>::TILE, st));

@@ -41,7 +41,7 @@ static int launch_one_warp_b(const gecon_kalman_args& a, cudaStream_t st, int* i
         return GECON_E_UNSUPPORTED_SIZE;
     }
     int grid = 0, per_sm = 0;
-    int rc = persistent_grid(kalman_ll_warp_kernel<NP, PT, MINB>, S::WPC * 32, smem, (a.N + S::WPC - 1) / S::WPC, &grid, &per_sm);
+    int rc = persistent_grid(kalman_ll_warp_kernel<NP, PT, MINB>, S::WPC * 32, smem, (a.N + S::WPC - 1) / S::WPC, &grid, &per_sm, "GECON_KF_CTAS_PER_SM");
     if (rc) return rc;
     if (info) {
         info[0] = per_sm;

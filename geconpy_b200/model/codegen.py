@@ -169,6 +169,101 @@ class LinearizedModel:
             "ops": int(sum(sp.count_ops(r) for _, r in subs) + sum(sp.count_ops(r) for r in red)),
         }
 
+    # ------------------------------------------------------------------------------------------------ observation equations
+    def log_linearized_variables(self) -> set:
+        """Names the state-space model treats as log-linearised (build.py:675, statespace.py:154)."""
+        return (set(self.var_names) - set(self.not_loglin_variables)) if self.log_linearize else set()
+
+    def parse_observation_equation(self, name: str, expr_str: str):
+        """GCN-syntax observation equation -> sympy, in this model's symbols (statespace.py:390-444): ``v[]`` is a
+        contemporaneous model variable, ``v[-k]`` a lag, ``v[ss]`` a steady-state value, bare names are parameters.
+        Leads, unknown variables and unknown symbols raise ``ValueError`` with the reference's wording."""
+        ns = dict(self.p_sym)
+        seen = {}
+
+        def ref(mm):
+            v, idx = mm.group(1), mm.group(2).replace(" ", "")
+            if idx == "ss":
+                key = f"{v}__ss"
+            else:
+                t = 0 if idx == "" else int(idx)
+                if t > 0:
+                    raise ValueError(
+                        f"Observation equation {name!r} contains a lead reference {v}[{idx}]. Only contemporaneous and lagged "
+                        "model variables are allowed."
+                    )
+                key = f"{v}__lag{-t}"
+            if v not in self.var_names:
+                raise ValueError(f"Observation equation {name!r} references unknown model variable {v!r}. Known: {sorted(self.var_names)}")
+            if key not in seen:
+                seen[key] = self.ss_sym[v] if idx == "ss" else sp.Symbol(_c_ident("obsx_", key), real=True)
+            return f" __OBSREF_{key}__ "
+
+        text = re.sub(r"([A-Za-z_][A-Za-z_0-9]*)\[([^\]]*)\]", ref, expr_str).replace("^", "**")
+        for key, sym in seen.items():
+            ns[f"__OBSREF_{key}__"] = sym
+        try:
+            expr = sp.sympify(text, locals=ns)
+        except (sp.SympifyError, SyntaxError, TypeError) as e:
+            raise ValueError(f"cannot parse observation equation {name!r}: {expr_str!r}") from e
+        known = set(ns.values())
+        for fs in expr.free_symbols:
+            if fs not in known:
+                raise ValueError(
+                    f"Observation equation {name!r} references unknown symbol {fs.name!r}: not a model variable, parameter, or hyperparameter."
+                )
+        refs = {}
+        for key, sym in seen.items():
+            if not key.endswith("__ss"):
+                v, lag = key.rsplit("__lag", 1)
+                refs[sym] = (v, -int(lag))
+        return expr, refs
+
+    def linearize_observation_equation(self, expr, refs):
+        """First-order linearisation around the steady state (statespace.py:446-507): every reference v_{t+k} becomes
+        v_ss exp(v~) (log-linearised) or v_ss + v~; intercept = value at v~ = 0, coefficient = d/dv~ there.  Returns
+        (intercept, {(variable, lag): coefficient}) in steady-state and parameter symbols."""
+        loglin = self.log_linearized_variables()
+        forward, tildes = {}, {}
+        for sym, (v, lag) in refs.items():
+            tl = sp.Symbol(f"_tilde_{v}_{'0' if lag == 0 else f'm{-lag}'}", real=True)
+            tildes[(v, lag)] = tl
+            forward[sym] = self.ss_sym[v] * sp.exp(tl) if v in loglin else self.ss_sym[v] + tl
+        g = expr.xreplace(forward)
+        zero = {tl: sp.Integer(0) for tl in tildes.values()}
+        return g.xreplace(zero), {key: sp.diff(g, tl).xreplace(zero) for key, tl in tildes.items()}
+
+    def _ss_prelude(self):
+        """Text of: free parameters -> deterministic parameters -> analytic steady state (one CSE pass)."""
+        cc = lambda e: sp.ccode(e, strict=True)  # noqa: E731
+        out = [f"    const double {self.p_sym[p].name} = th[{i}];" for i, p in enumerate(self.param_names)]
+        for d, e in zip(self.det_names, self.det_exprs):
+            out.append(f"    const double {self.p_sym[d].name} = {cc(e)};")
+        ss_subs, ss_red = sp.cse(self.ss_exprs, symbols=sp.numbered_symbols("s_tmp_"), optimizations="basic")
+        for sym, e in ss_subs:
+            out.append(f"    const double {sym.name} = {cc(e)};")
+        for v, e in zip(self.var_names, ss_red):
+            out.append(f"    const double {self.ss_sym[v].name} = {cc(e)};")
+        return out
+
+    def obs_source(self, z_cells: dict, d_cells: dict, tag: str) -> str:
+        """CUDA source of the per-draw observation kernel: writes the parameter-dependent cells of the design matrix
+        (``z_cells``: {flat index into a draw's [p][k_states] block: sympy expr}) and of the observation intercept
+        (``d_cells``: {row: expr}); every other cell of Z and d is left as the caller initialised it."""
+        cc = lambda e: sp.ccode(e, strict=True)  # noqa: E731
+        exprs = [sp.sympify(e) for e in list(z_cells.values()) + list(d_cells.values())]
+        subs, red = sp.cse(exprs, symbols=sp.numbered_symbols("o_tmp_"), optimizations="basic") if exprs else ([], [])
+        lines = self._ss_prelude()
+        for sym, e in subs:
+            lines.append(f"    const double {sym.name} = {cc(e)};")
+        nz = len(z_cells)
+        for idx, e in zip(z_cells, red[:nz]):
+            lines.append(f"    Z[{int(idx)}] = {cc(e)};")
+        for row, e in zip(d_cells, red[nz:]):
+            lines.append(f"    d[{int(row)}] = {cc(e)};")
+        ident = re.sub(r"[^0-9A-Za-z_]", "_", f"{self.name}_{tag}")
+        return _OBS_TEMPLATE.format(name=ident, n_theta=self.n_theta, body="\n".join(lines))
+
     # ------------------------------------------------------------------------------------------------ reverse mode
     def vjp_body(self) -> str:
         """Device code of the vector-Jacobian product  theta_bar = sum_M <M_bar, dM/dtheta> (+ <xss_bar, dxss/dtheta>):
@@ -466,4 +561,50 @@ extern "C" int gecon_model_jacobian_host(const double* theta, int64_t N, double*
     return (int)e;
 }}
 #endif  // GECON_HOST_CHECK
+"""
+
+
+_OBS_TEMPLATE = r"""// GENERATED by geconpy_b200/model/codegen.py (observation equations of "{name}") -- do not edit.
+// theta -> steady state -> parameter-dependent cells of the design matrix Z and of the observation intercept d
+// (gEconpy/model/statespace.py:299-331, 363-388, 446-507).  One thread per draw.
+#include <math.h>
+#include <stdint.h>
+#include <stddef.h>
+#ifdef GECON_HOST_CHECK
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#else
+#include <cuda_runtime.h>
+#endif
+#define GECON_MODEL_NTHETA {n_theta}
+
+__device__ __forceinline__ void gecon_obs_eval(const double* __restrict__ th, double* __restrict__ Z, double* __restrict__ d) {{
+{body}
+}}
+
+#ifdef GECON_HOST_CHECK
+extern "C" int gecon_obs_host_check(const double* theta, int64_t N, double* Z, int64_t z_stride, double* d, int64_t d_stride) {{
+    for (int64_t i = 0; i < N; ++i) gecon_obs_eval(theta + (size_t)i * GECON_MODEL_NTHETA, Z + (size_t)i * z_stride, d + (size_t)i * d_stride);
+    return 0;
+}}
+#else
+__global__ void __launch_bounds__(128) gecon_obs_kernel(const double* __restrict__ theta, long long N, double* __restrict__ Z,
+                                                        long long z_stride, double* __restrict__ d, long long d_stride) {{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        gecon_obs_eval(theta + (size_t)i * GECON_MODEL_NTHETA, Z + (size_t)i * z_stride, d + (size_t)i * d_stride);
+}}
+
+// DEVICE pointers: Z is [N][p][k_states] (z_stride doubles per draw), d is [N][p] (d_stride); returns 0 or a cudaError_t
+extern "C" int gecon_obs_batched(const double* theta, int64_t N, double* Z, int64_t z_stride, double* d, int64_t d_stride, void* stream) {{
+    if (N <= 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (N + 127) / 128;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    gecon_obs_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(theta, N, Z, z_stride, d, d_stride);
+    return (int)cudaGetLastError();
+}}
+#endif
 """

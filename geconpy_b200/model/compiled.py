@@ -10,6 +10,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 from pathlib import Path
 
@@ -142,20 +143,40 @@ class BatchedStateSpace:
         check_bk: bool = True,
         chunk: int = 65536,
         reduce_state: bool = True,
+        n_streams: int | None = None,
         temporal_aggregation: dict | None = None,
         aggregation_period: int = 4,
         ss_obs_intercept: list | None = None,
+        observation_equations: dict | None = None,
     ):
         """Same meaning as ``DSGEStateSpace.configure`` (gEconpy/model/statespace.py:822-1090) for the arguments it
         shares: ``temporal_aggregation`` {"sum" | "mean" | "first" | "last"} with ``aggregation_period`` adds cumulator
         states (statespace.py:598-650), ``ss_obs_intercept`` puts log x_ss(theta) / x_ss(theta) of the listed observed
-        states into the observation intercept d (statespace.py:363-388)."""
+        states into the observation intercept d (statespace.py:363-388), ``observation_equations`` {observed series: GCN-syntax
+        expression in model variables (``v[]``, ``v[-1]``, ``v[ss]``) and parameters} is linearised around the steady state into a
+        parameter-dependent design-matrix row, an intercept and observation-lag states (statespace.py:390-556,652-694)."""
         m = self.model
         if solver not in ("cycle_reduction", "gensys"):
             raise NotImplementedError(f"solver={solver!r}: the B200 path solves by cycle reduction (gensys maps to CR + BK flag)")
-        unknown = [v for v in observed_states if v not in m.var_names]
+        observation_equations = dict(observation_equations or {})
+        unknown_keys = [k_ for k_ in observation_equations if k_ not in observed_states]
+        if unknown_keys:
+            raise ValueError(f"The following observation_equations entries are not in observed_states: {', '.join(unknown_keys)}")
+        overlap = set(observation_equations) & set(ss_obs_intercept or [])
+        if overlap:
+            raise ValueError(
+                f"The following observed states appear in both observation_equations and ss_obs_intercept: {', '.join(sorted(overlap))}. "
+                "An observation equation already determines its intercept; remove these names from one or the other."
+            )
+        unknown = [v for v in observed_states if v not in m.var_names and v not in observation_equations]
         if unknown:
             raise ValueError(f"unknown observed states {unknown}")
+        # parse + linearise now so that errors surface at configure time (statespace.py:1027-1035)
+        self._obs_eq = {}
+        for name_, expr_ in observation_equations.items():
+            sym_, refs_ = m.lin.parse_observation_equation(name_, expr_)
+            self._obs_eq[name_] = m.lin.linearize_observation_equation(sym_, refs_)
+        model_observed = [v for v in observed_states if v not in observation_equations]
         measurement_error = list(measurement_error or [])
         bad = [v for v in measurement_error if v not in observed_states]
         if bad:
@@ -170,7 +191,7 @@ class BatchedStateSpace:
         self.measurement_error = measurement_error
         self.p = len(observed_states)
         # filter runs in solver order: observed variable -> permuted position (T, R are not un-permuted in between)
-        self.obs_idx = m.inv_var_order[[m.var_names.index(v) for v in observed_states]].astype(np.int32)
+        self.obs_idx = m.inv_var_order[[m.var_names.index(v) for v in model_observed]].astype(np.int32)
         # the reference puts the error variances at positions 0..len(error_states)-1 of diag(H), whatever the position of
         # those states among the observed ones (statespace.py:800-808, "mirror the previous semantics"): reproduced
         self.err_pos = np.arange(len(measurement_error), dtype=np.int64)
@@ -178,23 +199,52 @@ class BatchedStateSpace:
         # T is identically zero, so those variables never feed back into the recursion.  With reduce_state the solver
         # kernel hands the filter the exact sub-blocks T[U][:, U], R[U] for U = states + observed (solver order).
         state_pos = m.inv_var_order[m.lin.state_var_idx]
-        self.filter_vars = np.array(sorted(set(state_pos.tolist()) | set(self.obs_idx.tolist())), dtype=np.int32) if reduce_state else np.arange(m.n, dtype=np.int32)
+        referenced = {int(m.inv_var_order[m.var_names.index(v)]) for _, co in self._obs_eq.values() for (v, _lag) in co}
+        self.filter_vars = (
+            np.array(sorted(set(state_pos.tolist()) | set(self.obs_idx.tolist()) | referenced), dtype=np.int32)
+            if reduce_state
+            else np.arange(m.n, dtype=np.int32)
+        )
         self.n_filter = int(self.filter_vars.size)
         self.obs_idx_filter = np.array([int(np.flatnonzero(self.filter_vars == o)[0]) for o in self.obs_idx], dtype=np.int32)
         self.reduce_state = bool(reduce_state)
+        self.n_streams = int(n_streams if n_streams is not None else os.environ.get("GECON_STREAMS", "1"))
         # ---- state augmentation (cumulators) and the observation intercept
         ss_obs_intercept = list(ss_obs_intercept or [])
         unknown = [v for v in ss_obs_intercept if v not in observed_states]
         if unknown:
             raise ValueError(f"The following ss_obs_intercept entries are not in observed_states: {', '.join(unknown)}")
-        self.aug = StateAugmentation(
-            [m.lin.vars_perm[int(u)] for u in self.filter_vars], list(observed_states), dict(temporal_aggregation or {}), int(aggregation_period)
+        depths = StateAugmentation.required_obs_lag_depths(
+            {k_: co.keys() for k_, (_ic, co) in self._obs_eq.items()}, temporal_aggregation, int(aggregation_period)
         )
+        self.aug = StateAugmentation(
+            [m.lin.vars_perm[int(u)] for u in self.filter_vars], list(observed_states), dict(temporal_aggregation or {}), int(aggregation_period),
+            obs_equation_names=tuple(self._obs_eq), obs_lag_depths=depths,
+        )  # fmt: skip
         self.n_aug = self.aug.k_states
         if self.n_aug > 64:
             raise NotImplementedError(f"augmented state dimension {self.n_aug} > 64")
         self.dense_Z = None if self.aug.is_selector() else np.ascontiguousarray(self.aug.design_matrix())
         self.ss_obs_intercept = ss_obs_intercept
+        self._obs_lib = None
+        if self._obs_eq:  # per-draw cells of Z and d: one generated kernel per configuration
+            z_cells, d_cells = {}, {}
+            for i_, name_ in enumerate(observed_states):
+                if name_ not in self._obs_eq:
+                    continue
+                icpt, coeffs = self._obs_eq[name_]
+                for col, terms in self.aug.design_cells(name_, coeffs).items():
+                    z_cells[i_ * self.n_aug + col] = sum(w_ * coeffs[key_] for w_, key_ in terms)
+                d_cells[i_] = icpt * (int(aggregation_period) if (temporal_aggregation or {}).get(name_) == "sum" else 1)
+            tag = "obs_" + "_".join(sorted(self._obs_eq))
+            src = m.lin.obs_source(z_cells, d_cells, tag)
+            lib_path = build_model(f"{m.name}_{tag}"[:80], src)
+            try:
+                self._obs_lib = C.CDLL(str(lib_path))
+            except OSError as e:
+                raise L.GeconLibraryError(f"cannot load {lib_path}: {e}") from e
+            self._obs_lib.gecon_obs_batched.restype = C.c_int
+            self._obs_lib.gecon_obs_batched.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         loglin = set(m.var_names) - set(m.lin.not_loglin_variables) if m.lin.log_linearize else set()
         self._d_pos = np.array([observed_states.index(v) for v in ss_obs_intercept], dtype=np.int64)
         self._d_var = np.array([m.var_names.index(v) for v in ss_obs_intercept], dtype=np.int64)
@@ -203,7 +253,7 @@ class BatchedStateSpace:
         self.tol, self.max_iter, self.solver_tol = float(tol), int(max_iter), float(solver_tol)
         self.cov_jitter, self.missing_fill_value, self.mvn_const = float(cov_jitter), float(missing_fill_value), mvn_const
         self.check_bk = bool(check_bk)
-        self.chunk = int(chunk)
+        self.chunk = int(os.environ.get("GECON_CHUNK", chunk))
         self.param_names = (
             list(m.param_names) + [f"sigma_{s}" for s in m.shock_names] + [f"error_sigma_{v}" for v in measurement_error]
         )
@@ -214,7 +264,15 @@ class BatchedStateSpace:
         return self
 
     # ------------------------------------------------------------------------------------------------ workspace
-    def _workspace(self, device, nc):
+    def _workspace(self, device, nc, slot: int = 0):
+        if slot:  # extra workspaces of the multi-stream pipeline
+            cache = self.__dict__.setdefault("_ws_extra", {})
+            main, self._ws = self._ws, cache.get(slot)
+            try:
+                cache[slot] = self._workspace(device, nc)
+            finally:
+                self._ws = main
+            return cache[slot]
         if self._ws is not None and self._ws["nc"] >= nc and self._ws["device"] == device:
             return self._ws
         m = self.model
@@ -237,9 +295,12 @@ class BatchedStateSpace:
             ws["T"][:, self.n_filter :, :] = torch.as_tensor(self.aug.transition_rows(), **f64)
         if self.dense_Z is not None:
             ws["Z"] = torch.as_tensor(self.dense_Z, **f64)
+            if self._obs_lib is not None:  # one design matrix per draw: constant rows now, equation rows by the obs kernel
+                ws["Z"] = ws["Z"].unsqueeze(0).repeat(nc, 1, 1).contiguous()
+        if self._obs_lib is not None or self.ss_obs_intercept:
+            ws["d"] = torch.zeros((nc, self.p), **f64)
         if self.ss_obs_intercept:
             ws["xss"] = torch.empty((nc, m.n), **f64)
-            ws["d"] = torch.zeros((nc, self.p), **f64)
             ws["d_var"] = torch.as_tensor(self._d_var, device=device)
             ws["d_pos"] = torch.as_tensor(self._d_pos, device=device)
             ws["d_loglin"] = torch.as_tensor(self._d_loglin, device=device)
@@ -266,9 +327,20 @@ class BatchedStateSpace:
         ll = out_ll if out_ll is not None else torch.empty((N,), dtype=torch.float64, device=dev)
         status = out_status if out_status is not None else torch.empty((N,), dtype=torch.int32, device=dev)
         nc = min(self.chunk, N)
-        ws = self._workspace(dev, nc)
-        stream = torch.cuda.current_stream(dev).cuda_stream
         n_err = len(self.measurement_error)
+        n_streams = max(1, int(getattr(self, "n_streams", 1)))
+        cur = torch.cuda.current_stream(dev)
+        if n_streams > 1:
+            # chunks alternate between streams (each with its own workspace) so that the solver kernel of one chunk and the
+            # filter kernel of another share the SMs; GECON_CR_CTAS_PER_SM / GECON_KF_CTAS_PER_SM size their grids for that
+            pool = self.__dict__.setdefault("_streams", {})
+            streams = pool.setdefault(dev, [torch.cuda.Stream(dev) for _ in range(n_streams)])
+            start = torch.cuda.Event()
+            start.record(cur)
+            for s_ in streams:
+                s_.wait_event(start)
+        else:
+            streams = [cur]
 
         def mark(name):
             """bench.py hook: CUDA events on the launching stream around each kernel (per-kernel roofline)."""
@@ -279,9 +351,13 @@ class BatchedStateSpace:
             events.append((name, e0, e1))
             return e1
 
-        for lo in range(0, N, nc):
+        for ci, lo in enumerate(range(0, N, nc)):
             cnt = min(nc, N - lo)
             th = theta_full[lo : lo + cnt]
+            slot = ci % len(streams)
+            ws = self._workspace(dev, nc, slot)
+            torch.cuda.set_stream(streams[slot])
+            stream = streams[slot].cuda_stream
             # split the parameter vector (strided device copies; no arithmetic)
             ws["theta"][:cnt].copy_(th[:, : m.n_theta])
             ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
@@ -294,6 +370,12 @@ class BatchedStateSpace:
             if self.ss_obs_intercept:  # d = log x_ss / x_ss of the listed observed states (x aggregation period for "sum")
                 xs = ws["xss"][:cnt].index_select(1, ws["d_var"])
                 ws["d"][:cnt].index_copy_(1, ws["d_pos"], torch.where(ws["d_loglin"], xs.log(), xs) * ws["d_scale"])
+            if self._obs_lib is not None:
+                rc = self._obs_lib.gecon_obs_batched(ws["theta"].data_ptr(), cnt, ws["Z"].data_ptr(), self.p * self.n_aug,
+                                                     ws["d"].data_ptr(), self.p, C.c_void_p(stream))  # fmt: skip
+                m.launches += 1
+                if rc != 0:
+                    raise L.GeconLibraryError(f"gecon_obs_batched failed with CUDA error {rc}")
             cr = L.CrArgs(
                 struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
                 D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
@@ -319,9 +401,10 @@ class BatchedStateSpace:
             kf = L.KalmanArgs(
                 struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), qdiag=ws["sig"].data_ptr(),
                 q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
-                Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None), z_stride=0,
+                Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None),
+                z_stride=(self.p * self.n_aug if self._obs_lib is not None else 0),
                 obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
-                d=(ws["d"].data_ptr() if self.ss_obs_intercept else None), d_stride=(self.p if self.ss_obs_intercept else 0),
+                d=(ws["d"].data_ptr() if "d" in ws else None), d_stride=(self.p if "d" in ws else 0),
                 Y=Y.data_ptr(), P0=None, N=cnt, n=self.n_aug, k=m.k, p=self.p,
                 Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
                 mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
@@ -333,6 +416,12 @@ class BatchedStateSpace:
             e and e.record()
             if out_n_iter is not None:
                 out_n_iter[lo : lo + cnt].copy_(ws["n_iter"][:cnt])
+        torch.cuda.set_stream(cur)
+        if n_streams > 1:
+            for s_ in streams:
+                done = torch.cuda.Event()
+                done.record(s_)
+                cur.wait_event(done)
         return ll, status
 
     # ------------------------------------------------------------------------------------------------ gradient
@@ -346,6 +435,8 @@ class BatchedStateSpace:
             raise RuntimeError("call configure(...) first")
         if not (torch is not None and isinstance(theta_full, torch.Tensor) and theta_full.is_cuda):
             raise TypeError("loglik_and_grad_device needs CUDA tensors; use loglik_and_grad() for host arrays")
+        if self._obs_lib is not None:
+            raise NotImplementedError("gradients through parameter-dependent observation equations are not implemented")
         m = self.model
         lib = L.load_library()
         dev = theta_full.device

@@ -254,23 +254,119 @@ def obs_intercept(x_ss, var_names, observed, ss_obs_intercept, log_linearized, t
     return d
 
 
+def observation_equation_terms(expr_str, var_names, x_ss, params, log_linearized):
+    """Linearisation of a GCN-syntax observation equation (gEconpy/model/statespace.py:446-507) WITHOUT symbolic
+    differentiation: every reference v[-k] is replaced by v_ss exp(v~) (log-linearised) or v_ss + v~, the intercept is
+    the value at v~ = 0 and each coefficient is d/dv~ there, taken by a complex step (exact to rounding).  Independent of
+    the product's sympy path on purpose.  Returns (intercept, {(variable, lag): coefficient})."""
+    import re
+
+    refs = {}
+
+    def ref(m):
+        v, idx = m.group(1), m.group(2).replace(" ", "")
+        if idx == "ss":
+            return f"_ss[{v!r}]"
+        lag = 0 if idx == "" else int(idx)
+        if lag > 0:
+            raise ValueError(f"lead reference {v}[{idx}] in an observation equation")
+        refs[(v, lag)] = True
+        return f"_x[({v!r}, {lag})]"
+
+    code = re.sub(r"([A-Za-z_][A-Za-z_0-9]*)\[([^\]]*)\]", ref, expr_str).replace("^", "**")
+    ss = {v: float(x_ss[var_names.index(v)]) for v in var_names}
+    env = {"log": np.log, "exp": np.exp, "sqrt": np.sqrt, "_ss": ss, **{k: float(v) for k, v in params.items()}}
+
+    def g(tildes):
+        x = {}
+        for (v, lag) in refs:
+            t = tildes.get((v, lag), 0.0)
+            x[(v, lag)] = ss[v] * np.exp(t) if v in log_linearized else ss[v] + t
+        return eval(code, {"__builtins__": {}}, {**env, "_x": x})  # noqa: S307 - test infrastructure, fixed expressions
+
+    intercept = float(np.real(g({})))
+    h = 1e-30
+    coeffs = {key: float(np.imag(g({key: 1j * h})) / h) for key in refs}
+    return intercept, coeffs
+
+
+def obs_lag_layout(coeff_keys, temporal_aggregation, aggregation_period, k_prev):
+    """``_obs_lag_depths`` and ``_obs_lag_starts`` (gEconpy/model/statespace.py:1040-1076)."""
+    ta = temporal_aggregation or {}
+    depths = {}
+    for obs_name, keys in coeff_keys.items():
+        broadcast = aggregation_period - 1 if ta.get(obs_name) in CUMULATOR_AGGREGATIONS else 0
+        for v, lag in keys:
+            need = -lag + broadcast
+            if need > 0:
+                depths[v] = max(depths.get(v, 0), need)
+    starts, off = {}, k_prev
+    for v, dep in depths.items():
+        starts[v] = off
+        off += dep
+    return depths, starts
+
+
+def append_obs_lag_block(T_aug, var_names, depths, starts):
+    """gEconpy/model/statespace.py:652-694: shift-companion chains for the variables an observation equation lags."""
+    n_lag = sum(depths.values())
+    if n_lag == 0:
+        return T_aug
+    k_prev = T_aug.shape[0]
+    F, Cc = np.zeros((n_lag, k_prev)), np.zeros((n_lag, n_lag))
+    for v, dep in depths.items():
+        b0 = starts[v] - k_prev
+        F[b0, var_names.index(v)] = 1.0
+        for j in range(1, dep):
+            Cc[b0 + j, b0 + j - 1] = 1.0
+    return np.block([[T_aug, np.zeros((k_prev, n_lag))], [F, Cc]])
+
+
 def loglik_augmented(
     model, theta, Y, observed, sigma_shock, sigma_err=None, temporal_aggregation=None, aggregation_period=4,
     ss_obs_intercept=None, log_linearized=None, tol=1e-8, max_iter=1000, solver_tol=1e-8, jitter=JITTER_DEFAULT,
-    mvn_const="per_obs",
+    mvn_const="per_obs", observation_equations=None,
 ):  # fmt: skip
     """theta -> logp with temporal aggregation and steady-state intercepts: make_symbolic_graph's sequence
     (gEconpy/model/statespace.py:769-820) -- solve, un-permute, augment T and R, build Z and d, P0 of the AUGMENTED
     system, filter, gate."""
-    base = loglik(model, theta, np.zeros((1, len(observed))), observed, sigma_shock, None, tol=tol, max_iter=max_iter, solver_tol=solver_tol)
-    T, R = base["T"], base["R"]
     names = model.var_names
+    eqs = dict(observation_equations or {})
+    model_observed = [v for v in observed if v not in eqs]
+    base = loglik(model, theta, np.zeros((1, max(1, len(model_observed)))), model_observed or [names[0]], sigma_shock, None, tol=tol,
+                  max_iter=max_iter, solver_tol=solver_tol)
+    T, R = base["T"], base["R"]
     ta = temporal_aggregation or {}
-    T_aug = augment_transition(T, names, ta, aggregation_period)
-    R_aug = augment_selection(R, T_aug.shape[0] - T.shape[0])
-    Z = design_matrix(names, observed, ta, aggregation_period)
     loglin = set(names) if log_linearized is None else set(log_linearized)
-    d = obs_intercept(model.steady_state(theta), names, observed, ss_obs_intercept, loglin, ta, aggregation_period)
+    x_ss = model.steady_state(theta)
+    ta_model = {k: v for k, v in ta.items() if k not in eqs}  # aggregated equations live in the lag block (statespace.py:562-571)
+    T_aug = augment_transition(T, names, ta_model, aggregation_period)
+    params = dict(zip(model.param_names, np.asarray(theta, dtype=np.float64)))
+    params.update(dict(zip(model.spec.get("deterministic_params", {}), model._det_values(theta))))
+    terms = {k: observation_equation_terms(e, names, x_ss, params, loglin) for k, e in eqs.items()}
+    depths, starts = obs_lag_layout({k: t[1].keys() for k, t in terms.items()}, ta, aggregation_period, T_aug.shape[0])
+    T_aug = append_obs_lag_block(T_aug, names, depths, starts)
+    R_aug = augment_selection(R, T_aug.shape[0] - T.shape[0])
+    Zm = design_matrix(names, model_observed, ta_model, aggregation_period)
+    Z = np.zeros((len(observed), T_aug.shape[0]))
+    d = np.zeros(len(observed))
+    dm = obs_intercept(x_ss, names, model_observed, ss_obs_intercept, loglin, ta_model, aggregation_period)
+    for i, name in enumerate(observed):
+        if name not in eqs:
+            j = model_observed.index(name)
+            Z[i, : Zm.shape[1]] = Zm[j]
+            d[i] = dm[j]
+            continue
+        icpt, coeffs = terms[name]
+        agg = ta.get(name)
+        n_per = aggregation_period if agg in CUMULATOR_AGGREGATIONS else 1
+        w = 1.0 / n_per if agg == "mean" else 1.0
+        for (v, lag), c in coeffs.items():  # statespace.py:308-322
+            for dd in range(n_per):
+                eff = lag - dd
+                col = names.index(v) if eff == 0 else starts[v] + (-eff - 1)
+                Z[i, col] += w * c
+        d[i] = aggregation_period * icpt if agg == "sum" else icpt
     Q = np.diag(np.asarray(sigma_shock, dtype=np.float64) ** 2)
     p = len(observed)
     H = np.zeros((p, p)) if sigma_err is None else np.diag(np.asarray(sigma_err, dtype=np.float64) ** 2)

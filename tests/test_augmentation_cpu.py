@@ -91,3 +91,71 @@ def test_prepare_mixed_frequency_data_matches_the_reference(g):
 def test_oracle_intercept_and_sum_rule():
     d = oss.obs_intercept(np.array([2.0, 3.0, 4.0]), ["a", "b", "c"], ["c", "a", "b"], ["a", "c"], {"a"}, {"c": "sum", "a": "mean"}, 4)
     assert np.allclose(d, [16.0, np.log(2.0), 0.0])
+
+
+# ------------------------------------------------------------------------------------------------ observation equations
+OBS_EQS = {"Yobs": "log(Y[])", "dC": "alpha * (log(C[]) - log(C[-1])) + beta", "mix": "Y[] / C[-2] + K[ss] * A[-1] ^ 2"}
+
+
+def test_observation_equation_linearisation_matches_the_complex_step_oracle(tmp_path):
+    """codegen's sympy linearisation + generated kernel text (compiled with g++ -DGECON_HOST_CHECK) against the oracle,
+    which differentiates numerically by a complex step: intercepts, coefficients, lag layout, aggregation broadcast."""
+    import ctypes as C
+    import subprocess
+
+    from helpers import draws, model
+
+    from geconpy_b200.model.codegen import LinearizedModel, load_spec
+
+    root = Path(__file__).resolve().parent.parent
+    lin = LinearizedModel(load_spec(root / "geconpy_b200" / "model" / "specs" / "rbc.json"))
+    mod = model("rbc")
+    observed, ta, period = ["Yobs", "dC", "mix"], {"dC": "sum", "mix": "mean"}, 3
+    lin_terms = {k: lin.linearize_observation_equation(*lin.parse_observation_equation(k, e)) for k, e in OBS_EQS.items()}
+    depths = StateAugmentation.required_obs_lag_depths({k: t[1].keys() for k, t in lin_terms.items()}, ta, period)
+    aug = StateAugmentation(list(mod.var_names), observed, ta, period, obs_equation_names=tuple(OBS_EQS), obs_lag_depths=depths)
+    assert aug._cumulator_variables == [] and aug._n_obs_lag_states == sum(depths.values())
+    # deepest effective lag: C at lag 2 + (3 - 1) aggregation headroom, Y at lag 0 + 2, A at lag 1 + 2 (statespace.py:1040-1053)
+    assert depths == {"C": 4, "Y": 2, "A": 3}
+    assert aug._obs_lag_state_names[:4] == ["C_obs_lag1", "C_obs_lag2", "C_obs_lag3", "C_obs_lag4"]
+    ns, p = aug.k_states, len(observed)
+    z_cells, d_cells = {}, {}
+    for i, name in enumerate(observed):
+        icpt, coeffs = lin_terms[name]
+        for col, terms in aug.design_cells(name, coeffs).items():
+            z_cells[i * ns + col] = sum(w * coeffs[key] for w, key in terms)
+        d_cells[i] = icpt * (period if ta.get(name) == "sum" else 1)
+    src = tmp_path / "obs.cpp"
+    src.write_text(lin.obs_source(z_cells, d_cells, "test"))
+    so = tmp_path / "obs.so"
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-DGECON_HOST_CHECK", "-o", str(so), str(src)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    lib.gecon_obs_host_check.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    th = draws(mod, 4, seed=7, width=0.05, valid=True)
+    N = len(th)
+    Z, d = np.zeros((N, p, ns)), np.zeros((N, p))
+    lib.gecon_obs_host_check(th.ctypes.data, N, Z.ctypes.data, p * ns, d.ctypes.data, p)
+    rng = np.random.default_rng(0)
+    Y = rng.standard_normal((6, p))
+    for i in range(N):
+        ref = oss.loglik_augmented(mod, th[i], Y, observed, [0.01], [0.01] * p, temporal_aggregation=ta, aggregation_period=period,
+                                   observation_equations=OBS_EQS)  # fmt: skip
+        assert ref["T_aug"].shape == (ns, ns)
+        assert np.array_equal(ref["T_aug"][mod.n :], aug.transition_rows())
+        np.testing.assert_allclose(Z[i], ref["Z"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(d[i], ref["d"], rtol=1e-12, atol=1e-14)
+
+
+def test_observation_equation_errors_follow_the_reference():
+    from geconpy_b200.model.codegen import LinearizedModel, load_spec
+
+    root = Path(__file__).resolve().parent.parent
+    lin = LinearizedModel(load_spec(root / "geconpy_b200" / "model" / "specs" / "rbc.json"))
+    with pytest.raises(ValueError, match="lead reference"):
+        lin.parse_observation_equation("x", "log(Y[1])")
+    with pytest.raises(ValueError, match="unknown model variable"):
+        lin.parse_observation_equation("x", "log(Q[])")
+    with pytest.raises(ValueError):
+        lin.parse_observation_equation("x", "not_a_parameter * Y[]")
+    icpt, coeffs = lin.linearize_observation_equation(*lin.parse_observation_equation("x", "log(Y[]) - log(Y[-1])"))
+    assert icpt == 0 and coeffs == {("Y", 0): 1, ("Y", -1): -1}

@@ -169,3 +169,66 @@ def test_per_draw_design_matrix(B, n, k, p):
         assert st[i] == 0 and abs(ll[i] - ref) <= TOL_LL, (i, ll[i], ref)
         ref0 = oss.kalman_loglik(Y, T[i], R[i], np.diag(q[i]), Z[0], np.diag(h[i]), d=d[i])
         assert abs(ll_shared[i] - ref0) <= TOL_LL
+
+
+# ------------------------------------------------------------------------------------------------ observation equations
+def _obs_eq_ss(name, observed, meas, reduce_state=True, **kw):
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    return BatchedStateSpace(CompiledModel(name)).configure(
+        observed_states=observed, measurement_error=meas, tol=1e-9, max_iter=200, reduce_state=reduce_state, chunk=16, **kw
+    )
+
+
+def test_observation_equation_equals_the_model_variable_formulation():
+    """The property the reference tests (test_statespace.py:583-630): observing ``log(Y[])`` through an observation
+    equation gives the likelihood of observing the log-linearised Y with a steady-state intercept."""
+    mod = model("rbc")
+    N = 12
+    th = draws(mod, N, seed=13, width=0.002, valid=True)
+    Y = _aggregated_data(mod, ["Y"], {}, 1, ["Y"], 40, seed=4, dense=True)
+    full = np.hstack([th, np.full((N, mod.k), SIGMA_SHOCK), np.full((N, 1), SIGMA_ERR)])
+    ll_eq, st_eq = _obs_eq_ss("rbc", ["Y_obs"], ["Y_obs"], observation_equations={"Y_obs": "log(Y[])"}).loglik(full, Y)
+    ll_var, st_var = _obs_eq_ss("rbc", ["Y"], ["Y"], ss_obs_intercept=["Y"]).loglik(full, Y)
+    assert (st_eq == 0).all() and (st_var == 0).all()
+    assert np.abs(ll_eq - ll_var).max() <= TOL_LL
+
+
+OBS_CASES = [
+    ("rbc", ["dY", "C"], {"dY": "log(Y[]) - log(Y[-1])"}, {}, 4),
+    ("rbc", ["C", "mix"], {"mix": "alpha * log(Y[]) + (1 - alpha) * log(K[-2]) - log(A[ss])"}, {}, 4),
+    ("rbc", ["dY", "C"], {"dY": "log(Y[]) - log(Y[-1])"}, {"dY": "sum", "C": "mean"}, 4),
+    ("full_nk", ["dY", "pi", "r_G"], {"dY": "100 * (log(Y[]) - log(Y[-1]))"}, {"dY": "mean"}, 2),
+]
+
+
+@pytest.mark.parametrize("name,observed,eqs,ta,period", OBS_CASES)
+@pytest.mark.parametrize("reduce_state", [True, False])
+def test_observation_equations_match_oracle(name, observed, eqs, ta, period, reduce_state):
+    mod = model(name)
+    ss = _obs_eq_ss(name, observed, observed, reduce_state, observation_equations=eqs, temporal_aggregation=ta, aggregation_period=period)
+    N, Tobs = 12, 36
+    th = draws(mod, N, seed=17, width=0.002, valid=True)  # intercepts depend on theta: keep ll O(1e2) for the absolute tolerance
+    rng = np.random.default_rng(5)
+    sig, err = np.full((N, mod.k), SIGMA_SHOCK), np.full((N, len(observed)), 5e-3)
+    # data: draw from the ORACLE's state space at the default parameters so that the likelihood is well scaled
+    ref0 = oss.loglik_augmented(mod, th[0], np.zeros((1, len(observed))), observed, sig[0], err[0], temporal_aggregation=ta,
+                                aggregation_period=period, observation_equations=eqs, tol=1e-9, max_iter=200)  # fmt: skip
+    Ta, Ra, Z, d = ref0["T_aug"], ref0["R_aug"], ref0["Z"], ref0["d"]
+    x = np.zeros(Ta.shape[0])
+    Y = np.zeros((Tobs, len(observed)))
+    for t in range(Tobs):
+        x = Ta @ x + Ra @ (SIGMA_SHOCK * rng.standard_normal(mod.k))
+        Y[t] = d + Z @ x + 5e-3 * rng.standard_normal(len(observed))
+    ll, st = ss.loglik(np.hstack([th, sig, err]), Y)
+    n_ok = 0
+    for i in range(N):
+        ref = oss.loglik_augmented(mod, th[i], Y, observed, sig[i], err[i], temporal_aggregation=ta, aggregation_period=period,
+                                   observation_equations=eqs, tol=1e-9, max_iter=200)  # fmt: skip
+        if ref["ok"] and np.isfinite(ref["ll"]):
+            n_ok += 1
+            assert st[i] == 0, (i, st[i])
+            assert abs(ll[i] - ref["ll"]) <= TOL_LL, (i, ll[i], ref["ll"])
+        else:
+            assert np.isneginf(ll[i]) and st[i] != 0
+    assert n_ok >= N // 2
