@@ -312,6 +312,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="draws timed on the CPU (default: sized for ~20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gradient", action="store_true", help="skip the gradient-path extra")
     ap.add_argument("--extra-workloads", action="store_true", help="also time the other workloads (kernel-only) at N=1")
     args = ap.parse_args()
 
@@ -452,6 +453,38 @@ def main():
     value = world * draws_per_gpu / (ms_per_step * 1e-3)
     e2e_value = world * draws_per_gpu / (e2e_ms / args.steps * 1e-3)
 
+    # ---- extras (reported beside the contract's numbers, never instead of them)
+    # (1) the same step with the chunks alternating between two CUDA streams, so that the drain of one chunk's kernels
+    #     overlaps the next chunk's; per-kernel event times are not meaningful under overlap, hence a separate pass
+    extras = {}
+    if draws_per_gpu > ss.chunk:
+        ss.n_streams = 2
+        for _ in range(2):
+            step_device()
+        ov_ms, _ = timed(step_device, args.steps)
+        ss.n_streams = 1
+        extras["two_stream_overlap"] = {"n_streams": 2, "value": world * draws_per_gpu / (ov_ms / args.steps * 1e-3), "unit": UNIT,
+                                        "ms_per_step": ov_ms / args.steps}
+    # (2) the gradient path: log-likelihood + d/d(theta, sigma) for a 32,768-draw slice
+    if ss.n_aug <= 48 and not args.no_gradient:
+        ng = min(draws_per_gpu, 32768)
+        for _ in range(2):
+            ss.loglik_and_grad_device(params_d[:ng], Y_d)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gev = []
+        g0.record()
+        _, gr, gst = ss.loglik_and_grad_device(params_d[:ng], Y_d, events=gev)
+        g1.record()
+        barrier()
+        gms = g0.elapsed_time(g1)
+        gk = {}
+        for nm, a, b in gev:
+            gk[nm] = gk.get(nm, 0.0) + a.elapsed_time(b)
+        extras["gradient"] = {"value": world * ng / (gms * 1e-3), "unit": "likelihood+gradient evals/s", "draws": int(ng), "ms": gms,
+                              "kernel_ms": gk, "n_param": int(gr.shape[1]), "finite": bool(torch.isfinite(gr).all().item()),
+                              "ok": int((gst == 0).sum().item())}
+
     # ---- per-kernel durations measured live (CUDA events on the launching stream), roofline of the dominant kernel
     kt = {}
     for ke in kern_events:
@@ -496,7 +529,7 @@ def main():
             "data": "synthetic", "config": config, "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params.nbytes),
                     "d2h_bytes_per_step": int(draws_per_gpu * (8 + 4)), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline,
+            "gpu_launches": int(launches), "roofline": roofline, "extras": extras,
             "draw_outcomes": {"ok": int(ok.sum()), "gated_minus_inf": int(((status & 0x400) != 0).sum()),
                               "bk_violated": int(((status & 0x10) != 0).sum()), "bk_inconclusive": int(((status & 0x20) != 0).sum()),
                               "cr_not_converged": int(((status & 0x1) != 0).sum()), "jacobian_nonfinite": int(((status & 0x200) != 0).sum()),
