@@ -286,6 +286,7 @@ def _random_statespace(rng, N, n, k, rho=0.9):
 
 
 @pytest.mark.parametrize("n,k,p", [(1, 1, 1), (3, 2, 1), (5, 3, 2), (7, 2, 4), (12, 4, 3), (15, 6, 5), (15, 16, 8), (20, 7, 7), (23, 9, 6), (23, 3, 8),
+                                    (9, 2, 1), (9, 4, 5), (10, 4, 3), (10, 3, 8), (11, 5, 2), (11, 2, 7),  # fringe variant of the warp kernel
                                     (24, 5, 2), (40, 8, 8), (60, 10, 7), (63, 4, 3)])
 def test_kalman_synthetic_sizes(B, rng, n, k, p):
     """Both filter kernels over their whole size range (one warp per draw up to n = 23, one CTA per draw above), every
