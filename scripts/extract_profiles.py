@@ -21,7 +21,7 @@ for f in src.glob(f"{tag}_bench_*.json"):
     lines = [l for l in f.read_text().splitlines() if l.startswith("{")]
     if lines:
         (dst / f.name).write_text(lines[-1] + "\n")
-for f in list(src.glob(f"{tag}_launches_nk.csv")) + list(src.glob(f"{tag}_*_lines.txt")):
+for f in list(src.glob(f"{tag}_launches_nk.csv")) + list(src.glob(f"{tag}_*_lines.txt")) + list(src.glob(f"{tag}_gradient_timing.json")):
     shutil.copy(f, dst / f.name)
 raw, traffic = {}, {"source": "ncu --set full --clock-control none, bench.py --draws 65536 (one chunk = one launch), medium NK"}
 for k in ("cr_solve", "kalman"):
