@@ -92,6 +92,8 @@ __device__ __forceinline__ void gemm_acc(Acc<NP>& acc, const double* __restrict_
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 // ------------------------------------------------------------------------------------------------ tile helpers
 template <int NP>
 __device__ __forceinline__ void tile_zero(double* __restrict__ dst) {

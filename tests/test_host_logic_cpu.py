@@ -177,3 +177,37 @@ def test_draw_sharding_and_allgather_world_size_2():
     )  # fmt: skip
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "gloo sharding ok" in r.stdout
+
+
+def test_gradient_entry_points_reject_bad_arguments_and_accept_empty_batches():
+    """Argument checks of gecon_kalman_grad_* / gecon_policy_adjoint_* run before anything touches a device."""
+    from geconpy_b200 import _lib
+
+    lib = _lib.load_library()
+    kg = _lib.KalmanGradArgs(struct_size=1)
+    assert lib.gecon_kalman_grad_batched(C.byref(kg), None) == -1 and b"struct_size" in lib.gecon_get_last_error()
+    ptr = dict(T=1, R=1, qdiag=1, Y=1, ll=1, status=1, T_bar=1, R_bar=1, q_bar=1, obs_idx=1)
+    big = _lib.KalmanGradArgs(struct_size=C.sizeof(_lib.KalmanGradArgs), N=1, n=49, k=1, p=1, Tobs=1, **ptr)
+    assert lib.gecon_kalman_grad_batched(C.byref(big), None) == -2  # n > 48 unsupported on the gradient path
+    nosel = _lib.KalmanGradArgs(struct_size=C.sizeof(_lib.KalmanGradArgs), N=1, n=4, k=1, p=1, Tobs=1, **{**ptr, "obs_idx": None})
+    assert lib.gecon_kalman_grad_batched(C.byref(nosel), None) == -1  # neither Z nor obs_idx
+    empty = _lib.KalmanGradArgs(struct_size=C.sizeof(_lib.KalmanGradArgs), N=0, n=4, k=1, p=1, Tobs=1, **ptr)
+    assert lib.gecon_kalman_grad_batched(C.byref(empty), None) == 0
+    pa = _lib.PolicyAdjointArgs(struct_size=C.sizeof(_lib.PolicyAdjointArgs), B=1, C=1, T=1, T_bar=1, A_bar=1, B_bar=1, C_bar=1, N=0, n=4, k=0)
+    assert lib.gecon_policy_adjoint_batched(C.byref(pa), None) == 0
+    pa.n, pa.N = 65, 1
+    assert lib.gecon_policy_adjoint_batched(C.byref(pa), None) == -2
+    pa.n, pa.T_bar = 4, None
+    assert lib.gecon_policy_adjoint_batched(C.byref(pa), None) == -1
+
+
+def test_strided_solver_outputs_are_validated():
+    from geconpy_b200 import _lib
+
+    lib = _lib.load_library()
+    a = _lib.CrArgs(struct_size=C.sizeof(_lib.CrArgs), A=1, B=1, T=1, status=1, N=1, n=8, k=0, t_ld=4)
+    assert lib.gecon_cr_solve_batched(C.byref(a), None) == -1 and b"t_ld" in lib.gecon_get_last_error()
+    a.t_ld, a.t_stride = 12, 12 * 12
+    assert lib.gecon_cr_solve_host(C.byref(a)) == -1  # strided outputs are a device-entry-point feature
+    kf = _lib.KalmanArgs(struct_size=C.sizeof(_lib.KalmanArgs), T=1, R=1, qdiag=1, Y=1, ll=1, status=1, Z=1, N=1, n=4, k=1, p=2, Tobs=1, z_stride=5)
+    assert lib.gecon_kalman_ll_batched(C.byref(kf), None) == -1 and b"z_stride" in lib.gecon_get_last_error()
