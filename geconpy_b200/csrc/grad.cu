@@ -30,8 +30,9 @@ static int grad_threads(int n) {
         const int v = atoi(e);
         if (v >= 32 && v <= 1024 && v % 32 == 0) return v;
     }
-    // measured on B200 (medium NK, filter dimension 10 / solver dimension 24): 64 and 128 threads are within 5 %, 256 is 1.6x slower
-    return n <= 12 ? 64 : (n <= 32 ? 128 : 256);
+    // measured on B200 (medium NK: filter dimension 10, solver dimension 24) with the register-blocked products: one warp per
+    // draw is best up to n = 12 (128 / 165 / 233 ms for 32 / 64 / 128 threads), 64-128 threads at n = 24, 256 is 1.6x slower
+    return n <= 12 ? 32 : (n <= 32 ? 128 : 256);
 }
 
 static int check_kg(const gecon_kalman_grad_args* a) {
