@@ -104,21 +104,21 @@ GHD double absmax(const double* X, int ldx, int m, int n, double* s_red) {
 
 // In-place inverse of the SPD p x p matrix F (row-major, ld = PMAXG) by Gauss-Jordan without pivoting, executed by one
 // thread; returns log det F through *logdet and false if a pivot is not positive.
-GHD bool spd_inverse_small(double* F, int p, double* logdet) {
+GHD bool spd_inverse_small(double* F, int p, int ps, double* logdet) {
     double det = 1.0;  // p <= 8 pivots of an innovation covariance: their product does not leave the double range
     bool ok = true;
     for (int c = 0; c < p; ++c) {
-        const double piv = F[c * PMAXG + c];
+        const double piv = F[c * ps + c];
         ok = ok && (piv > 0.0);
         det *= piv;
         const double inv = 1.0 / piv;
-        for (int j = 0; j < p; ++j) F[c * PMAXG + j] *= inv;
-        F[c * PMAXG + c] = inv;
+        for (int j = 0; j < p; ++j) F[c * ps + j] *= inv;
+        F[c * ps + c] = inv;
         for (int i = 0; i < p; ++i) {
             if (i == c) continue;
-            const double f = F[i * PMAXG + c];
-            F[i * PMAXG + c] = 0.0;
-            for (int j = 0; j < p; ++j) F[i * PMAXG + j] = fma(-f, F[c * PMAXG + j], F[i * PMAXG + j]);
+            const double f = F[i * ps + c];
+            F[i * ps + c] = 0.0;
+            for (int j = 0; j < p; ++j) F[i * ps + j] = fma(-f, F[c * ps + j], F[i * ps + j]);
         }
     }
     if (logdet) *logdet = log(det);  // one log per step; the reverse sweep's recomputation does not need it at all
@@ -157,8 +157,8 @@ struct KalmanGradArgs {
 // doubles of shared memory needed by kalman_grad_draw
 GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
     const int ld = ldim(n);
-    return (size_t)9 * n * ld + (size_t)5 * n * PMAXG + (size_t)p * n + 6 * (size_t)n + 4 * PMAXG * PMAXG + 12 * PMAXG + (size_t)n * (k > 0 ? k : 1) + k +
-           nt + 8;
+    return (size_t)9 * n * ld + (size_t)5 * n * p + (size_t)p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
+           k + nt + 8;
 }
 
 // One draw.  sm: shared memory (kalman_grad_smem_doubles), cta: index of this CTA's workspace slot.
@@ -174,33 +174,31 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     double* Pfb = Pb + tile;  // adjoint of the filtered covariance
     double* W1 = Pfb + tile;
     double* W2 = W1 + tile;
-    double* PZ = W2 + tile;       // [n][PMAXG]
-    double* K = PZ + n * PMAXG;   // [n][PMAXG]
-    double* Kb = K + n * PMAXG;   // [n][PMAXG]
-    double* PZb = Kb + n * PMAXG;  // [n][PMAXG]
-    double* PK = PZb + n * PMAXG;  // [n][PMAXG]
-    double* Zs = PK + n * PMAXG;  // [p][n]
+    const int ps = p;             // row stride of the n x p panels and of the p x p matrices
+    double* PZ = W2 + tile;       // [n][p]
+    double* K = PZ + n * ps;
+    double* Kb = K + n * ps;
+    double* PZb = Kb + n * ps;
+    double* PK = PZb + n * ps;
+    double* Zs = PK + n * ps;     // [p][n]
     double* a = Zs + p * n;
     double* af = a + n;
     double* ab = af + n;
     double* afb = ab + n;
     double* an = afb + n;
-    double* tmpn = an + n;
-    double* F = tmpn + n;             // [PMAXG][PMAXG]  F, then F^-1
-    double* Fb = F + PMAXG * PMAXG;   // adjoint of F
-    double* Gm = Fb + PMAXG * PMAXG;  // scratch
-    double* Gm2 = Gm + PMAXG * PMAXG;
-    double* v = Gm2 + PMAXG * PMAXG;
-    double* e = v + PMAXG;
-    double* vb = e + PMAXG;
-    double* w = vb + PMAXG;
-    double* ym = w + PMAXG;
-    double* hv = ym + PMAXG;
-    double* dv = hv + PMAXG;
-    double* hb = dv + PMAXG;
-    double* db = hb + PMAXG;
-    double* sc = db + PMAXG;  // [0] logdet, [1] ok flag, [2] ll, [3] all-missing flag
-    double* Rs = sc + 3 * PMAXG;  // [n][k]
+    double* F = an + n;           // [p][p]  F, then F^-1
+    double* Fb = F + p * p;       // adjoint of F
+    double* v = Fb + p * p;
+    double* e = v + p;
+    double* vb = e + p;
+    double* w = vb + p;
+    double* ym = w + p;
+    double* hv = ym + p;
+    double* dv = hv + p;
+    double* hb = dv + p;
+    double* db = hb + p;
+    double* sc = db + p;  // [0] logdet, [1] ok flag, [2] ll, [3] all-missing flag
+    double* Rs = sc + 4;  // [n][k]
     double* qs = Rs + n * (k > 0 ? k : 1);
     double* s_red = qs + k;
 
@@ -309,7 +307,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             const int i = idx / p, c = idx - i * p;
             double s = 0.0;
             for (int j = 0; j < n; ++j) s = fma(P[i * ld + j], Zs[c * n + j], s);
-            PZ[i * PMAXG + c] = w[c] * s;
+            PZ[i * ps + c] = w[c] * s;
         }
         GFOR(c, p) {
             double s = 0.0;
@@ -320,21 +318,21 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         GFOR(idx, p * p) {
             const int c = idx / p, b = idx - c * p;
             double s = 0.0;
-            for (int j = 0; j < n; ++j) s = fma(Zs[c * n + j], PZ[j * PMAXG + b], s);
+            for (int j = 0; j < n; ++j) s = fma(Zs[c * n + j], PZ[j * ps + b], s);
             s *= w[c];
             if (c == b) s += w[c] * hv[c] + jit;
-            F[c * PMAXG + b] = s;
+            F[c * ps + b] = s;
         }
         GSYNC();
         if (G_TID == 0) {
             // symmetrise (the two triangles differ by rounding), invert
             for (int c = 0; c < p; ++c)
                 for (int b = 0; b < c; ++b) {
-                    const double s = 0.5 * (F[c * PMAXG + b] + F[b * PMAXG + c]);
-                    F[c * PMAXG + b] = F[b * PMAXG + c] = s;
+                    const double s = 0.5 * (F[c * ps + b] + F[b * ps + c]);
+                    F[c * ps + b] = F[b * ps + c] = s;
                 }
             double logdet = 0.0;
-            const bool ok = spd_inverse_small(F, p, accumulate_ll ? &logdet : nullptr);
+            const bool ok = spd_inverse_small(F, p, ps, accumulate_ll ? &logdet : nullptr);
             if (!ok) sc[1] = 0.0;
             sc[0] = logdet;
             double allmiss = 1.0;
@@ -346,24 +344,24 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         GFOR(idx, n * p) {
             const int i = idx / p, c = idx - i * p;
             double s = 0.0;
-            for (int b = 0; b < p; ++b) s = fma(PZ[i * PMAXG + b], F[b * PMAXG + c], s);
-            K[i * PMAXG + c] = s;
+            for (int b = 0; b < p; ++b) s = fma(PZ[i * ps + b], F[b * ps + c], s);
+            K[i * ps + c] = s;
         }
         GFOR(c, p) {
             double s = 0.0;
-            for (int b = 0; b < p; ++b) s = fma(F[c * PMAXG + b], v[b], s);
+            for (int b = 0; b < p; ++b) s = fma(F[c * ps + b], v[b], s);
             e[c] = s;
         }
         GSYNC();
         GFOR(i, n) {
             double s = a[i];
-            for (int c = 0; c < p; ++c) s = fma(K[i * PMAXG + c], v[c], s);
+            for (int c = 0; c < p; ++c) s = fma(K[i * ps + c], v[c], s);
             af[i] = s;
         }
         GFOR(idx, n * n) {
             const int i = idx / n, j = idx - i * n;
             double s = (i == j) ? 1.0 : 0.0;
-            for (int c = 0; c < p; ++c) s = fma(-K[i * PMAXG + c] * w[c], Zs[c * n + j], s);
+            for (int c = 0; c < p; ++c) s = fma(-K[i * ps + c] * w[c], Zs[c * n + j], s);
             L[i * ld + j] = s;
         }
         if (accumulate_ll && G_TID == 0 && sc[3] == 0.0) {
@@ -378,7 +376,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         gemm4(n, n, n, [&](int i, int k_) { return W1[i * ld + k_]; }, [&](int k_, int j) { return L[j * ld + k_]; },
               [&](int i, int j, double v_) {
                   double s = v_ + ((i == j) ? jit : 0.0);
-                  for (int c = 0; c < p; ++c) s = fma(K[i * PMAXG + c] * (w[c] * hv[c]), K[j * PMAXG + c], s);
+                  for (int c = 0; c < p; ++c) s = fma(K[i * ps + c] * (w[c] * hv[c]), K[j * ps + c], s);
                   Pf[i * ld + j] = s;
               });
         GSYNC();
@@ -439,7 +437,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         // log-likelihood term
         GFOR(idx, p * p) {
             const int c = idx / p, b = idx - c * p;
-            Fb[c * PMAXG + b] = (sc[3] == 0.0) ? -0.5 * (F[c * PMAXG + b] - e[c] * e[b]) : 0.0;
+            Fb[c * ps + b] = (sc[3] == 0.0) ? -0.5 * (F[c * ps + b] - e[c] * e[b]) : 0.0;
         }
         GFOR(c, p) vb[c] = (sc[3] == 0.0) ? -e[c] : 0.0;
         GSYNC();
@@ -448,57 +446,57 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
               [&](int i, int j, double v_) { W2[i * ld + j] = v_; });  // L_bar -> W2
         gemm4(n, n, n, [&](int i, int k_) { return Pfb[i * ld + k_]; }, [&](int k_, int j) { return L[k_ * ld + j]; },
               [&](int i, int j, double v_) { Pf[i * ld + j] = v_; });  // Pf tile now holds Pfb L
-        gemm4(n, p, n, [&](int i, int k_) { return Pfb[i * ld + k_]; }, [&](int k_, int c) { return K[k_ * PMAXG + c]; },
-              [&](int i, int c, double v_) { PK[i * PMAXG + c] = v_; });  // PK = Pfb K
+        gemm4(n, p, n, [&](int i, int k_) { return Pfb[i * ld + k_]; }, [&](int k_, int c) { return K[k_ * ps + c]; },
+              [&](int i, int c, double v_) { PK[i * ps + c] = v_; });  // PK = Pfb K
         GSYNC();
         GFOR(idx, n * p) {  // K_bar
             const int i = idx / p, c = idx - i * p;
             double s = afb[i] * v[c];
             double s1 = 0.0, s2 = 0.0;
             for (int kk = 0; kk < n; ++kk) {
-                s1 = fma(Pfb[i * ld + kk] + Pfb[kk * ld + i], K[kk * PMAXG + c], s1);
+                s1 = fma(Pfb[i * ld + kk] + Pfb[kk * ld + i], K[kk * ps + c], s1);
                 s2 = fma(W2[i * ld + kk], Zs[c * n + kk], s2);
             }
-            Kb[i * PMAXG + c] = s + s1 * (w[c] * hv[c]) - s2 * w[c];
+            Kb[i * ps + c] = s + s1 * (w[c] * hv[c]) - s2 * w[c];
         }
         GFOR(c, p) {
             double s = 0.0;
-            for (int i = 0; i < n; ++i) s = fma(K[i * PMAXG + c], PK[i * PMAXG + c], s);
+            for (int i = 0; i < n; ++i) s = fma(K[i * ps + c], PK[i * ps + c], s);
             hb[c] += w[c] * s;
             double u = vb[c];
-            for (int i = 0; i < n; ++i) u = fma(K[i * PMAXG + c], afb[i], u);
+            for (int i = 0; i < n; ++i) u = fma(K[i * ps + c], afb[i], u);
             vb[c] = u;
         }
         GSYNC();
         GFOR(idx, n * p) {  // PZ_bar = K_bar F^-1
             const int i = idx / p, c = idx - i * p;
             double s = 0.0;
-            for (int b = 0; b < p; ++b) s = fma(Kb[i * PMAXG + b], F[b * PMAXG + c], s);
-            PZb[i * PMAXG + c] = s;
+            for (int b = 0; b < p; ++b) s = fma(Kb[i * ps + b], F[b * ps + c], s);
+            PZb[i * ps + c] = s;
         }
         GSYNC();
         GFOR(idx, p * p) {  // F_bar -= K' PZ_bar
             const int c = idx / p, b = idx - c * p;
             double s = 0.0;
-            for (int i = 0; i < n; ++i) s = fma(K[i * PMAXG + c], PZb[i * PMAXG + b], s);
-            Fb[c * PMAXG + b] -= s;
+            for (int i = 0; i < n; ++i) s = fma(K[i * ps + c], PZb[i * ps + b], s);
+            Fb[c * ps + b] -= s;
         }
         GSYNC();
         GFOR(idx, n * p) {  // PZ_bar += Zm' F_bar
             const int i = idx / p, b = idx - i * p;
-            double s = PZb[i * PMAXG + b];
-            for (int c = 0; c < p; ++c) s = fma(w[c] * Zs[c * n + i], Fb[c * PMAXG + b], s);
-            PZb[i * PMAXG + b] = s;
+            double s = PZb[i * ps + b];
+            for (int c = 0; c < p; ++c) s = fma(w[c] * Zs[c * n + i], Fb[c * ps + b], s);
+            PZb[i * ps + b] = s;
         }
         GFOR(c, p) {
-            hb[c] += w[c] * Fb[c * PMAXG + c];
+            hb[c] += w[c] * Fb[c * ps + c];
             db[c] -= vb[c];
         }
         GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return L[k_ * ld + i]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
               [&](int i, int j, double v_) {  // P_bar = L' (Pfb L) + PZ_bar Zm
                   double s = v_;
-                  for (int c = 0; c < p; ++c) s = fma(PZb[i * PMAXG + c] * w[c], Zs[c * n + j], s);
+                  for (int c = 0; c < p; ++c) s = fma(PZb[i * ps + c] * w[c], Zs[c * n + j], s);
                   Pb[i * ld + j] = s;
               });
         GFOR(j, n) {
