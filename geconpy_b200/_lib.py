@@ -190,6 +190,8 @@ class KalmanGradArgs(C.Structure):
         ("q_bar", C.c_void_p),
         ("h_bar", C.c_void_p),
         ("d_bar", C.c_void_p),
+        ("z_stride", C.c_int64),
+        ("Z_bar", C.c_void_p),
     ]
 
 

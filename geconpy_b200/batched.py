@@ -332,7 +332,8 @@ def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None,
                        mvn_const="per_obs", status_in=None, gate_mask=0, sigma_inputs=False, lyap_max_iter=0):
     """Log-likelihood AND its gradient (``gecon_kalman_grad_*``): returns a dict with ``ll`` [N],
     ``status`` [N], ``T`` [N,n,n], ``R`` [N,n,k], ``q`` [N,k], ``h`` [N,p], ``d`` [N,p] -- the derivatives of ll with
-    respect to the arguments of the same name (``q``/``h`` w.r.t. the standard deviations when ``sigma_inputs``).
+    respect to the arguments of the same name (``q``/``h`` w.r.t. the standard deviations when ``sigma_inputs``) -- and,
+    for a dense design matrix (shared ``(p, n)`` or one per draw ``(N, p, n)``), ``Z`` [N,p,n].
     What pytensor differentiates behind ``build_statespace_graph`` (gEconpy/model/statespace.py:812-820,1151-1157)."""
     if (Z is None) == (obs_idx is None):
         raise ValueError("give exactly one of Z (dense design matrix) and obs_idx (selector)")
@@ -347,11 +348,12 @@ def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None,
     q, pq = m.inp(qdiag)
     h, ph = m.inp(hdiag)
     dd, pd_ = m.inp(d)
-    _, pZ = m.inp(Z)
+    Za, pZ = m.inp(Z)
     _, pO = m.inp(None if obs_idx is None else np.ascontiguousarray(obs_idx, dtype=np.int32), np.int32)
     _, pSin = m.inp(status_in, np.int32)
     ll, pll = m.out((N,))
     st, pS = m.out((N,), np.int32)
+    Zb, pZb = m.out((N, p, n)) if Za is not None else (None, None)
     Tb, pTb = m.out((N, n, n))
     Rb, pRb = m.out((N, n, k))
     qb, pqb = m.out((N, k))
@@ -363,7 +365,7 @@ def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None,
         d_stride=(p if (dd is not None and dd.ndim == 2) else 0), Y=pY, N=N, n=n, k=k, p=p, Tobs=Tobs, jitter=float(jitter),
         missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1), lyap_max_iter=int(lyap_max_iter),
         status_in=pSin, gate_mask=int(gate_mask), sigma_inputs=int(bool(sigma_inputs)), ll=pll, status=pS, T_bar=pTb, R_bar=pRb,
-        q_bar=pqb, h_bar=phb, d_bar=pdb,
+        q_bar=pqb, h_bar=phb, d_bar=pdb, z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0), Z_bar=pZb,
     )  # fmt: skip
     lib = L.load_library()
     if m.device:
@@ -371,6 +373,8 @@ def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None,
     else:
         L.check(lib.gecon_kalman_grad_host(C.byref(args)), "gecon_kalman_grad_host")
     out = dict(ll=ll, status=st, T=Tb, R=Rb, q=qb, h=hb, d=db)
+    if Zb is not None:
+        out["Z"] = Zb
     if squeeze:
         out = {key: val[0] for key, val in out.items()}
     return out

@@ -45,6 +45,10 @@ static int check_kg(const gecon_kalman_grad_args* a) {
         set_last_error("gecon_kalman_grad_args: null pointer or bad dimension");
         return GECON_E_BADARG;
     }
+    if ((a->Z && a->z_stride && a->z_stride != (int64_t)a->p * a->n) || (a->Z_bar && !a->Z)) {
+        set_last_error("gecon_kalman_grad_args: z_stride must be 0 or p * n, and Z_bar needs a dense Z");
+        return GECON_E_BADARG;
+    }
     if (a->n > 48 || a->k > a->n || a->p > gecon_grad::PMAXG || a->p > a->n) {
         set_last_error("gecon_kalman_grad_args: unsupported size n = %d (max 48), k = %d (max n), p = %d (max %d)", a->n, a->k, a->p, gecon_grad::PMAXG);
         return GECON_E_UNSUPPORTED_SIZE;
@@ -131,13 +135,13 @@ extern "C" int gecon_kalman_grad_host(const gecon_kalman_grad_args* a) {
     if (rc) return rc;
     if (a->N == 0) return 0;
     const size_t N = (size_t)a->N, n = a->n, k = a->k, p = a->p, Tobs = a->Tobs;
-    DevBuf bT, bR, bq, bh, bZ, bo, bd, bY, bS, oll, ost, oT, oR, oq, oh, od;
+    DevBuf bT, bR, bq, bh, bZ, bo, bd, bY, bS, oll, ost, oT, oR, oq, oh, od, oZ;
     gecon_kalman_grad_args d = *a;
     G_H2D(bT, T, double, N * n * n)
     G_H2D(bR, R, double, N * n * k)
     G_H2D(bq, qdiag, double, (a->q_stride ? N * k : k))
     G_H2D(bh, hdiag, double, (a->h_stride ? N * p : p))
-    G_H2D(bZ, Z, double, p * n)
+    G_H2D(bZ, Z, double, (a->z_stride ? N * p * n : p * n))
     G_H2D(bo, obs_idx, int32_t, p)
     G_H2D(bd, d, double, (a->d_stride ? N * p : p))
     G_H2D(bY, Y, double, Tobs * p)
@@ -149,6 +153,7 @@ extern "C" int gecon_kalman_grad_host(const gecon_kalman_grad_args* a) {
     G_OUT(oq, q_bar, double, N * k)
     G_OUT(oh, h_bar, double, N * p)
     G_OUT(od, d_bar, double, N * p)
+    G_OUT(oZ, Z_bar, double, N * p * n)
     rc = gecon_kalman_grad_batched(&d, nullptr);
     if (rc) return rc;
     GECON_CUDA(cudaDeviceSynchronize());
@@ -159,6 +164,7 @@ extern "C" int gecon_kalman_grad_host(const gecon_kalman_grad_args* a) {
     G_D2H(q_bar, double, N * k)
     G_D2H(h_bar, double, N * p)
     G_D2H(d_bar, double, N * p)
+    G_D2H(Z_bar, double, N * p * n)
     return 0;
 }
 

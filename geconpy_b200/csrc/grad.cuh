@@ -132,7 +132,8 @@ struct KalmanGradArgs {
     long long q_stride;
     const double* hdiag;  // [N][p], [p] or NULL
     long long h_stride;
-    const double* Z;        // [p][n] shared, or NULL
+    const double* Z;        // [p][n] shared (z_stride = 0) or [N][p][n] (z_stride = p n), or NULL
+    long long z_stride;
     const int32_t* obs_idx;  // [p] or NULL
     const double* d;        // [N][p], [p] or NULL
     long long d_stride;
@@ -150,6 +151,7 @@ struct KalmanGradArgs {
     double* q_bar;    // [N][k]   (w.r.t. sigma when sigma_inputs)
     double* h_bar;    // [N][p]
     double* d_bar;    // [N][p]
+    double* Z_bar;    // [N][p][n] or NULL: dll/dZ (dense design matrices only)
     double* traj;     // workspace [n_cta][Tobs][n n + n]
     double* c0bar_ws;  // workspace [n_cta][n n]
 };
@@ -157,7 +159,7 @@ struct KalmanGradArgs {
 // doubles of shared memory needed by kalman_grad_draw
 GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
     const int ld = ldim(n);
-    return (size_t)9 * n * ld + (size_t)5 * n * p + (size_t)p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
+    return (size_t)9 * n * ld + (size_t)5 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
            k + nt + 8;
 }
 
@@ -181,7 +183,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     double* PZb = Kb + n * ps;
     double* PK = PZb + n * ps;
     double* Zs = PK + n * ps;     // [p][n]
-    double* a = Zs + p * n;
+    double* Zb = Zs + p * n;      // [p][n] adjoint of the design matrix
+    double* a = Zb + p * n;
     double* af = a + n;
     double* ab = af + n;
     double* afb = ab + n;
@@ -216,6 +219,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             if (g.h_bar) g.h_bar[(size_t)draw * p + i] = 0.0;
             if (g.d_bar) g.d_bar[(size_t)draw * p + i] = 0.0;
         }
+        if (g.Z_bar) GFOR(i, p * n) g.Z_bar[(size_t)draw * p * n + i] = 0.0;
         if (G_TID == 0) {
             g.ll[draw] = -INFINITY;
             g.status[draw] = status | 0x400;
@@ -248,7 +252,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     }
     GFOR(idx, p * n) {
         const int i = idx / n, j = idx - i * n;
-        Zs[idx] = g.Z ? g.Z[idx] : ((g.obs_idx[i] == j) ? 1.0 : 0.0);
+        Zs[idx] = g.Z ? g.Z[(size_t)draw * (size_t)g.z_stride + idx] : ((g.obs_idx[i] == j) ? 1.0 : 0.0);
+        Zb[idx] = 0.0;
     }
     GFOR(i, n) {
         a[i] = 0.0;
@@ -499,6 +504,15 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
                   for (int c = 0; c < p; ++c) s = fma(PZb[i * ps + c] * w[c], Zs[c * n + j], s);
                   Pb[i * ld + j] = s;
               });
+        if (g.Z_bar) {  // Zm = diag(w) Z enters L = I - K Zm, v = ym - d - Zm a, PZ = P Zm', G = Zm PZ
+            GFOR(idx, p * n) {
+                const int c = idx / n, j = idx - c * n;
+                double s = -vb[c] * a[j];
+                for (int i = 0; i < n; ++i) s += fma(PZb[i * ps + c], P[i * ld + j], -K[i * ps + c] * W2[i * ld + j]);
+                for (int b = 0; b < p; ++b) s = fma(Fb[c * ps + b], PZ[j * ps + b], s);
+                Zb[idx] += w[c] * s;
+            }
+        }
         GFOR(j, n) {
             double s = afb[j];
             for (int c = 0; c < p; ++c) s = fma(-w[c] * Zs[c * n + j], vb[c], s);
@@ -563,6 +577,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         if (g.d_bar) g.d_bar[(size_t)draw * p + c] = db[c];
     }
+    if (g.Z_bar) GFOR(idx, p * n) g.Z_bar[(size_t)draw * p * n + idx] = Zb[idx];
     if (G_TID == 0) {
         g.ll[draw] = ll;
         g.status[draw] = status;

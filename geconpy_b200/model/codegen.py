@@ -261,8 +261,34 @@ class LinearizedModel:
             lines.append(f"    Z[{int(idx)}] = {cc(e)};")
         for row, e in zip(d_cells, red[nz:]):
             lines.append(f"    d[{int(row)}] = {cc(e)};")
+        # reverse mode over the same program: theta_bar += sum_cells Zb[cell] dZ[cell]/dtheta + sum_rows db[row] dd[row]/dtheta
+        stmts = [(self.p_sym[d], e) for d, e in zip(self.det_names, self.det_exprs)]
+        ss_subs, ss_red = sp.cse(self.ss_exprs, symbols=sp.numbered_symbols("s_tmp_"), optimizations="basic")
+        stmts += list(ss_subs) + [(self.ss_sym[v], e) for v, e in zip(self.var_names, ss_red)] + list(subs)
+        fwd = [ln for ln in lines if " Z[" not in ln and " d[" not in ln]
+        rev = [f"    double b_{self.p_sym[p].name} = 0.0;" for p in self.param_names] + [f"    double b_{sym.name} = 0.0;" for sym, _ in stmts]
+        rev.append("    double g;")
+
+        def push(expr, seed):
+            for sv in sorted(expr.free_symbols, key=lambda x: x.name):
+                dv = sp.diff(expr, sv)
+                if dv != 0:
+                    rev.append(f"    b_{sv.name} += {seed} * ({cc(dv)});")
+
+        for idx, e in zip(z_cells, red[:nz]):
+            if sp.sympify(e).free_symbols:
+                rev.append(f"    g = Zb[{int(idx)}];")
+                push(sp.sympify(e), "g")
+        for row, e in zip(d_cells, red[nz:]):
+            if sp.sympify(e).free_symbols:
+                rev.append(f"    g = db[{int(row)}];")
+                push(sp.sympify(e), "g")
+        for sym, e in reversed(stmts):
+            push(e, f"b_{sym.name}")
+        for i, p in enumerate(self.param_names):
+            rev.append(f"    thb[{i}] += b_{self.p_sym[p].name};")
         ident = re.sub(r"[^0-9A-Za-z_]", "_", f"{self.name}_{tag}")
-        return _OBS_TEMPLATE.format(name=ident, n_theta=self.n_theta, body="\n".join(lines))
+        return _OBS_TEMPLATE.format(name=ident, n_theta=self.n_theta, body="\n".join(lines), vjp_body="\n".join(fwd + rev))
 
     # ------------------------------------------------------------------------------------------------ reverse mode
     def vjp_body(self) -> str:
@@ -583,7 +609,21 @@ __device__ __forceinline__ void gecon_obs_eval(const double* __restrict__ th, do
 {body}
 }}
 
+// theta_bar += <(Z_bar, d_bar), d(Z, d)/dtheta>: reverse mode over the same program (the adjoint of the observation equations)
+__device__ __forceinline__ void gecon_obs_vjp(const double* __restrict__ th, const double* __restrict__ Zb, const double* __restrict__ db,
+                                              double* __restrict__ thb) {{
+{vjp_body}
+}}
+
 #ifdef GECON_HOST_CHECK
+extern "C" int gecon_obs_vjp_host_check(const double* theta, int64_t N, const double* Zb, int64_t z_stride, const double* db, int64_t d_stride,
+                                        double* theta_bar) {{
+    for (int64_t i = 0; i < N; ++i)
+        gecon_obs_vjp(theta + (size_t)i * GECON_MODEL_NTHETA, Zb + (size_t)i * z_stride, db + (size_t)i * d_stride,
+                      theta_bar + (size_t)i * GECON_MODEL_NTHETA);
+    return 0;
+}}
+
 extern "C" int gecon_obs_host_check(const double* theta, int64_t N, double* Z, int64_t z_stride, double* d, int64_t d_stride) {{
     for (int64_t i = 0; i < N; ++i) gecon_obs_eval(theta + (size_t)i * GECON_MODEL_NTHETA, Z + (size_t)i * z_stride, d + (size_t)i * d_stride);
     return 0;
@@ -593,6 +633,27 @@ __global__ void __launch_bounds__(128) gecon_obs_kernel(const double* __restrict
                                                         long long z_stride, double* __restrict__ d, long long d_stride) {{
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
         gecon_obs_eval(theta + (size_t)i * GECON_MODEL_NTHETA, Z + (size_t)i * z_stride, d + (size_t)i * d_stride);
+}}
+
+__global__ void __launch_bounds__(128) gecon_obs_vjp_kernel(const double* __restrict__ theta, long long N, const double* __restrict__ Zb,
+                                                            long long z_stride, const double* __restrict__ db, long long d_stride,
+                                                            double* __restrict__ theta_bar) {{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        gecon_obs_vjp(theta + (size_t)i * GECON_MODEL_NTHETA, Zb + (size_t)i * z_stride, db + (size_t)i * d_stride,
+                      theta_bar + (size_t)i * GECON_MODEL_NTHETA);
+}}
+
+// DEVICE pointers: theta_bar[N][n_theta] += vector-Jacobian product of (Z_bar [N][p][k_states], d_bar [N][p])
+extern "C" int gecon_obs_vjp_batched(const double* theta, int64_t N, const double* Zb, int64_t z_stride, const double* db, int64_t d_stride,
+                                     double* theta_bar, void* stream) {{
+    if (N <= 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (N + 127) / 128;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    gecon_obs_vjp_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(theta, N, Zb, z_stride, db, d_stride, theta_bar);
+    return (int)cudaGetLastError();
 }}
 
 // DEVICE pointers: Z is [N][p][k_states] (z_stride doubles per draw), d is [N][p] (d_stride); returns 0 or a cudaError_t

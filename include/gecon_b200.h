@@ -263,7 +263,7 @@ typedef struct gecon_kalman_grad_args {
     int64_t q_stride;
     const double* hdiag;
     int64_t h_stride;
-    const double* Z;         /* [p][n] shared, or NULL when obs_idx is given */
+    const double* Z;         /* [p][n] shared or [N][p][n] (z_stride), or NULL when obs_idx is given */
     const int32_t* obs_idx;
     const double* d;
     int64_t d_stride;
@@ -287,6 +287,8 @@ typedef struct gecon_kalman_grad_args {
     double* q_bar;    /* [N][k] out: dll/dq (variances) or dll/dsigma */
     double* h_bar;    /* [N][p] out or NULL */
     double* d_bar;    /* [N][p] out or NULL */
+    int64_t z_stride; /* 0: Z shared by all draws; p * n: one design matrix per draw */
+    double* Z_bar;    /* [N][p][n] out or NULL: dll/dZ (dense design matrices; the adjoint of observation equations) */
 } gecon_kalman_grad_args;
 
 int gecon_kalman_grad_batched(const gecon_kalman_grad_args* args, void* stream);

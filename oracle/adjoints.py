@@ -114,6 +114,7 @@ def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, 
     # ---- reverse sweep
     T_bar, C0_bar = np.zeros((n, n)), np.zeros((n, n))
     h_bar, d_bar = np.zeros(p), np.zeros(p)
+    Z_bar = np.zeros((p, n))
     a_bar, P_bar = np.zeros(n), np.zeros((n, n))  # adjoints of the predicted moments of step t + 1
     for t in range(Tobs - 1, -1, -1):
         a, P = As[t], Ps[t]
@@ -155,13 +156,15 @@ def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, 
         a_bar = a_bar - Zm.T @ v_bar
         d_bar -= v_bar
         h_bar += w * np.diag(Hm_bar)
+        # design matrix: L = I - K Zm, v = ym - d - Zm a, PZ = P Zm', G = Zm PZ   (Zm = diag(w) Z)
+        Z_bar += w[:, None] * (-K.T @ L_bar - np.outer(v_bar, a) + PZ_bar.T @ P + F_bar @ PZ.T)
     # ---- P0 = dlyap(T, C0), a0 = 0
     S, T_lyap = dlyap_adjoint(T, P0, P_bar)
     C0_bar += S
     T_bar += T_lyap
     R_bar = C0_bar @ R @ np.diag(q) + C0_bar.T @ R @ np.diag(q)
     q_bar = np.einsum("ic,ij,jc->c", R, C0_bar, R)
-    return dict(ll=ll, T=T_bar, R=R_bar, q=q_bar, h=h_bar, d=d_bar)
+    return dict(ll=ll, T=T_bar, R=R_bar, q=q_bar, h=h_bar, d=d_bar, Z=Z_bar)
 
 
 def loglik_grad(model, theta, Y, observed, sigma_shock, sigma_err=None, tol=1e-13, max_iter=1000, jitter=oss.JITTER_DEFAULT, fd_eps=1e-6):

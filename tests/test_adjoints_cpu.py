@@ -58,6 +58,8 @@ def test_oracle_kalman_adjoints_match_finite_differences(missing):
         return oss.kalman_loglik(Y, T, R, np.diag(q), Z, np.diag(h), d=d)
 
     assert abs(g["ll"] - f()) < 1e-10
+    numZ = _fd(Z, lambda z: oss.kalman_loglik(Y, T, R, np.diag(q), z, np.diag(h), d=d))
+    assert np.abs(numZ - g["Z"]).max() <= 2e-7 * max(1.0, np.abs(numZ).max())
     for name, x in (("T", T), ("R", R), ("q", q), ("h", h), ("d", d)):
         num = _fd(x, lambda v, name=name: f(**{name: v}))
         assert np.abs(num - g[name]).max() <= 2e-7 * max(1.0, np.abs(num).max()), name
@@ -130,12 +132,13 @@ def test_kalman_grad_source_matches_oracle(hostcheck, n, k, p, Tobs, missing, se
     sig, serr = np.sqrt(q), np.sqrt(h)
     ll, st = np.zeros(N), np.zeros(N, np.int32)
     Tb, Rb, qb, hb, db = np.zeros((N, n, n)), np.zeros((N, n, k)), np.zeros((N, k)), np.zeros((N, p)), np.zeros((N, p))
+    Zb = np.zeros((N, p, n))
     a = L.KalmanGradArgs(
         struct_size=C.sizeof(L.KalmanGradArgs), T=T.ctypes.data, R=R.ctypes.data, qdiag=sig.ctypes.data, q_stride=k, hdiag=serr.ctypes.data,
         h_stride=p, Z=None if selector else Z.ctypes.data, obs_idx=obs.ctypes.data if selector else None, d=d.ctypes.data, d_stride=p,
         Y=Y.ctypes.data, N=N, n=n, k=k, p=p, Tobs=Tobs, jitter=1e-8, missing_fill=-9999.0, mvn_const_mode=0, lyap_max_iter=0,
         status_in=None, gate_mask=0, sigma_inputs=1, ll=ll.ctypes.data, status=st.ctypes.data, T_bar=Tb.ctypes.data, R_bar=Rb.ctypes.data,
-        q_bar=qb.ctypes.data, h_bar=hb.ctypes.data, d_bar=db.ctypes.data,
+        q_bar=qb.ctypes.data, h_bar=hb.ctypes.data, d_bar=db.ctypes.data, z_stride=0, Z_bar=None if selector else Zb.ctypes.data,
     )  # fmt: skip
     assert hostcheck.gecon_kalman_grad_hostcheck(C.byref(a)) == 0
     for i in range(N):
@@ -143,6 +146,8 @@ def test_kalman_grad_source_matches_oracle(hostcheck, n, k, p, Tobs, missing, se
         assert st[i] == 0 and abs(ll[i] - g["ll"]) <= 1e-9
         for got, ref in ((Tb[i], g["T"]), (Rb[i], g["R"]), (qb[i], 2 * sig[i] * g["q"]), (hb[i], 2 * serr[i] * g["h"]), (db[i], g["d"])):
             assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+        if not selector:
+            assert np.abs(Zb[i] - g["Z"]).max() <= 1e-10 * max(1.0, np.abs(g["Z"]).max())
 
 
 @pytest.mark.parametrize("name", ["rbc", "rbc_extended", "full_nk", "nk_complete_more_shocks"])
