@@ -245,6 +245,8 @@ class BatchedStateSpace:
                 raise L.GeconLibraryError(f"cannot load {lib_path}: {e}") from e
             self._obs_lib.gecon_obs_batched.restype = C.c_int
             self._obs_lib.gecon_obs_batched.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+            self._obs_lib.gecon_obs_vjp_batched.restype = C.c_int
+            self._obs_lib.gecon_obs_vjp_batched.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         loglin = set(m.var_names) - set(m.lin.not_loglin_variables) if m.lin.log_linearize else set()
         self._d_pos = np.array([observed_states.index(v) for v in ss_obs_intercept], dtype=np.int64)
         self._d_var = np.array([m.var_names.index(v) for v in ss_obs_intercept], dtype=np.int64)
@@ -435,8 +437,6 @@ class BatchedStateSpace:
             raise RuntimeError("call configure(...) first")
         if not (torch is not None and isinstance(theta_full, torch.Tensor) and theta_full.is_cuda):
             raise TypeError("loglik_and_grad_device needs CUDA tensors; use loglik_and_grad() for host arrays")
-        if self._obs_lib is not None:
-            raise NotImplementedError("gradients through parameter-dependent observation equations are not implemented")
         m = self.model
         lib = L.load_library()
         dev = theta_full.device
@@ -462,6 +462,7 @@ class BatchedStateSpace:
                 Cb=torch.empty((nc, n, n), **f64), Db=torch.empty((nc, n, k), **f64), thb=torch.empty((nc, m.n_theta), **f64),
                 xssb=torch.zeros((nc, n), **f64), U=torch.as_tensor(self.filter_vars.astype(np.int64), device=dev),
                 ll=torch.empty((nc,), **f64), st2=torch.empty((nc,), dtype=torch.int32, device=dev),
+                Zb=(torch.empty((nc, p, na), **f64) if self._obs_lib is not None else None),
                 rows=torch.empty((nc, self.n_filter, n), **f64), err_pos=torch.as_tensor(self.err_pos, device=dev),
             )  # fmt: skip
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -489,6 +490,12 @@ class BatchedStateSpace:
             if self.ss_obs_intercept:
                 xs = ws["xss"][:cnt].index_select(1, ws["d_var"])
                 ws["d"][:cnt].index_copy_(1, ws["d_pos"], torch.where(ws["d_loglin"], xs.log(), xs) * ws["d_scale"])
+            if self._obs_lib is not None:
+                rc = self._obs_lib.gecon_obs_batched(ws["theta"].data_ptr(), cnt, ws["Z"].data_ptr(), self.p * self.n_aug,
+                                                     ws["d"].data_ptr(), self.p, C.c_void_p(stream))  # fmt: skip
+                m.launches += 1
+                if rc != 0:
+                    raise L.GeconLibraryError(f"gecon_obs_batched failed with CUDA error {rc}")
             cr = L.CrArgs(
                 struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
                 D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
@@ -516,7 +523,9 @@ class BatchedStateSpace:
                 q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
                 Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None),
                 obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
-                d=(ws["d"].data_ptr() if self.ss_obs_intercept else None), d_stride=(self.p if self.ss_obs_intercept else 0),
+                d=(ws["d"].data_ptr() if "d" in ws else None), d_stride=(self.p if "d" in ws else 0),
+                z_stride=(self.p * self.n_aug if self._obs_lib is not None else 0),
+                Z_bar=(g["Zb"].data_ptr() if self._obs_lib is not None else None),
                 Y=Y.data_ptr(), N=cnt, n=self.n_aug, k=m.k, p=self.p, Tobs=Tobs, jitter=self.cov_jitter,
                 missing_fill=self.missing_fill_value, mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0,
                 status_in=st.data_ptr(), gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(),
@@ -553,6 +562,12 @@ class BatchedStateSpace:
                 xssb.index_add_(1, ws["d_var"], torch.where(ws["d_loglin"], dbar / xs, dbar))
             e = mark("jacobian_vjp")
             m.vjp_device(ws["theta"][:cnt], g["Ab"], g["Bb"], g["Cb"], g["Db"], xssb, g["thb"], stream)
+            if self._obs_lib is not None:  # the observation equations' share: theta_bar += <(Z_bar, d_bar), d(Z, d)/dtheta>
+                rc = self._obs_lib.gecon_obs_vjp_batched(ws["theta"].data_ptr(), cnt, g["Zb"].data_ptr(), self.p * self.n_aug,
+                                                         g["db"].data_ptr(), self.p, g["thb"].data_ptr(), C.c_void_p(stream))  # fmt: skip
+                m.launches += 1
+                if rc != 0:
+                    raise L.GeconLibraryError(f"gecon_obs_vjp_batched failed with CUDA error {rc}")
             e and e.record()
             out = grad[lo : lo + cnt]
             out[:, : m.n_theta] = g["thb"][:cnt]
