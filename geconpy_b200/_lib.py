@@ -154,6 +154,8 @@ class KalmanArgs(C.Structure):
         ("status", C.c_void_p),
         ("ll_t", C.c_void_p),
         ("z_stride", C.c_int64),
+        ("qfull", C.c_void_p),
+        ("qfull_stride", C.c_int64),
     ]
 
 

@@ -279,12 +279,14 @@ def kalman_loglik(
     gate_mask=0,
     return_per_step=False,
     lyap_max_iter=0,
+    Q=None,
 ):
     """Batched Kalman-filter log-likelihood (``gecon_kalman_ll_*``): returns (ll[N], status[N][, ll_t[N, Tobs]]).
 
     Reference call site: gEconpy/model/statespace.py:1151-1157 (pymc_extras StandardFilter); semantics in
     SURVEY.md Appendix A.5.  ``qdiag`` / ``hdiag`` are VARIANCES, per draw (N, k) / (N, p) or shared (k,) / (p,).
     ``Z`` is (p, n) shared or (N, p, n), one design matrix per draw (parameter-dependent observation equations).
+    ``Q``: full shock covariance, (k, k) shared or (N, k, k) (``full_shock_covariance``); ``qdiag`` is then ignored.
     """
     if (Z is None) == (obs_idx is None):
         raise ValueError("give exactly one of Z (dense design matrix) and obs_idx (selector)")
@@ -299,7 +301,8 @@ def kalman_loglik(
         Tobs, p = Ya.shape[0], 1
     else:
         Tobs, p = Ya.shape
-    q, pq = m.inp(qdiag)
+    q, pq = m.inp(qdiag if Q is None else None)
+    Qa, pQ = m.inp(Q)
     h, ph = m.inp(hdiag)
     dd, pd_ = m.inp(d)
     Za, pZ = m.inp(Z)
@@ -310,9 +313,10 @@ def kalman_loglik(
     st, pS = m.out((N,), np.int32)
     llt, pllt = m.out((N, Tobs)) if return_per_step else (None, None)
     args = L.KalmanArgs(
-        struct_size=C.sizeof(L.KalmanArgs), T=pT, R=pR, qdiag=pq, q_stride=(k if q.ndim == 2 else 0), hdiag=ph,
+        struct_size=C.sizeof(L.KalmanArgs), T=pT, R=pR, qdiag=pq, q_stride=(k if (q is not None and q.ndim == 2) else 0), hdiag=ph,
         h_stride=(p if (h is not None and h.ndim == 2) else 0), Z=pZ, obs_idx=pO, d=pd_,
-        d_stride=(p if (dd is not None and dd.ndim == 2) else 0), Y=pY, P0=pP0, N=N, n=n, k=k, p=p, Tobs=Tobs,
+        d_stride=(p if (dd is not None and dd.ndim == 2) else 0), Y=pY, P0=pP0, qfull=pQ,
+        qfull_stride=(k * k if (Qa is not None and Qa.ndim == 3) else 0), N=N, n=n, k=k, p=p, Tobs=Tobs,
         jitter=float(jitter), missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1),
         lyap_max_iter=int(lyap_max_iter), status_in=pSin, gate_mask=int(gate_mask), ll=pll, status=pS, ll_t=pllt,
         z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0),

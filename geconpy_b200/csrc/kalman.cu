@@ -52,13 +52,17 @@ static int check_kf_args(const gecon_kalman_args* a) {
         set_last_error("gecon_kalman_args: bad struct_size");
         return GECON_E_BADARG;
     }
-    if (!a->T || !a->R || !a->qdiag || !a->Y || !a->ll || !a->status || a->N < 0 || a->n < 1 || a->k < 0 || a->p < 1 || a->Tobs < 0 ||
+    if (!a->T || !a->R || (!a->qdiag && !a->qfull) || !a->Y || !a->ll || !a->status || a->N < 0 || a->n < 1 || a->k < 0 || a->p < 1 || a->Tobs < 0 ||
         (!a->Z && !a->obs_idx)) {
         set_last_error("gecon_kalman_args: null pointer or bad dimension");
         return GECON_E_BADARG;
     }
     if (a->Z && a->z_stride && a->z_stride != (int64_t)a->p * a->n) {
         set_last_error("gecon_kalman_args: z_stride must be 0 (shared Z) or p * n");
+        return GECON_E_BADARG;
+    }
+    if (a->qfull && a->qfull_stride && a->qfull_stride != (int64_t)a->k * a->k) {
+        set_last_error("gecon_kalman_args: qfull_stride must be 0 (shared Q) or k * k");
         return GECON_E_BADARG;
     }
     if (a->p > PMAX || a->p > a->n) {
@@ -78,7 +82,7 @@ int launch_kw_24(const gecon_kalman_args& a, cudaStream_t st, int* info);
 
 // padded dimension of the warp-per-draw kernel (needs a spare column for the mean), or 0 when the CTA kernel must run
 static int warp_kernel_np(const gecon_kalman_args& a) {
-    if (!a.obs_idx || a.Z) return 0;  // dense design matrices stay on the CTA kernel
+    if (!a.obs_idx || a.Z || a.qfull) return 0;  // dense design matrices and full shock covariances stay on the CTA kernel
     const int np = round_up8((a.n + 1) > a.k ? (a.n + 1) : a.k);
     return np <= 24 ? np : 0;
 }
@@ -213,7 +217,7 @@ extern "C" int gecon_kalman_ll_host(const gecon_kalman_args* a) {
     if (rc) return rc;
     if (a->N == 0) return 0;
     const size_t N = (size_t)a->N, n = a->n, k = a->k, p = a->p, Tobs = a->Tobs;
-    DevBuf dT, dR, dq, dh, dZ, dobs, dd, dY, dP0, dSin, dll, dSt, dllt;
+    DevBuf dT, dR, dq, dqf, dh, dZ, dobs, dd, dY, dP0, dSin, dll, dSt, dllt;
     gecon_kalman_args d = *a;
 #define H2D(buf, field, type, count)                                                          \
     if (a->field) {                                                                           \
@@ -224,6 +228,7 @@ extern "C" int gecon_kalman_ll_host(const gecon_kalman_args* a) {
     H2D(dT, T, double, N * n * n)
     H2D(dR, R, double, N * n * k)
     H2D(dq, qdiag, double, (a->q_stride ? N * k : k))
+    H2D(dqf, qfull, double, (a->qfull_stride ? N * k * k : k * k))
     H2D(dh, hdiag, double, (a->h_stride ? N * p : p))
     H2D(dZ, Z, double, (a->z_stride ? N * p * n : p * n))
     H2D(dobs, obs_idx, int32_t, p)

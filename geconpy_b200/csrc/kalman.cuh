@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
         tile_load<NP>(Tm, p.T + (size_t)draw * n * n, n, n, n);
         tile_load<NP>(W, p.R + (size_t)draw * n * k, n, k, k);
         tile_zero<NP>(RQ);
-        if (tid < k) {
+        if (tid < k && !p.qfull) {
             const double qv = p.qdiag[(size_t)draw * p.q_stride + tid];
             s_q[tid] = p.sigma_inputs ? qv * qv : qv;
         }
@@ -268,7 +268,22 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
             }
         }
         __syncthreads();
-        rqr_fill<NP>(RQ, W, s_q, n, k);
+        if (p.qfull) {  // R Q R' with a full shock covariance: two DMMA products through the tiles that are still free
+            tile_load<NP>(P, p.qfull + (size_t)draw * (size_t)p.qfull_stride, k, k, k);
+            __syncthreads();
+            Acc<NP> acc;
+            acc_zero(acc);
+            gemm_acc<NP, false, false>(acc, W, P, 1.0);
+            acc_store<NP>(acc, Aw);
+            __syncthreads();
+            acc_zero(acc);
+            gemm_acc<NP, false, true>(acc, Aw, W, 1.0);
+            acc_store<NP>(acc, RQ);
+            __syncthreads();
+            tile_symmetrize<NP>(RQ, n);
+        } else {
+            rqr_fill<NP>(RQ, W, s_q, n, k);
+        }
         int lo, hi;
         nonzero_col_range<NP>(Tm, n, s_i, lo, hi);  // barriers inside also publish RQ
         const int klo = lo & ~3, khi = (hi + 3) & ~3, ctlo = lo >> 3, cthi = (hi + 7) >> 3;

@@ -148,13 +148,16 @@ class BatchedStateSpace:
         aggregation_period: int = 4,
         ss_obs_intercept: list | None = None,
         observation_equations: dict | None = None,
+        full_shock_covariance: bool = False,
     ):
         """Same meaning as ``DSGEStateSpace.configure`` (gEconpy/model/statespace.py:822-1090) for the arguments it
         shares: ``temporal_aggregation`` {"sum" | "mean" | "first" | "last"} with ``aggregation_period`` adds cumulator
         states (statespace.py:598-650), ``ss_obs_intercept`` puts log x_ss(theta) / x_ss(theta) of the listed observed
         states into the observation intercept d (statespace.py:363-388), ``observation_equations`` {observed series: GCN-syntax
         expression in model variables (``v[]``, ``v[-1]``, ``v[ss]``) and parameters} is linearised around the steady state into a
-        parameter-dependent design-matrix row, an intercept and observation-lag states (statespace.py:390-556,652-694)."""
+        parameter-dependent design-matrix row, an intercept and observation-lag states (statespace.py:390-556,652-694);
+        ``full_shock_covariance`` replaces the k ``sigma_<shock>`` entries of the parameter vector by the k x k matrix
+        ``state_cov`` (row-major, used as Q directly: statespace.py:245-249)."""
         m = self.model
         if solver not in ("cycle_reduction", "gensys"):
             raise NotImplementedError(f"solver={solver!r}: the B200 path solves by cycle reduction (gensys maps to CR + BK flag)")
@@ -256,9 +259,10 @@ class BatchedStateSpace:
         self.cov_jitter, self.missing_fill_value, self.mvn_const = float(cov_jitter), float(missing_fill_value), mvn_const
         self.check_bk = bool(check_bk)
         self.chunk = int(os.environ.get("GECON_CHUNK", chunk))
-        self.param_names = (
-            list(m.param_names) + [f"sigma_{s}" for s in m.shock_names] + [f"error_sigma_{v}" for v in measurement_error]
-        )
+        self.full_covariance = bool(full_shock_covariance)
+        self._n_cov = m.k * m.k if self.full_covariance else m.k
+        cov_names = [f"state_cov[{i},{j}]" for i in range(m.k) for j in range(m.k)] if self.full_covariance else [f"sigma_{s}" for s in m.shock_names]
+        self.param_names = list(m.param_names) + cov_names + [f"error_sigma_{v}" for v in measurement_error]
         self.n_param = len(self.param_names)
         self.configured = True
         self._ws = None
@@ -295,6 +299,8 @@ class BatchedStateSpace:
             # constant rows [F | kron(I, shift)] of the augmented transition: written once, the solver kernel only ever
             # writes the top-left n_filter x n_filter block (t_ld / t_stride) and the top n_filter rows of R
             ws["T"][:, self.n_filter :, :] = torch.as_tensor(self.aug.transition_rows(), **f64)
+        if self.full_covariance:
+            ws["Q"] = torch.empty((nc, m.k, m.k), **f64)
         if self.dense_Z is not None:
             ws["Z"] = torch.as_tensor(self.dense_Z, **f64)
             if self._obs_lib is not None:  # one design matrix per draw: constant rows now, equation rows by the obs kernel
@@ -362,9 +368,12 @@ class BatchedStateSpace:
             stream = streams[slot].cuda_stream
             # split the parameter vector (strided device copies; no arithmetic)
             ws["theta"][:cnt].copy_(th[:, : m.n_theta])
-            ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
+            if self.full_covariance:
+                ws["Q"][:cnt].copy_(th[:, m.n_theta : m.n_theta + self._n_cov].reshape(cnt, m.k, m.k))
+            else:
+                ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
             if n_err:
-                ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + m.k :])
+                ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + self._n_cov :])
             st = ws["status"][:cnt]
             e = mark("jacobian")
             m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
@@ -401,8 +410,10 @@ class BatchedStateSpace:
                 L.check(lib.gecon_bk_count_batched(C.byref(bk), C.c_void_p(stream)), "gecon_bk_count_batched")
                 e and e.record()
             kf = L.KalmanArgs(
-                struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), qdiag=ws["sig"].data_ptr(),
-                q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
+                struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
+                qdiag=(None if self.full_covariance else ws["sig"].data_ptr()), q_stride=m.k,
+                qfull=(ws["Q"].data_ptr() if self.full_covariance else None), qfull_stride=m.k * m.k,
+                hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
                 Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None),
                 z_stride=(self.p * self.n_aug if self._obs_lib is not None else 0),
                 obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
@@ -437,6 +448,8 @@ class BatchedStateSpace:
             raise RuntimeError("call configure(...) first")
         if not (torch is not None and isinstance(theta_full, torch.Tensor) and theta_full.is_cuda):
             raise TypeError("loglik_and_grad_device needs CUDA tensors; use loglik_and_grad() for host arrays")
+        if self.full_covariance:
+            raise NotImplementedError("the gradient path takes diagonal shock covariances (sigma_<shock>) only")
         m = self.model
         lib = L.load_library()
         dev = theta_full.device

@@ -200,6 +200,10 @@ typedef struct gecon_kalman_args {
     double* ll_t;         /* [N][Tobs] out or NULL: per-observation log-likelihood */
     int64_t z_stride;     /* 0: Z is shared by all draws; p * n: Z is [N][p][n], one design matrix per draw (parameter-
                              dependent observation equations, statespace.py:299-331) */
+    const double* qfull;  /* full shock covariance Q ("state_cov" of full_shock_covariance=True, statespace.py:245-249):
+                             [N][k][k] (qfull_stride = k k) or shared [k][k] (0); when given, qdiag is ignored (may be NULL)
+                             and the state dimension runs on the CTA-per-draw kernel */
+    int64_t qfull_stride;
 } gecon_kalman_args;
 
 int gecon_kalman_ll_batched(const gecon_kalman_args* args, void* stream);

@@ -133,6 +133,7 @@ def loglik_from_matrices(
     check_resid=True,
     mvn_const="per_obs",
     lyapunov_method="bilinear",
+    Q_full=None,
 ):
     """One likelihood evaluation from already-evaluated (permuted) Jacobians.
 
@@ -165,7 +166,8 @@ def loglik_from_matrices(
         T = T[inv_var_order][:, inv_var_order]
         R = R[inv_var_order]
     out["T"], out["R"] = T, R
-    Q = np.diag(np.asarray(sigma_shock, dtype=np.float64) ** 2)
+    # full_shock_covariance: state_cov is used as Q directly (gEconpy/model/statespace.py:245-249)
+    Q = np.diag(np.asarray(sigma_shock, dtype=np.float64) ** 2) if Q_full is None else np.asarray(Q_full, dtype=np.float64)
     p = len(obs_idx)
     Z = np.zeros((p, n))
     Z[np.arange(p), obs_idx] = 1.0

@@ -232,3 +232,63 @@ def test_observation_equations_match_oracle(name, observed, eqs, ta, period, red
         else:
             assert np.isneginf(ll[i]) and st[i] != 0
     assert n_ok >= N // 2
+
+
+# ------------------------------------------------------------------------------------------------ full shock covariance
+@pytest.mark.parametrize("n,k,p", [(6, 3, 2), (12, 4, 3), (30, 5, 4)])
+def test_full_shock_covariance_kernel(B, n, k, p):
+    """gecon_kalman_args.qfull: Q = state_cov used directly (statespace.py:245-249), shared and per draw."""
+    rng = np.random.default_rng(100 + n)
+    N, Tobs = 4, 30
+    T = rng.standard_normal((N, n, n))
+    for i in range(N):
+        T[i] *= 0.85 / np.abs(np.linalg.eigvals(T[i])).max()
+    R = rng.standard_normal((N, n, k))
+    Lq = rng.standard_normal((N, k, k))
+    Q = Lq @ Lq.transpose(0, 2, 1) + 0.1 * np.eye(k)
+    h = 0.1 + rng.random((N, p))
+    obs = np.sort(rng.choice(n, size=p, replace=False)).astype(np.int32)
+    Z = np.zeros((p, n))
+    Z[np.arange(p), obs] = 1.0
+    Y = rng.standard_normal((Tobs, p))
+    ll, st = B.kalman_loglik(T, R, None, Y, obs_idx=obs, hdiag=h, Q=Q)
+    ll0, _ = B.kalman_loglik(T, R, None, Y, Z=Z, hdiag=h, Q=Q[0])
+    ll_diag, _ = B.kalman_loglik(T, R, np.ones((N, k)), Y, obs_idx=obs, hdiag=h)
+    ll_eye, _ = B.kalman_loglik(T, R, None, Y, obs_idx=obs, hdiag=h, Q=np.eye(k))
+    assert np.abs(ll_diag - ll_eye).max() <= TOL_LL  # Q = I through both code paths (warp kernel vs CTA kernel)
+    for i in range(N):
+        assert st[i] == 0
+        assert abs(ll[i] - oss.kalman_loglik(Y, T[i], R[i], Q[i], Z, np.diag(h[i]))) <= TOL_LL
+        assert abs(ll0[i] - oss.kalman_loglik(Y, T[i], R[i], Q[0], Z, np.diag(h[i]))) <= TOL_LL
+
+
+def test_full_shock_covariance_pipeline():
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    mod = model("full_nk")
+    observed = mod.spec["observed_default"]
+    ss = BatchedStateSpace(CompiledModel("full_nk")).configure(
+        observed_states=observed, measurement_error=observed, tol=1e-9, max_iter=200, full_shock_covariance=True, chunk=8
+    )
+    k, N = mod.k, 10
+    assert ss.param_names[len(mod.param_names)] == "state_cov[0,0]" and len(ss.param_names) == len(mod.param_names) + k * k + len(observed)
+    th = draws(mod, N, seed=23, width=0.02, valid=True)
+    rng = np.random.default_rng(3)
+    Lq = SIGMA_SHOCK * (np.eye(k) + 0.3 * rng.standard_normal((N, k, k)))
+    Q = Lq @ Lq.transpose(0, 2, 1)
+    err = np.full((N, len(observed)), SIGMA_ERR)
+    from helpers import simulate_obs
+
+    Y = simulate_obs(mod, 50, seed=3, sigma_err=SIGMA_ERR)
+    ll, st = ss.loglik(np.hstack([th, Q.reshape(N, -1), err]), Y)
+    n_ok = 0
+    for i in range(N):
+        ref = oss.loglik(mod, th[i], Y, observed, None, err[i], tol=1e-9, max_iter=200, Q_full=Q[i])
+        if ref["ok"] and np.isfinite(ref["ll"]):
+            n_ok += 1
+            assert st[i] == 0 and abs(ll[i] - ref["ll"]) <= TOL_LL, (i, ll[i], ref["ll"])
+        else:
+            assert np.isneginf(ll[i])
+    assert n_ok >= N // 2
+    with pytest.raises(NotImplementedError):
+        ss.loglik_and_grad(np.hstack([th, Q.reshape(N, -1), err]), Y)
