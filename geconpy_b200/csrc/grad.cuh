@@ -672,6 +672,7 @@ GHD void policy_adjoint_draw(const PolicyAdjointArgs& g, long long draw, double*
         GSYNC();
         GFOR(idx, n * n) {
             const int i = idx / n, j = idx - i * n;
+            if (i == c) continue;  // the pivot row is read by everyone in this phase: leave it alone (its multiplier is 0)
             const double f = X2[i * ld];
             X1[i * ld + j] = fma(-f, X1[c * ld + j], X1[i * ld + j]);
             X0[i * ld + j] = fma(-f, X0[c * ld + j], X0[i * ld + j]);
