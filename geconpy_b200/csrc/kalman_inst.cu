@@ -1,5 +1,7 @@
 // Instantiations of the Kalman kernel for ONE padded dimension (compile with -DGECON_KF_NP=8|16|...|56) and every
 // number of observables p = 1..8.
+#include <cstdlib>
+
 #include "kalman.cuh"
 #include "kalman_warp.cuh"
 
@@ -32,16 +34,16 @@ static int launch_one(const gecon_kalman_args& a, cudaStream_t st, int* info) {
 }
 
 // one warp per draw (kalman_warp.cuh): selector Z, n + 1 <= NP <= 24
-template <int NP, int PT, int MINB>
+template <int NP, int PT, int MINB, int WPC_ = 4>
 static int launch_one_warp_b(const gecon_kalman_args& a, cudaStream_t st, int* info) {
-    using S = KwSmem<NP, PT>;
+    using S = KwSmem<NP, PT, WPC_>;
     const size_t smem = S::bytes(a.Tobs);
     if (smem > 227 * 1024) {
         set_last_error("observation matrix does not fit in shared memory (%zu bytes needed)", smem);
         return GECON_E_UNSUPPORTED_SIZE;
     }
     int grid = 0, per_sm = 0;
-    int rc = persistent_grid(kalman_ll_warp_kernel<NP, PT, MINB>, S::WPC * 32, smem, (a.N + S::WPC - 1) / S::WPC, &grid, &per_sm, "GECON_KF_CTAS_PER_SM");
+    int rc = persistent_grid(kalman_ll_warp_kernel<NP, PT, MINB, WPC_>, S::WPC * 32, smem, (a.N + S::WPC - 1) / S::WPC, &grid, &per_sm, "GECON_KF_CTAS_PER_SM");
     if (rc) return rc;
     if (info) {
         info[0] = per_sm;
@@ -49,7 +51,7 @@ static int launch_one_warp_b(const gecon_kalman_args& a, cudaStream_t st, int* i
         info[2] = S::WPC * 32;
         return 0;
     }
-    kalman_ll_warp_kernel<NP, PT, MINB><<<grid, S::WPC * 32, smem, st>>>(a);
+    kalman_ll_warp_kernel<NP, PT, MINB, WPC_><<<grid, S::WPC * 32, smem, st>>>(a);
     g_launch_count++;
     GECON_CUDA(cudaGetLastError());
     return 0;
@@ -59,6 +61,16 @@ template <int NP, int PT>
 static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* info) {
     // resident CTAs the register allocator must leave room for: 4 x 4 warps per SM up to NP = 16 (measured: 128 registers
     // with the constant term in shared memory beats 168 registers and 3 CTAs), 2 CTAs at NP = 24
+    if constexpr (NP == 16) {
+        // one CTA of 16 warps per SM (same 16 warps per SM as 4 CTAs of 4, but one staged copy of Y and one set-up per SM):
+        // measured 45.6 -> 43.9 ms on the medium NK model; 20 warps (96 registers, spills) 50.5 ms, 12 warps 46.6 ms.
+        // Falls back to 4-warp CTAs when 16 private tile sets + Y do not fit in shared memory.
+        if (KwSmem<NP, PT, 16>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 16>(a, st, info);
+    }
+    if constexpr (NP == 24) {  // same idea: one CTA of 8 warps instead of two of 4
+        static const bool small_ctas = getenv("GECON_KF_SMALL_CTAS") != nullptr;  // experiment hook
+        if (!small_ctas && KwSmem<NP, PT, 8>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 8>(a, st, info);
+    }
     return launch_one_warp_b<NP, PT, (NP <= 16 ? 4 : 2)>(a, st, info);
 }
 

@@ -31,9 +31,9 @@ struct KmCfg {
     static constexpr int KW = 4 * KS2;                          // rows of the (transposed) panels [K|M|a+]', [M|K|e_n]'
 };
 
-template <int NP, int PT>
+template <int NP, int PT, int WPC_ = 4>
 struct KwSmem {
-    static constexpr int WPC = 4;  // warps (= draws in flight) per CTA
+    static constexpr int WPC = WPC_;  // warps (= draws in flight) per CTA: 4 (several CTAs per SM) or 16 (one CTA per SM, one copy of Y)
     static constexpr int TILE = Cfg<NP>::TILE;
     static constexpr int KM2 = 2 * KmCfg<PT>::KW * Cfg<NP>::LD;    // KM and MK panels, stored transposed: [k][LD]
     static constexpr int ALIAS = KM2 > TILE ? KM2 : TILE;          // the Lyapunov scratch tile shares their storage
@@ -151,9 +151,9 @@ __device__ __forceinline__ void warp_tile_load(double* __restrict__ dst, const d
     }
 }
 
-template <int NP, int PT, int MINB>
-__global__ void __launch_bounds__(KwSmem<NP, PT>::WPC * 32, MINB) kalman_ll_warp_kernel(const gecon_kalman_args p) {
-    using S = KwSmem<NP, PT>;
+template <int NP, int PT, int MINB, int WPC_ = 4>
+__global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const gecon_kalman_args p) {
+    using S = KwSmem<NP, PT, WPC_>;
     constexpr int LD = Cfg<NP>::LD, TILE = Cfg<NP>::TILE, NS = NP / 8, KSN = NP / 4;
     constexpr int KS2 = KmCfg<PT>::KS2, KW = KmCfg<PT>::KW, WPC = S::WPC;
     constexpr bool C0_REGS = S::C0_REGS;
