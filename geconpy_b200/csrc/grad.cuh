@@ -46,17 +46,6 @@ constexpr int ST_SINGULAR = 0x004, ST_LYAP = 0x040, ST_NOT_PD = 0x080, ST_LL_NON
 
 GHH int ldim(int n) { return n | 1; }  // odd leading dimension: column walks hit distinct 8-byte banks
 
-// C (m x n, ldc) = alpha * op(A) * op(B) + beta * C;  op(A) is m x kk, op(B) is kk x n.  C must not alias A or B.
-template <bool TA, bool TB>
-GHD void mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n, int kk, double alpha, double beta) {
-    GFOR(idx, m * n) {
-        const int i = idx / n, j = idx - i * n;
-        double s = 0.0;
-        for (int k = 0; k < kk; ++k) s = fma(TA ? A[k * lda + i] : A[i * lda + k], TB ? B[j * ldb + k] : B[k * ldb + j], s);
-        C[i * ldc + j] = (beta != 0.0) ? fma(alpha, s, beta * C[i * ldc + j]) : alpha * s;
-    }
-}
-
 // Register-blocked product: every work item is one row i and four consecutive columns j0..j0+3 of the output,
 //   epi(i, j, sum_k a(i, k) * b(k, j)),   i < m, j < n, k < kk,
 // so one a-load and four b-loads feed four FMA (1.25 shared loads per FMA instead of 2) and the index decode is paid once
@@ -81,6 +70,15 @@ GHD void gemm4(int m, int n, int kk, FA a, FB b, FE epi) {
         if (j0 + 2 < n) epi(i, j0 + 2, s2);
         if (j0 + 3 < n) epi(i, j0 + 3, s3);
     }
+}
+
+// C (m x n, ldc) = alpha * op(A) * op(B) + beta * C;  op(A) is m x kk, op(B) is kk x n.  C must not alias A or B.
+template <bool TA, bool TB>
+GHD void mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n, int kk, double alpha, double beta) {
+    gemm4(
+        m, n, kk, [&](int i, int k) { return TA ? A[k * lda + i] : A[i * lda + k]; },
+        [&](int k, int j) { return TB ? B[j * ldb + k] : B[k * ldb + j]; },
+        [&](int i, int j, double v) { C[i * ldc + j] = (beta != 0.0) ? fma(alpha, v, beta * C[i * ldc + j]) : alpha * v; });
 }
 
 // max |x| over m x n (NaN-propagating: a NaN makes the result NaN); s_red: G_NT doubles.  Contains barriers.
