@@ -68,7 +68,8 @@ static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* inf
         if (KwSmem<NP, PT, 16>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 16>(a, st, info);
     }
     // (NP = 24: one CTA of 8 warps instead of two of 4 measured the same, 99.8 vs 99.5 ms on the large NK model: not built)
-    return launch_one_warp_b<NP, PT, (NP <= 16 ? 4 : 2)>(a, st, info);
+    // NP = 8 needs 94 registers: five 4-warp CTAs per SM fit (2.57 -> 2.47 ms on the RBC workload)
+    return launch_one_warp_b<NP, PT, (NP <= 8 ? 5 : NP <= 16 ? 4 : 2)>(a, st, info);
 }
 
 #define GECON_CAT2(a, b) a##b
