@@ -537,6 +537,20 @@ def main():
                               "of": int(draws_per_gpu), "rank": 0}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # parity at the benchmark's own size: 48 draws of THIS run, spread over the whole population, against the CPU
+        # restatement (checker only; nothing of it is timed here)
+        pick = np.unique(np.linspace(0, draws_per_gpu - 1, 48).astype(np.int64))
+        ll_gpu = ll_d.cpu().numpy()[pick]
+        herr_full = np.zeros(len(wl["observed"]))
+        for v in wl["meas"]:
+            herr_full[wl["observed"].index(v)] = SIGMA_ERR
+        ll_cpu = np.array([_oracle_eval((wl["model"], theta[i], np.full(k, SIGMA_SHOCK), herr_full if wl["meas"] else np.zeros(0),
+                                        wl["observed"], Y)) for i in pick])
+        both = np.isfinite(ll_gpu) & np.isfinite(ll_cpu)
+        line["parity_spot_check"] = {"draws": int(pick.size), "finite_on_both": int(both.sum()),
+                                     "flags_agree": bool((np.isfinite(ll_gpu) == np.isfinite(ll_cpu)).all()),
+                                     "max_abs_ll_error": float(np.abs(ll_gpu[both] - ll_cpu[both]).max()) if both.any() else None,
+                                     "tolerance": 1e-7}
         n_sample = args.cpu_sample or 256 * cores
         rate, dt, nfin = cpu_reference_rate(wl, Y, n_sample, cores, seed=0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

@@ -139,3 +139,45 @@ def test_pipeline_device_path_and_chunking(compiled):
     big = BatchedStateSpace(cm).configure(observed_states=["Y"], chunk=65536)
     ll_b, _ = big.loglik(full, Y)
     assert np.array_equal(ll_b, ll_h)
+
+
+def test_full_size_population_is_permutation_chunk_and_duplicate_invariant(compiled):
+    """Size-independent properties at the benchmark's own size (262,144 medium-NK draws): every draw's result is a function
+    of that draw alone -- bit-identical under a permutation of the population, under a different chunking, and for
+    duplicated draws -- and a subsample agrees with the oracle."""
+    import torch
+
+    from geconpy_b200.model.compiled import BatchedStateSpace
+
+    cm, mod = compiled("full_nk"), model("full_nk")
+    observed = mod.spec["observed_default"]
+    N = 262144
+    base = draws(mod, 4096, seed=77, width=0.05, valid=True)
+    rng = np.random.default_rng(0)
+    th = base[rng.integers(0, len(base), size=N)]  # duplicates on purpose
+    th[: len(base)] = base
+    full = np.hstack([th, np.full((N, mod.k), SIGMA_SHOCK), np.full((N, len(observed)), SIGMA_ERR)])
+    Y = simulate_obs(mod, 200, seed=3, sigma_err=SIGMA_ERR)
+    dev = torch.device("cuda")
+    full_d, Y_d = torch.as_tensor(full, device=dev), torch.as_tensor(Y, device=dev)
+    ss = BatchedStateSpace(cm).configure(observed_states=observed, measurement_error=observed, tol=1e-8, max_iter=100)
+    ll, st = ss.loglik_device(full_d, Y_d)
+    ll, st = ll.clone(), st.clone()
+    perm = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    ll_p, st_p = ss.loglik_device(full_d[perm].contiguous(), Y_d)
+    assert torch.equal(ll_p, ll[perm]) and torch.equal(st_p, st[perm])
+    small = BatchedStateSpace(cm).configure(observed_states=observed, measurement_error=observed, tol=1e-8, max_iter=100, chunk=20000, n_streams=2)
+    ll_c, st_c = small.loglik_device(full_d, Y_d)
+    assert torch.equal(ll_c, ll) and torch.equal(st_c, st)
+    # duplicated parameter vectors give bit-identical results wherever they sit in the population
+    _, inv = np.unique(th, axis=0, return_inverse=True)
+    llh = ll.cpu().numpy()
+    first = np.zeros(inv.max() + 1)
+    first[inv[::-1]] = llh[::-1]
+    assert np.array_equal(first[inv], llh, equal_nan=True)
+    for i in rng.integers(0, N, size=6):
+        ref = oss.loglik(mod, th[i], Y, observed, np.full(mod.k, SIGMA_SHOCK), np.full(len(observed), SIGMA_ERR), tol=1e-8, max_iter=100)
+        if ref["ok"] and np.isfinite(ref["ll"]):
+            assert st[i] == 0 and abs(llh[i] - ref["ll"]) <= 1e-7
+        else:
+            assert np.isneginf(llh[i])
