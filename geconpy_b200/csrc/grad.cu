@@ -87,7 +87,7 @@ extern "C" int gecon_kalman_grad_batched(const gecon_kalman_grad_args* a, void* 
     int grid = 0;
     rc = persistent_grid(kalman_grad_kernel, nt, smem, a->N, &grid, nullptr);
     if (rc) return rc;
-    const size_t per_cta = (size_t)a->Tobs * ((size_t)a->n * a->n + a->n) + (size_t)a->n * a->n;
+    const size_t per_cta = (size_t)a->Tobs * ((size_t)a->n * a->n + a->n) + 2 * (size_t)a->n * a->n;
     double* ws = nullptr;
     GECON_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * per_cta * grid, st));
     g.traj = ws;

@@ -151,13 +151,13 @@ struct KalmanGradArgs {
     double* d_bar;    // [N][p]
     double* Z_bar;    // [N][p][n] or NULL: dll/dZ (dense design matrices only)
     double* traj;     // workspace [n_cta][Tobs][n n + n]
-    double* c0bar_ws;  // workspace [n_cta][n n]
+    double* c0bar_ws;  // workspace [n_cta][2][n n]: adjoint of R Q R', and R Q R' itself
 };
 
 // doubles of shared memory needed by kalman_grad_draw
 GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
     const int ld = ldim(n);
-    return (size_t)9 * n * ld + (size_t)5 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
+    return (size_t)8 * n * ld + (size_t)5 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
            k + nt + 8;
 }
 
@@ -166,8 +166,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     const int n = g.n, k = g.k, p = g.p, Tobs = g.Tobs, ld = ldim(n);
     const int tile = n * ld;
     double* Tm = sm;
-    double* C0 = Tm + tile;
-    double* P = C0 + tile;
+    double* P = Tm + tile;
     double* Pf = P + tile;
     double* L = Pf + tile;
     double* Pb = L + tile;   // adjoint of the predicted covariance
@@ -225,7 +224,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         return;
     }
     double* traj = g.traj + (size_t)cta * Tobs * (size_t)(n * n + n);
-    double* gC0b = g.c0bar_ws + (size_t)cta * n * n;
+    double* gC0b = g.c0bar_ws + (size_t)cta * 2 * n * n;
+    double* C0 = gC0b + n * n;  // R Q R' (read once per forward step): global, L2-resident, to keep the shared-memory footprint down
     const double* gT = g.T + (size_t)draw * n * n;
     const double* gR = g.R + (size_t)draw * n * k;
 
@@ -264,7 +264,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         const int lo = i < j ? i : j, hi = i < j ? j : i;
         double s = 0.0;
         for (int c = 0; c < k; ++c) s = fma(Rs[lo * k + c] * qs[c], Rs[hi * k + c], s);
-        C0[i * ld + j] = s;
+        C0[i * n + j] = s;
         P[i * ld + j] = s;
         L[i * ld + j] = Tm[i * ld + j];  // A_0 = T
     }
@@ -400,7 +400,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return W2[i * ld + k_]; }, [&](int k_, int j) { return Tm[j * ld + k_]; },
-              [&](int i, int j, double v_) { P[i * ld + j] = v_ + C0[i * ld + j]; });
+              [&](int i, int j, double v_) { P[i * ld + j] = v_ + C0[i * n + j]; });
         GFOR(i, n) a[i] = an[i];
         GSYNC();
     }
