@@ -462,7 +462,7 @@ class BatchedStateSpace:
         ll = torch.empty((N,), **f64)
         status = torch.empty((N,), dtype=torch.int32, device=dev)
         grad = torch.zeros((N, self.n_param), **f64)
-        nc = min(self.chunk, N, 16384)  # the gradient path keeps full-size adjoints per draw: smaller chunks
+        nc = min(self.chunk, N)  # (full-size adjoints per draw: ~50 KB per draw at n = 24, 3 GB per 65,536-draw chunk)
         ws = self._workspace(dev, nc)
         g = self._grad_ws
         if g is None or g["nc"] < nc or g["device"] != dev:
