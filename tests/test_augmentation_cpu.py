@@ -159,3 +159,56 @@ def test_observation_equation_errors_follow_the_reference():
         lin.parse_observation_equation("x", "not_a_parameter * Y[]")
     icpt, coeffs = lin.linearize_observation_equation(*lin.parse_observation_equation("x", "log(Y[]) - log(Y[-1])"))
     assert icpt == 0 and coeffs == {("Y", 0): 1, ("Y", -1): -1}
+
+
+# ------------------------------------------------------------------------------------------------ configure() host logic
+@pytest.fixture(scope="module")
+def rbc_statespace():
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    return lambda: BatchedStateSpace(CompiledModel("rbc"))  # builds (or finds) the generated Jacobian library; no device needed
+
+
+def test_configure_validation_follows_the_reference(rbc_statespace):
+    """Argument checks of DSGEStateSpace.configure (statespace.py:930-1005), same conditions and wording."""
+    ss = rbc_statespace()
+    with pytest.raises(ValueError, match="unknown observed states"):
+        ss.configure(observed_states=["Q"])
+    with pytest.raises(ValueError, match="stochastic singularity"):
+        ss.configure(observed_states=["Y", "C"])  # one shock, no measurement error
+    with pytest.raises(ValueError, match="measurement error on unobserved"):
+        ss.configure(observed_states=["Y"], measurement_error=["C"])
+    with pytest.raises(ValueError, match="ss_obs_intercept entries are not in observed_states"):
+        ss.configure(observed_states=["Y"], ss_obs_intercept=["C"])
+    with pytest.raises(ValueError, match="temporal_aggregation entries are not in observed_states"):
+        ss.configure(observed_states=["Y"], temporal_aggregation={"C": "sum"})
+    with pytest.raises(ValueError, match="aggregation_period must be >= 2"):
+        ss.configure(observed_states=["Y"], temporal_aggregation={"Y": "sum"}, aggregation_period=1)
+    with pytest.raises(ValueError, match="observation_equations entries are not in observed_states"):
+        ss.configure(observed_states=["Y"], observation_equations={"dY": "log(Y[])"})
+    with pytest.raises(ValueError, match="both observation_equations and ss_obs_intercept"):
+        ss.configure(observed_states=["dY"], measurement_error=["dY"], observation_equations={"dY": "log(Y[])"}, ss_obs_intercept=["dY"])
+    with pytest.raises(NotImplementedError, match="augmented state dimension"):
+        ss.configure(observed_states=["Y"], temporal_aggregation={"Y": "sum"}, aggregation_period=80)
+
+
+def test_configure_layout_and_parameter_names(rbc_statespace):
+    ss = rbc_statespace().configure(
+        observed_states=["Y", "dC"], measurement_error=["Y", "dC"], temporal_aggregation={"Y": "mean"}, aggregation_period=3,
+        ss_obs_intercept=["Y"], observation_equations={"dC": "log(C[]) - log(C[-1])"},
+    )  # fmt: skip
+    m = ss.model
+    # filter states: lagged variables + observed model variables + variables an observation equation refers to
+    names = [m.lin.vars_perm[int(u)] for u in ss.filter_vars]
+    assert {"Y", "C"} <= set(names) and ss.n_filter == len(names) < m.n
+    assert ss.aug.augmented_state_names[ss.n_filter :] == ["Y_cumulator_lag1", "Y_cumulator_lag2", "C_obs_lag1"]
+    assert ss.n_aug == ss.n_filter + 3 and ss.dense_Z.shape == (2, ss.n_aug)
+    assert np.count_nonzero(ss.dense_Z[0]) == 3 and np.allclose(ss.dense_Z[0][ss.dense_Z[0] != 0], 1 / 3)
+    assert not ss.dense_Z[1].any()  # the equation's row is written per draw by the generated observation kernel
+    assert ss.param_names == list(m.param_names) + ["sigma_epsilon_A" if "epsilon_A" in m.shock_names else f"sigma_{m.shock_names[0]}"] + [
+        "error_sigma_Y", "error_sigma_dC"]
+    full = rbc_statespace().configure(observed_states=["Y"], full_shock_covariance=True)
+    assert full.param_names[len(m.param_names) :] == ["state_cov[0,0]"]
+    # reduce_state=False keeps every variable, in solver order
+    allv = rbc_statespace().configure(observed_states=["Y"], reduce_state=False)
+    assert allv.n_filter == m.n and list(allv.filter_vars) == list(range(m.n))
