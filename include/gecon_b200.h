@@ -22,7 +22,8 @@
  *     gecon_get_last_error() returns a message for the calling thread's last failure.
  *   - Numerical failure is never an error code: it is reported per draw in `status` (bit field below), exactly as
  *     the reference reports it through flags / NaN fills / -inf potentials.
- *   - Supported sizes: 1 <= n <= 56, 0 <= k <= n, 1 <= p <= 8.
+ *   - Supported sizes: 1 <= n <= 64 (Blanchard-Kahn pencils and the general solve up to 88; the gradient path's filter up to 48),
+ *     0 <= k <= n, 1 <= p <= 8.
  */
 #ifndef GECON_B200_H
 #define GECON_B200_H
