@@ -71,6 +71,7 @@ class BatchedHMC:
         dh = torch.where(alive, h1 - h0, torch.full_like(h0, float("inf")))
         log_u = torch.log(torch.rand(th0.shape[0], generator=self.gen, dtype=th0.dtype, device=th0.device))
         accept = alive & (log_u < -dh)
+        self.last_accept_prob = torch.clamp(torch.exp(-dh), max=1.0)  # per chain; 0 for rejected-by-construction trajectories
         self.theta = torch.where(accept[:, None], th, th0)
         self.logp = torch.where(accept, lp, lp0)
         self.grad = torch.where(accept[:, None], g, g0)
@@ -88,6 +89,27 @@ class BatchedHMC:
         for _ in range(n_steps):
             self.step()
         return self.stats
+
+    def warmup(self, n_steps: int, target_accept: float = 0.8, gamma: float = 0.05, t0: float = 10.0, kappa: float = 0.75):
+        """Dual-averaging adaptation of the (common) step-size scale towards a mean acceptance probability of
+        ``target_accept`` over the population (Hoffman & Gelman 2014, section 3.2, with the population mean in place of a
+        single chain's statistic -- thousands of chains make it a low-noise signal).  Ends with the averaged step size."""
+        import math
+
+        mu = math.log(10.0 * self.step_scale)
+        log_eps_bar, h_bar = 0.0, 0.0
+        for m_ in range(1, n_steps + 1):
+            self.step()
+            alpha = float(self.last_accept_prob.mean())
+            h_bar = (1.0 - 1.0 / (m_ + t0)) * h_bar + (target_accept - alpha) / (m_ + t0)
+            log_eps = mu - math.sqrt(m_) / gamma * h_bar
+            eta = m_ ** (-kappa)
+            log_eps_bar = eta * log_eps + (1.0 - eta) * log_eps_bar
+            self.step_scale = math.exp(log_eps)
+            self.eps = self.step_scale * (self.hi - self.lo)
+        self.step_scale = math.exp(log_eps_bar)
+        self.eps = self.step_scale * (self.hi - self.lo)
+        return self.step_scale
 
 
 def statespace_target(statespace, Y, fixed_tail, phi: float = 1.0):

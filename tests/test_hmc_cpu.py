@@ -48,3 +48,19 @@ def test_leapfrog_is_reversible_and_rejects_outside_the_box_or_gated_points():
         assert torch.all(hmc.theta >= lo) and torch.all(hmc.theta <= hi)
         assert torch.all(hmc.theta[:, 0] <= 0.9) and torch.isfinite(hmc.logp).all()
     assert any(s.accept_rate < 1.0 for s in hmc.stats)  # some trajectories did leave the box / hit the gated region
+
+
+def test_dual_averaging_finds_a_step_size_with_the_target_acceptance():
+    torch.manual_seed(1)
+    d, N = 4, 2048
+    mu, sd = torch.zeros(d, dtype=torch.float64), torch.tensor([0.05, 0.1, 0.2, 0.4], dtype=torch.float64)
+    lo, hi = mu - 10 * sd, mu + 10 * sd
+    th0 = mu + sd * torch.randn((N, d), dtype=torch.float64)
+    for start in (1e-4, 0.2):  # far too small and far too large
+        hmc = BatchedHMC(_gaussian_target(mu, sd), lo, hi, step_scale=start, n_leapfrog=5, seed=2).initialise(th0)
+        eps = hmc.warmup(150, target_accept=0.8)
+        assert 1e-3 < eps < 0.2
+        hmc.stats.clear()
+        hmc.run(20)
+        acc = sum(s.accept_rate for s in hmc.stats) / len(hmc.stats)
+        assert 0.65 < acc < 0.95, (start, eps, acc)
