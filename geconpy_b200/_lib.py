@@ -13,6 +13,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CORE_LIB = PKG / "_lib" / "libgecon_b200.so"
+ABI_VERSION = 2  # include/gecon_b200.h: GECON_ABI_VERSION
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -82,6 +83,10 @@ class CrArgs(C.Structure):
         ("t_stride", C.c_int64),
         ("r_stride", C.c_int64),
         ("t_ld", C.c_int32),
+        ("lag_lo", C.c_int32),
+        ("lag_hi", C.c_int32),
+        ("lead_lo", C.c_int32),
+        ("lead_hi", C.c_int32),
         ("reserved1", C.c_int32),
     ]
 
@@ -156,6 +161,8 @@ class KalmanArgs(C.Structure):
         ("z_stride", C.c_int64),
         ("qfull", C.c_void_p),
         ("qfull_stride", C.c_int64),
+        ("mask_intercept", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -194,6 +201,8 @@ class KalmanGradArgs(C.Structure):
         ("d_bar", C.c_void_p),
         ("z_stride", C.c_int64),
         ("Z_bar", C.c_void_p),
+        ("mask_intercept", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -280,8 +289,8 @@ def load_library(path: os.PathLike | str | None = None) -> C.CDLL:
             raise GeconLibraryError(f"{p} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.gecon_abi_version() != 1:
-        raise GeconLibraryError(f"{p}: ABI version {lib.gecon_abi_version()} != 1")
+    if lib.gecon_abi_version() != ABI_VERSION:
+        raise GeconLibraryError(f"{p}: ABI version {lib.gecon_abi_version()} != {ABI_VERSION}")
     if path is None:
         _lib = lib
     return lib

@@ -105,7 +105,7 @@ class CycleReductionResult:
 
 
 def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None, subset=None, lead_idx=None,
-             solvability_norms=False, trunc_tol=1e-8) -> CycleReductionResult:
+             solvability_norms=False, trunc_tol=1e-8, col_ranges=None) -> CycleReductionResult:
     """Batched cycle reduction + R + residual (``gecon_cr_solve_*``).
 
     Reference: ``_cycle_reduction_core`` (gEconpy/solvers/cycle_reduction.py:127-183), ``pt_compute_selection_matrix``
@@ -114,6 +114,8 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     ``subset``: index list, outputs are the sub-blocks ``T[subset][:, subset]``, ``R[subset]``.
     ``lead_idx``: lead-variable columns; converged draws then carry ``ST_BK_CERTIFIED`` in ``status`` when the kernel
     could prove n_unstable == n_forward (``result.n_unstable`` = n_lead for those draws, -1 otherwise).
+    ``col_ranges`` = (lag_lo, lag_hi, lead_lo, lead_hi): the caller's promise that A is zero outside columns
+    [lag_lo, lag_hi) and C outside [lead_lo, lead_hi) (``gecon_cr_args.lag_lo`` ...); entries outside are not read.
     """
     if unperm is not None and subset is not None:
         raise ValueError("give at most one of unperm and subset")
@@ -147,6 +149,8 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
         n_lead=(0 if lead is None else int(lead.size)), lead_idx=pL, n_unstable=pNu,
         solv_norms=pSn, trunc_tol=float(trunc_tol),
     )  # fmt: skip
+    if col_ranges is not None:
+        args.lag_lo, args.lag_hi, args.lead_lo, args.lead_hi = (int(v) for v in col_ranges)
     lib = L.load_library()
     if m.device:
         L.check(lib.gecon_cr_solve_batched(C.byref(args), m.stream()), "gecon_cr_solve_batched")
@@ -280,6 +284,7 @@ def kalman_loglik(
     return_per_step=False,
     lyap_max_iter=0,
     Q=None,
+    mask_intercept=False,
 ):
     """Batched Kalman-filter log-likelihood (``gecon_kalman_ll_*``): returns (ll[N], status[N][, ll_t[N, Tobs]]).
 
@@ -319,7 +324,7 @@ def kalman_loglik(
         qfull_stride=(k * k if (Qa is not None and Qa.ndim == 3) else 0), N=N, n=n, k=k, p=p, Tobs=Tobs,
         jitter=float(jitter), missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1),
         lyap_max_iter=int(lyap_max_iter), status_in=pSin, gate_mask=int(gate_mask), ll=pll, status=pS, ll_t=pllt,
-        z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0),
+        z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0), mask_intercept=int(bool(mask_intercept)),
     )  # fmt: skip
     lib = L.load_library()
     if m.device:
@@ -333,7 +338,7 @@ def kalman_loglik(
 
 
 def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None, jitter=1e-8, missing_fill=-9999.0,
-                       mvn_const="per_obs", status_in=None, gate_mask=0, sigma_inputs=False, lyap_max_iter=0):
+                       mvn_const="per_obs", status_in=None, gate_mask=0, sigma_inputs=False, lyap_max_iter=0, mask_intercept=False):
     """Log-likelihood AND its gradient (``gecon_kalman_grad_*``): returns a dict with ``ll`` [N],
     ``status`` [N], ``T`` [N,n,n], ``R`` [N,n,k], ``q`` [N,k], ``h`` [N,p], ``d`` [N,p] -- the derivatives of ll with
     respect to the arguments of the same name (``q``/``h`` w.r.t. the standard deviations when ``sigma_inputs``) -- and,
@@ -370,6 +375,7 @@ def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None,
         missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1), lyap_max_iter=int(lyap_max_iter),
         status_in=pSin, gate_mask=int(gate_mask), sigma_inputs=int(bool(sigma_inputs)), ll=pll, status=pS, T_bar=pTb, R_bar=pRb,
         q_bar=pqb, h_bar=phb, d_bar=pdb, z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0), Z_bar=pZb,
+        mask_intercept=int(bool(mask_intercept)),
     )  # fmt: skip
     lib = L.load_library()
     if m.device:

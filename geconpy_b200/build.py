@@ -23,6 +23,9 @@ CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate
 # the Kalman kernel is instantiated for (NP, p) in 8 x 8 combinations: one object per padded dimension NP, built in parallel
 KALMAN_INST = "kalman_inst.cu"
 KALMAN_NPS = [8, 16, 24, 32, 40, 48, 56, 64]
+# the one-warp-per-draw cycle-reduction kernel: one object per padded dimension (every packed width C = 1 .. NP / 8)
+CR_WARP_INST = "cr_warp_inst.cu"
+CR_WARP_NPS = [8, 16, 24, 32]
 
 NVCC_FLAGS = [
     "-O3",
@@ -62,7 +65,7 @@ def _run(cmd):
 def build_core(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu -> _lib/libgecon_b200.so (skipped when the sources are unchanged)."""
     LIBDIR.mkdir(exist_ok=True)
-    deps = [CSRC / s for s in CORE_SOURCES + [KALMAN_INST]] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "gecon_b200.h"]
+    deps = [CSRC / s for s in CORE_SOURCES + [KALMAN_INST, CR_WARP_INST]] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "gecon_b200.h"]
     stamp = LIBDIR / "libgecon_b200.stamp"
     dig = _digest(deps, NVCC_FLAGS)
     if not force and CORE_LIB.exists() and stamp.exists() and stamp.read_text() == dig:
@@ -81,6 +84,7 @@ def build_core(force: bool = False, verbose: bool = False) -> Path:
 
     jobs = [(s, [], Path(s).stem) for s in CORE_SOURCES]
     jobs += [(KALMAN_INST, [f"-DGECON_KF_NP={np_}"], f"kalman_inst_np{np_}") for np_ in KALMAN_NPS]
+    jobs += [(CR_WARP_INST, [f"-DGECON_CW_NP={np_}"], f"cr_warp_inst_np{np_}") for np_ in CR_WARP_NPS]
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, jobs))
     _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CORE_LIB), *map(str, objs), "-lcudart"])

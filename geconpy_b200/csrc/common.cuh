@@ -91,6 +91,17 @@ struct DevBuf {
             return GECON_E_UNSUPPORTED_SIZE;        \
     }
 
+// one-warp-per-draw cycle reduction (cr_warp.cuh, instantiated in cr_warp_inst.cu once per padded dimension): packed
+// column ranges of the launch and the per-NP launchers (info != nullptr: only query {CTAs per SM, smem, threads})
+struct cw_ranges {
+    int o0, w0;  // lag columns: packed offset (even), packed width (hi - o0)
+    int o2, w2;  // lead columns
+};
+int cr_warp_launch_np8(const gecon_cr_args& a, const cw_ranges& rg, int c, cudaStream_t st, int* info);
+int cr_warp_launch_np16(const gecon_cr_args& a, const cw_ranges& rg, int c, cudaStream_t st, int* info);
+int cr_warp_launch_np24(const gecon_cr_args& a, const cw_ranges& rg, int c, cudaStream_t st, int* info);
+int cr_warp_launch_np32(const gecon_cr_args& a, const cw_ranges& rg, int c, cudaStream_t st, int* info);
+
 // pencil dimensions of the Blanchard-Kahn count (n + n_lead) and the general solve: 3 / 2 tiles, up to 88
 #define GECON_DISPATCH_NP_WIDE(np, ...)             \
     switch (np) {                                   \

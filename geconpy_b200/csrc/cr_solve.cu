@@ -391,6 +391,10 @@ static int check_cr_args(const gecon_cr_args* a) {
         set_last_error("gecon_cr_args: n_lead = %d out of range", a->n_lead);
         return GECON_E_BADARG;
     }
+    if (a->lag_lo < 0 || a->lag_hi < a->lag_lo || a->lag_hi > a->n || a->lead_lo < 0 || a->lead_hi < a->lead_lo || a->lead_hi > a->n) {
+        set_last_error("gecon_cr_args: column ranges [%d, %d), [%d, %d) out of order or beyond n", a->lag_lo, a->lag_hi, a->lead_lo, a->lead_hi);
+        return GECON_E_BADARG;
+    }
     if (a->k > round_up8(a->n)) {
         set_last_error("gecon_cr_args: k = %d exceeds the padded state dimension", a->k);
         return GECON_E_UNSUPPORTED_SIZE;
@@ -429,11 +433,54 @@ int cr_kernel_info(int n, int* ctas, int* smem, int* threads) {
 
 using namespace gecon;
 
+// One warp per draw (cr_warp.cuh) when the system is forward looking, fits a lane per row and the caller does not ask for
+// the diagnostics only the CTA-per-draw kernel produces.  c_out = packed width in column tiles, rg = packed ranges.
+// GECON_CR_KERNEL=cta|warp overrides the choice (warp: wherever it is eligible).
+static bool cr_warp_eligible(const gecon_cr_args& a, cw_ranges* rg, int* c_out) {
+    const int np = round_up8(a.n);
+    if (!a.C || np > 32 || a.solv_norms) return false;
+    const char* e = getenv("GECON_CR_KERNEL");
+    if (e && strcmp(e, "cta") == 0) return false;
+    const bool hint = (a.lag_hi > a.lag_lo) || (a.lead_hi > a.lead_lo);
+    rg->o0 = hint ? (a.lag_lo & ~1) : 0;
+    rg->w0 = hint ? a.lag_hi - rg->o0 : a.n;
+    rg->o2 = hint ? (a.lead_lo & ~1) : 0;
+    rg->w2 = hint ? a.lead_hi - rg->o2 : a.n;
+    const int kd = (a.D && a.R) ? a.k : 0;
+    const int nl = a.lead_idx ? a.n_lead : 0;
+    int w = rg->w0 > rg->w2 ? rg->w0 : rg->w2;
+    w = kd > w ? kd : w;
+    w = nl > w ? nl : w;
+    int c = (w + 7) / 8;
+    if (c < 1) c = 1;
+    if (8 * c > np) return false;
+    *c_out = c;
+    if (e && strcmp(e, "warp") == 0) return true;
+    return np <= 24;
+}
+
+static int launch_cr_warp(const gecon_cr_args& a, const cw_ranges& rg, int c, cudaStream_t st, int* info) {
+    switch (round_up8(a.n)) {
+        case 8: return cr_warp_launch_np8(a, rg, c, st, info);
+        case 16: return cr_warp_launch_np16(a, rg, c, st, info);
+        case 24: return cr_warp_launch_np24(a, rg, c, st, info);
+        case 32: return cr_warp_launch_np32(a, rg, c, st, info);
+        default: break;
+    }
+    set_last_error("cr_warp: padded dimension %d > 32", round_up8(a.n));
+    return GECON_E_UNSUPPORTED_SIZE;
+}
+
 extern "C" int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream) {
     int rc = check_cr_args(args);
     if (rc) return rc;
     if (args->N == 0) return 0;
     const int np = round_up8(args->n);
+    {
+        cw_ranges rg;
+        int c = 0;
+        if (cr_warp_eligible(*args, &rg, &c)) return launch_cr_warp(*args, rg, c, (cudaStream_t)stream, nullptr);
+    }
     GECON_DISPATCH_NP(np, return launch_cr<NP_>(*args, (cudaStream_t)stream));
     return 0;
 }

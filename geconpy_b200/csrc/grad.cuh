@@ -142,6 +142,7 @@ struct KalmanGradArgs {
     int mvn_const_mode, lyap_max_iter;
     const int32_t* status_in;
     int gate_mask, sigma_inputs;
+    int mask_intercept;  // 1: the intercept is masked at missing entries like Z and H
     double* ll;       // [N]
     int32_t* status;  // [N]
     double* T_bar;    // [N][n][n]
@@ -315,7 +316,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         GFOR(c, p) {
             double s = 0.0;
             for (int j = 0; j < n; ++j) s = fma(Zs[c * n + j], a[j], s);
-            v[c] = ym[c] - (dv[c] + w[c] * s);
+            v[c] = ym[c] - ((g.mask_intercept ? w[c] : 1.0) * dv[c] + w[c] * s);
         }
         GSYNC();
         GFOR(idx, p * p) {
@@ -493,7 +494,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GFOR(c, p) {
             hb[c] += w[c] * Fb[c * ps + c];
-            db[c] -= vb[c];
+            db[c] -= (g.mask_intercept ? w[c] : 1.0) * vb[c];
         }
         GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return L[k_ * ld + i]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
                     za = 0.0;
                     for (int j = 0; j < n; ++j) za = fma(s_Z[a * NP + j], aug ? W[j * LD + n] : s_a[j], za);
                 }
-                s_v[a] = (obs ? y[a] : 0.0) - (s_d[a] + (obs ? za : 0.0));
+                s_v[a] = (obs ? y[a] : 0.0) - (((obs || !p.mask_intercept) ? s_d[a] : 0.0) + (obs ? za : 0.0));
             }
             if (!sel) __syncthreads();  // dense Z: G below is formed from PZt
             // ---- phase 1b (warp 0): G, F = G + jitter I and its L D L' factorisation, all in registers

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
                 const double s = P[sym_off<NP>(obs_r[a], il)];
                 pz[a] = ob ? s : 0.0;
                 const double za = W[obs_r[a] * LD + n];
-                v[a] = (ob ? y[a] : 0.0) - (dv0[a] + (ob ? za : 0.0));
+                v[a] = (ob ? y[a] : 0.0) - (((ob || !p.mask_intercept) ? dv0[a] : 0.0) + (ob ? za : 0.0));
 #pragma unroll
                 for (int b = 0; b <= a; ++b) {
                     double x = P[sym_off<NP>(obs_r[a], obs_r[b])];

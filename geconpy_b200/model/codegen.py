@@ -122,6 +122,10 @@ class LinearizedModel:
         self.permuted_lead_var_idx = self.inv_var_order[self.lead_var_idx].astype(np.int32)
         # state (lagged) variables occupy one contiguous column block in solver order
         self.state_var_idx = np.flatnonzero(var_lag).astype(np.int32)
+        # ... and so do the lead variables: solver order is [static | lag only | lag and lead | lead only].  These are the
+        # structural non-zero column ranges of A and C handed to the solver kernel (gecon_cr_args.lag_lo ... lead_hi).
+        n_static, n_lagonly, n_mixed = (int(g_.sum()) for g_ in groups_v[:3])
+        self.col_ranges = (n_static, n_static + n_lagonly + n_mixed, n_static + n_lagonly, n)
 
         # ---- entries in solver order: rows eq_order, columns var_order; vars -> ss, shocks -> 0 (compile.py:196-202)
         to_ss = {}

@@ -64,6 +64,7 @@ class CompiledModel:
     eq_order = property(lambda self: self.lin.eq_order)
     inv_var_order = property(lambda self: self.lin.inv_var_order)
     permuted_lead_var_idx = property(lambda self: self.lin.permuted_lead_var_idx)
+    col_ranges = property(lambda self: self.lin.col_ranges)
 
     def theta_vector(self, **updates) -> np.ndarray:
         d = dict(self.lin.defaults)
@@ -149,6 +150,7 @@ class BatchedStateSpace:
         ss_obs_intercept: list | None = None,
         observation_equations: dict | None = None,
         full_shock_covariance: bool = False,
+        mask_intercept: bool = False,
     ):
         """Same meaning as ``DSGEStateSpace.configure`` (gEconpy/model/statespace.py:822-1090) for the arguments it
         shares: ``temporal_aggregation`` {"sum" | "mean" | "first" | "last"} with ``aggregation_period`` adds cumulator
@@ -157,7 +159,11 @@ class BatchedStateSpace:
         expression in model variables (``v[]``, ``v[-1]``, ``v[ss]``) and parameters} is linearised around the steady state into a
         parameter-dependent design-matrix row, an intercept and observation-lag states (statespace.py:390-556,652-694);
         ``full_shock_covariance`` replaces the k ``sigma_<shock>`` entries of the parameter vector by the k x k matrix
-        ``state_cov`` (row-major, used as Q directly: statespace.py:245-249)."""
+        ``state_cov`` (row-major, used as Q directly: statespace.py:245-249).  ``mask_intercept``: False = the observation
+        intercept is not masked at missing entries (SURVEY A.5's restatement of the upstream filter: a missing entry then
+        contributes -(d_i^2 / jitter + log jitter) / 2, which matters as soon as ``ss_obs_intercept`` meets missing data);
+        True = missing entries contribute nothing.  ``tests/golden/make_kalman_goldens.py`` records which one the installed
+        pymc_extras follows."""
         m = self.model
         if solver not in ("cycle_reduction", "gensys"):
             raise NotImplementedError(f"solver={solver!r}: the B200 path solves by cycle reduction (gensys maps to CR + BK flag)")
@@ -260,12 +266,14 @@ class BatchedStateSpace:
         self.check_bk = bool(check_bk)
         self.chunk = int(os.environ.get("GECON_CHUNK", chunk))
         self.full_covariance = bool(full_shock_covariance)
+        self.mask_intercept = bool(mask_intercept)
         self._n_cov = m.k * m.k if self.full_covariance else m.k
         cov_names = [f"state_cov[{i},{j}]" for i in range(m.k) for j in range(m.k)] if self.full_covariance else [f"sigma_{s}" for s in m.shock_names]
         self.param_names = list(m.param_names) + cov_names + [f"error_sigma_{v}" for v in measurement_error]
         self.n_param = len(self.param_names)
         self.configured = True
         self._ws = None
+        self._ws_extra = {}  # per-stream workspaces of the multi-stream pipeline: shapes depend on the configuration
         self._grad_ws = None
         return self
 
@@ -395,6 +403,7 @@ class BatchedStateSpace:
                 n_out=self.n_filter, n_lead=(int(ws["lead"].numel()) if self.check_bk else 0),
                 lead_idx=(ws["lead"].data_ptr() if self.check_bk else None), n_unstable=ws["n_unstable"].data_ptr(),
                 t_stride=self.n_aug * self.n_aug, r_stride=self.n_aug * m.k, t_ld=self.n_aug,
+                lag_lo=m.col_ranges[0], lag_hi=m.col_ranges[1], lead_lo=m.col_ranges[2], lead_hi=m.col_ranges[3],
             )  # fmt: skip
             e = mark("cr_solve")
             L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
@@ -422,7 +431,7 @@ class BatchedStateSpace:
                 Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
                 mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
                 gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),
-                ll_t=None,
+                ll_t=None, mask_intercept=int(self.mask_intercept),
             )  # fmt: skip
             e = mark("kalman_ll")
             L.check(lib.gecon_kalman_ll_batched(C.byref(kf), C.c_void_p(stream)), "gecon_kalman_ll_batched")
@@ -516,6 +525,7 @@ class BatchedStateSpace:
                 status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
                 n_out=0, n_lead=(int(ws["lead"].numel()) if self.check_bk else 0),
                 lead_idx=(ws["lead"].data_ptr() if self.check_bk else None), n_unstable=ws["n_unstable"].data_ptr(),
+                lag_lo=m.col_ranges[0], lag_hi=m.col_ranges[1], lead_lo=m.col_ranges[2], lead_hi=m.col_ranges[3],
             )  # fmt: skip
             e = mark("cr_solve")
             L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
@@ -543,7 +553,7 @@ class BatchedStateSpace:
                 missing_fill=self.missing_fill_value, mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0,
                 status_in=st.data_ptr(), gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(),
                 status=status[lo : lo + cnt].data_ptr(), T_bar=g["Tb_f"].data_ptr(), R_bar=g["Rb_f"].data_ptr(),
-                q_bar=g["qb"].data_ptr(), h_bar=g["hb"].data_ptr(), d_bar=g["db"].data_ptr(),
+                q_bar=g["qb"].data_ptr(), h_bar=g["hb"].data_ptr(), d_bar=g["db"].data_ptr(), mask_intercept=int(self.mask_intercept),
             )  # fmt: skip
             e = mark("kalman_grad")
             L.check(lib.gecon_kalman_grad_batched(C.byref(kg), C.c_void_p(stream)), "gecon_kalman_grad_batched")

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GECON_ABI_VERSION 1
+#define GECON_ABI_VERSION 2
 
 /* argument errors */
 #define GECON_E_BADARG (-1)
@@ -104,6 +104,15 @@ typedef struct gecon_cr_args {
     int64_t t_stride;       /* doubles between consecutive draws of T (0: n_out * n_out) */
     int64_t r_stride;       /* doubles between consecutive draws of R (0: n_out * k) */
     int32_t t_ld;           /* leading dimension of a draw's T (0: n_out) */
+    /* Structural column ranges (all four 0: none given).  A = d/dx_{t-1} has non-zero entries only in the columns of lagged
+     * variables and C = d/dx_{t+1} only in those of lead variables, and both sets are contiguous in the reference's solver
+     * order (gEconpy/model/perturbation.py:130-158, model/model.py:199-250).  When lag_hi > lag_lo or lead_hi > lead_lo the
+     * caller PROMISES that A (C) is zero outside columns [lag_lo, lag_hi) ([lead_lo, lead_hi)): entries outside are not
+     * read, and the one-warp-per-draw kernel keeps A0, A2, X0, X2 packed to those ranges (csrc/cr_warp.cuh). */
+    int32_t lag_lo;
+    int32_t lag_hi;
+    int32_t lead_lo;
+    int32_t lead_hi;
     int32_t reserved1;
 } gecon_cr_args;
 
@@ -205,6 +214,11 @@ typedef struct gecon_kalman_args {
                              [N][k][k] (qfull_stride = k k) or shared [k][k] (0); when given, qdiag is ignored (may be NULL)
                              and the state dimension runs on the CTA-per-draw kernel */
     int64_t qfull_stride;
+    int32_t mask_intercept; /* 0 (upstream StandardFilter as restated there): the intercept d is NOT masked at missing
+                               entries, v_i = 0 - d_i there.  1: missing entries have v_i = 0 (d masked like Z and H), the
+                               convention of a filter that drops missing rows.  tests/golden/make_kalman_goldens.py records which
+                               one the installed pymc_extras follows */
+    int32_t reserved2;
 } gecon_kalman_args;
 
 int gecon_kalman_ll_batched(const gecon_kalman_args* args, void* stream);
@@ -294,6 +308,8 @@ typedef struct gecon_kalman_grad_args {
     double* d_bar;    /* [N][p] out or NULL */
     int64_t z_stride; /* 0: Z shared by all draws; p * n: one design matrix per draw */
     double* Z_bar;    /* [N][p][n] out or NULL: dll/dZ (dense design matrices; the adjoint of observation equations) */
+    int32_t mask_intercept; /* as in gecon_kalman_args */
+    int32_t reserved2;
 } gecon_kalman_grad_args;
 
 int gecon_kalman_grad_batched(const gecon_kalman_grad_args* args, void* stream);

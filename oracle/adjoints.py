@@ -75,7 +75,8 @@ def dlyap_adjoint(T, P0, P0_bar, max_iter=64):
     return S, S @ T @ P0.T + S.T @ T @ P0
 
 
-def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, missing_fill=oss.MISSING_FILL, mvn_const="per_obs"):
+def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, missing_fill=oss.MISSING_FILL, mvn_const="per_obs",
+                           mask_intercept=False):
     """ll and its gradient with respect to T (n,n), R (n,k), q (k, shock VARIANCES), h (p, error VARIANCES), d (p).
 
     Forward pass as ``oracle.statespace.kalman_loglik`` (a0 = 0, P0 = dlyap(T, R diag(q) R'), d NOT masked), storing the
@@ -98,7 +99,7 @@ def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, 
         mask = np.isnan(y) | (y == missing_fill)
         w = (~mask).astype(np.float64)
         Zm, Hm, ym = w[:, None] * Z, np.diag(w * h), np.where(mask, 0.0, y)
-        v = ym - (d + Zm @ a)
+        v = ym - ((w * d if mask_intercept else d) + Zm @ a)
         PZ = P @ Zm.T
         F = Zm @ PZ + Hm + jitter * I_p
         Finv = np.linalg.inv(F)
@@ -122,7 +123,7 @@ def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, 
         mask = np.isnan(y) | (y == missing_fill)
         w = (~mask).astype(np.float64)
         Zm, Hm, ym = w[:, None] * Z, np.diag(w * h), np.where(mask, 0.0, y)
-        v = ym - (d + Zm @ a)
+        v = ym - ((w * d if mask_intercept else d) + Zm @ a)
         PZ = P @ Zm.T
         F = Zm @ PZ + Hm + jitter * I_p
         Finv = np.linalg.inv(F)
@@ -154,7 +155,7 @@ def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, 
         Hm_bar = Hm_bar + F_bar
         P_bar = P_bar + PZ_bar @ Zm
         a_bar = a_bar - Zm.T @ v_bar
-        d_bar -= v_bar
+        d_bar -= (w * v_bar) if mask_intercept else v_bar
         h_bar += w * np.diag(Hm_bar)
         # design matrix: L = I - K Zm, v = ym - d - Zm a, PZ = P Zm', G = Zm PZ   (Zm = diag(w) Z)
         Z_bar += w[:, None] * (-K.T @ L_bar - np.outer(v_bar, a) + PZ_bar.T @ P + F_bar @ PZ.T)

@@ -51,8 +51,13 @@ def kalman_loglik(
     missing_fill=MISSING_FILL,
     mvn_const="per_obs",
     return_all=False,
+    mask_intercept=False,
 ):
     """Standard (covariance-form) Kalman filter log-likelihood, SURVEY.md Appendix A.5.
+
+    ``mask_intercept``: False (A.5 as recorded: y_hat = d + Z_masked a, so a missing entry has v_i = -d_i against
+    F_ii = jitter); True: d is masked like Z and H (v_i = 0).  Which one upstream follows is recorded by
+    tests/golden/make_kalman_goldens.py wherever pymc_extras is installed.
 
     Y: (T_obs, p); T: (n,n); R: (n,k); Q: (k,k); Z: (p,n); H: (p,p); d: (p,) or None; c: (n,) or None.
     a0/P0 are the PREDICTED moments of the first observation (a0 = 0, P0 = dlyap by default).
@@ -79,7 +84,7 @@ def kalman_loglik(
             Hm = W @ H
             ym = np.where(mask, 0.0, y)
             # update
-            v = ym - (d + Zm @ a)
+            v = ym - ((W @ d if mask_intercept else d) + Zm @ a)
             PZt = P @ Zm.T
             F = Zm @ PZt + Hm + jitter * I_p
             try:
@@ -327,7 +332,7 @@ def append_obs_lag_block(T_aug, var_names, depths, starts):
 def loglik_augmented(
     model, theta, Y, observed, sigma_shock, sigma_err=None, temporal_aggregation=None, aggregation_period=4,
     ss_obs_intercept=None, log_linearized=None, tol=1e-8, max_iter=1000, solver_tol=1e-8, jitter=JITTER_DEFAULT,
-    mvn_const="per_obs", observation_equations=None,
+    mvn_const="per_obs", observation_equations=None, mask_intercept=False,
 ):  # fmt: skip
     """theta -> logp with temporal aggregation and steady-state intercepts: make_symbolic_graph's sequence
     (gEconpy/model/statespace.py:769-820) -- solve, un-permute, augment T and R, build Z and d, P0 of the AUGMENTED
@@ -374,7 +379,7 @@ def loglik_augmented(
     H = np.zeros((p, p)) if sigma_err is None else np.diag(np.asarray(sigma_err, dtype=np.float64) ** 2)
     with np.errstate(all="ignore"):
         P0 = dlyap(T_aug, R_aug @ Q @ R_aug.T)
-        ll_raw = kalman_loglik(Y, T_aug, R_aug, Q, Z, H, d=d, P0=P0, jitter=jitter, mvn_const=mvn_const) if np.all(np.isfinite(P0)) else np.nan
+        ll_raw = kalman_loglik(Y, T_aug, R_aug, Q, Z, H, d=d, P0=P0, jitter=jitter, mvn_const=mvn_const, mask_intercept=mask_intercept) if np.all(np.isfinite(P0)) else np.nan
     out = dict(base)
     out.update(T_aug=T_aug, R_aug=R_aug, Z=Z, d=d, P0=P0, ll_raw=ll_raw, ll=ll_raw if base["ok"] else -np.inf)
     return out

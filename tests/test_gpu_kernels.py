@@ -230,7 +230,9 @@ def test_dlyap_parity(B, name):
         assert np.abs(P[i] - (T[i] @ P[i] @ T[i].T + R[i] @ np.diag(q) @ R[i].T)).max() <= 1e-13 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc", 200), ("full_nk", 200), ("nk_complete_more_shocks", 50), ("nk_rbc_composite", 40)])
+# (the last two are BASELINE configs 4a / 4b at their own sample length, T_obs = 200)
+@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc", 200), ("full_nk", 200), ("nk_complete_more_shocks", 50), ("nk_rbc_composite", 40),
+                                       ("nk_complete_more_shocks", 200), ("nk_rbc_composite", 200)])
 @pytest.mark.parametrize("selector", [True, False])
 def test_kalman_parity(B, name, Tobs, selector):
     mod = model(name)

@@ -59,7 +59,9 @@ def _configure(compiled, name, reduce_state=True, with_err=True):
     return cm, mod, ss, observed, meas
 
 
-@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc_extended", 80), ("full_nk", 200), ("nk_complete_more_shocks", 60), ("nk_rbc_composite", 40)])
+# (the last two are BASELINE configs 4a / 4b at their own sample length, T_obs = 200)
+@pytest.mark.parametrize("name,Tobs", [("rbc", 100), ("rbc_extended", 80), ("full_nk", 200), ("nk_complete_more_shocks", 60), ("nk_rbc_composite", 40),
+                                       ("nk_complete_more_shocks", 200), ("nk_rbc_composite", 200)])
 @pytest.mark.parametrize("reduce_state", [True, False])
 def test_pipeline_loglik_matches_oracle(compiled, name, Tobs, reduce_state):
     """North-star tolerances: flags exact, |ll - oracle| <= 1e-7, failures gated to -inf on both sides."""
