@@ -87,7 +87,7 @@ class CrArgs(C.Structure):
         ("lag_hi", C.c_int32),
         ("lead_lo", C.c_int32),
         ("lead_hi", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("scan_semantics", C.c_int32),
     ]
 
 
@@ -262,6 +262,8 @@ EXPORTS = {
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p],
     ),
     "gecon_gemm_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
+    "gecon_real_eig_batched": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gecon_real_eig_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -105,7 +105,7 @@ class CycleReductionResult:
 
 
 def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=None, subset=None, lead_idx=None,
-             solvability_norms=False, trunc_tol=1e-8, col_ranges=None) -> CycleReductionResult:
+             solvability_norms=False, trunc_tol=1e-8, col_ranges=None, scan_semantics=False) -> CycleReductionResult:
     """Batched cycle reduction + R + residual (``gecon_cr_solve_*``).
 
     Reference: ``_cycle_reduction_core`` (gEconpy/solvers/cycle_reduction.py:127-183), ``pt_compute_selection_matrix``
@@ -116,6 +116,8 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     could prove n_unstable == n_forward (``result.n_unstable`` = n_lead for those draws, -1 otherwise).
     ``col_ranges`` = (lag_lo, lag_hi, lead_lo, lead_hi): the caller's promise that A is zero outside columns
     [lag_lo, lag_hi) and C outside [lead_lo, lead_hi) (``gecon_cr_args.lag_lo`` ...); entries outside are not read.
+    ``scan_semantics``: the conventions of the reference's scan twin (cycle_reduction.py:246-294) instead of the numba
+    core's: stop as soon as ||A0||_1 < tol, always solve for T, ``n_iter`` = the steps actually taken.
     """
     if unperm is not None and subset is not None:
         raise ValueError("give at most one of unperm and subset")
@@ -151,6 +153,7 @@ def cr_solve(A, B, C_, D=None, max_iter=1000, tol=1e-9, resid_tol=0.0, unperm=No
     )  # fmt: skip
     if col_ranges is not None:
         args.lag_lo, args.lag_hi, args.lead_lo, args.lead_hi = (int(v) for v in col_ranges)
+    args.scan_semantics = int(bool(scan_semantics))
     lib = L.load_library()
     if m.device:
         L.check(lib.gecon_cr_solve_batched(C.byref(args), m.stream()), "gecon_cr_solve_batched")
@@ -463,6 +466,36 @@ def gemm(A, B, trans_a=False, trans_b=False, alpha=1.0):
     else:
         L.check(lib.gecon_gemm_host(pA, pB, N, n, int(trans_a), int(trans_b), float(alpha), pC), "gecon_gemm_host")
     return out[0] if squeeze else out
+
+
+def real_eig(M, balance=True, sort=True):
+    """Eigenvalues of real general matrices ``M`` ((m, m) or (N, m, m); numpy or torch CUDA): ``(re, im, status)``.
+
+    ``gecon_real_eig_*``: balancing, Householder Hessenberg reduction and Francis double-shift QR, one warp per matrix.
+    ``sort``: ascending modulus, as ``RealEig.perform`` returns them (gEconpy/pytensorf/real_eig.py:31-36); ties (complex
+    pairs) keep the kernel's order, positive imaginary part first."""
+    m = _marshal_for(M)
+    M, pM = m.inp(M)
+    M, squeeze = _batch3(M)
+    N, n = M.shape[0], M.shape[1]
+    re, pre = m.out((N, n))
+    im, pim = m.out((N, n))
+    st, pS = m.out((N,), np.int32)
+    lib = L.load_library()
+    if m.device:
+        L.check(lib.gecon_real_eig_batched(pM, N, n, int(bool(balance)), pre, pim, pS, m.stream()), "gecon_real_eig_batched")
+    else:
+        L.check(lib.gecon_real_eig_host(pM, N, n, int(bool(balance)), pre, pim, pS), "gecon_real_eig_host")
+    if sort:
+        if m.device:
+            idx = torch.argsort(torch.hypot(re, im), dim=1, stable=True)
+            re, im = torch.gather(re, 1, idx), torch.gather(im, 1, idx)
+        else:
+            idx = np.argsort(np.hypot(re, im), axis=1, kind="stable")
+            re, im = np.take_along_axis(re, idx, 1), np.take_along_axis(im, idx, 1)
+    if squeeze:
+        return re[0], im[0], st[0]
+    return re, im, st
 
 
 def kernel_info(which: str, n: int, p: int = 1, Tobs: int = 1) -> dict:

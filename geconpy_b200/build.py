@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 MODEL_LIBDIR = LIBDIR / "models"
 CORE_LIB = LIBDIR / "libgecon_b200.so"
-CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu", "grad.cu"]
+CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu", "grad.cu", "eig.cu"]
 # the Kalman kernel is instantiated for (NP, p) in 8 x 8 combinations: one object per padded dimension NP, built in parallel
 KALMAN_INST = "kalman_inst.cu"
 KALMAN_NPS = [8, 16, 24, 32, 40, 48, 56, 64]
@@ -37,6 +37,8 @@ NVCC_FLAGS = [
     "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+# experiment hook: extra nvcc flags (e.g. GECON_NVCC_EXTRA="-DGECON_CW_EXPERIMENT_WPC=13"); part of the build digest
+NVCC_FLAGS += os.environ.get("GECON_NVCC_EXTRA", "").split()
 
 
 def find_nvcc() -> str:
@@ -99,10 +101,21 @@ def build_model(name: str, source: str, force: bool = False) -> Path:
     lib = MODEL_LIBDIR / f"libgecon_model_{name}_{dig}.so"
     if lib.exists() and not force:
         return lib
+    # several ranks (one process per GPU) may build the same model at once: write source and library under process-private
+    # names and move them into place atomically, so that nobody ever dlopens a half-written file
+    tag = f".{os.getpid()}.tmp"
     src = MODEL_LIBDIR / f"gecon_model_{name}_{dig}.cu"
-    src.write_text(source)
+    tmp_src, tmp_lib = src.with_name(src.name[:-3] + tag + ".cu"), lib.with_name(lib.name + tag)
+    tmp_src.write_text(source)
     nvcc = find_nvcc()
-    _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-o", str(lib), str(src), "-lcudart"])
+    try:
+        _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-o", str(tmp_lib), str(tmp_src), "-lcudart"])
+        os.replace(tmp_src, src)
+        os.replace(tmp_lib, lib)
+    finally:
+        for f in (tmp_src, tmp_lib):
+            if f.exists():
+                f.unlink()
     return lib
 
 

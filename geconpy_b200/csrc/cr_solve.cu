@@ -142,6 +142,10 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
                 __syncthreads();
                 a0n = norm1_fast<NP>(A0, s_red);
                 if (a0n < p.tol) {
+                    if (p.scan_semantics) {  // the scan twin tests ||A0||_1 only (cycle_reduction.py:268-273)
+                        converged = true;
+                        break;
+                    }
                     a2n = norm1_fast<NP>(A2, s_red + 4 * NP);
                     if (a2n < p.tol) {
                         converged = true;
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
                     break;
                 }
             }
+            if (p.scan_semantics && (status & GECON_ST_CR_NAN)) it = p.max_iter;  // the scan keeps stepping on NaNs to the end
             if (!converged) {
                 status |= GECON_ST_CR_NOT_CONVERGED;
                 if (p.norms) {  // diagnostics of the numpy twin's failure tuple (cycle_reduction.py:101-109)
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
         tile_load<NP>(A0, gA, n, n, n);
         tile_zero<NP>(X0);
         __syncthreads();
-        if (converged || !gC) {
+        if (converged || !gC || p.scan_semantics) {
             const bool ok = gj_solve_blocked<NP>(A1h, W, A0, X0, c0lo, c0hi, nullptr, nullptr, 0, 0, n, true, s_piv, s_flag);  // backward looking: A1h == B
             if (!ok) {
                 status |= GECON_ST_SINGULAR;
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
         __syncthreads();
         // One solve with W for both right-hand sides: D (-> R) and, for the Blanchard-Kahn certificate, the non-zero
         // columns of C (-> W^-1 C = -F, left in the A2 tile).
-        const bool want_cert = p.lead_idx && gC && converged && !(status & GECON_ST_SINGULAR);
+        const bool want_cert = p.lead_idx && gC && converged && !(status & (GECON_ST_SINGULAR | GECON_ST_CR_NAN));
         bool have_F = false;
         if ((gD && p.R) || want_cert) {
             for (int i = threadIdx.x; i < C::TILE; i += C::NT) W[i] = A1[i] + A1h[i];

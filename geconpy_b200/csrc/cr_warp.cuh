@@ -11,14 +11,20 @@
 // only in the lead columns [lead_lo, lead_hi) (contiguous in the reference's solver order, perturbation.py:130-158), and the
 // iteration preserves both ranges: A0, X0 = A1^-1 A0 and the accumulated correction of A1hat live in lag columns, A2 and
 // X2 in lead columns.  They are stored PACKED (column c of the range at packed column c - lo, lo rounded down to an even
-// number) in tiles of C column tiles, LDC = 8 C + 4:
-//   shared memory per warp   A1 (NP x LD), W (NP x LD, Gauss-Jordan workspace), X0 (NP x LDC), X2 (NP x LDC)
+// number), C column tiles each, next to the Gauss-Jordan workspace in ONE augmented tile:
+//   shared memory per warp   A1 (NP x LD)  and  WA = [W | X0 | X2]  (NP x LDW, LDW = NP + 16 C + 4)
 //   registers                the A-operand fragments of A0 and A2 (loaded before the in-place solve overwrites them with
 //                            X0, X2), the accumulated correction H = sum A2 X0 (A1hat = B - H)
-// Per iteration: [X0 | X2] = A1^-1 [A0 | A2] by blocked Gauss-Jordan (8-column panels, lane = row, pivots by redux.sync,
-// trailing updates as DMMA products with k = 8; the first block step reads A1 and writes W, so A1 needs no copy); four
-// DMMA products from the register fragments through the pivot-row map; A1 -= A0 X2 + A2 X0 read-modify-written in shared
-// memory; ||A0||_1 from the packed tile.  The tail (T, R, residual, certificate) reuses the four regions.
+// Per iteration: W <- A1; [X0 | X2] = A1^-1 [A0 | A2] by blocked Gauss-Jordan on the augmented tile (8-column panels, lane =
+// row, pivots by redux.sync, every trailing column tile updated by a DMMA product with k = 8); four DMMA products from the
+// register fragments through the pivot-row map; A1 -= A0 X2 + A2 X0 read-modify-written in shared memory; ||A0||_1 from the
+// packed block.  The tail (T, R, residual, certificate) reuses the same two regions.
+//
+// Code size is a first-class constraint here (first version, fully unrolled and inlined three times: 9.6 k SASS instructions,
+// ncu stall "no instruction" 5.3 warps per issue -- twelve warps at twelve different places of 150 KB of code against a
+// 32 KB L1.5 instruction cache): the Gauss-Jordan solve and the power bound are single __noinline__ functions, the pivot
+// loop of a panel is rolled (the panel registers rotate so that the current column is always a[0]), and the trailing update
+// is one loop over the column tiles of the augmented matrix.
 #pragma once
 #include "linalg.cuh"
 
@@ -28,13 +34,15 @@ template <int NP, int C>
 struct CwCfg {
     static_assert(NP % 8 == 0 && NP >= 8 && NP <= 32, "one lane per row: NP <= 32");
     static_assert(C >= 1 && 8 * C <= NP, "C column tiles");
-    static constexpr int LD = NP + 4;
-    static constexpr int LDC = 8 * C + 4;
-    static constexpr int NS = NP / 8;
-    static constexpr int KS = 2 * C;
-    static constexpr int TW = NP * LD, TC = NP * LDC;
-    static constexpr int PER_WARP_D = 2 * TW + 2 * TC;  // doubles (even)
-    static constexpr int PER_WARP_I = 2 * NP + 8;       // piv[NP], flag[NP], spare
+    static constexpr int LD = NP + 4;             // A1
+    static constexpr int LDW = NP + 16 * C + 4;   // augmented [W | Xa | Xb]
+    static constexpr int LDC = 8 * C + 4;         // packed tiles of the tail (T, certificate)
+    static constexpr int NS = NP / 8;             // row strips = column tiles of W
+    static constexpr int KS = 2 * C;              // k-steps spanned by a packed range
+    static constexpr int XA = NP, XB = NP + 8 * C;  // column offsets of the two right-hand-side blocks
+    static constexpr int TA1 = NP * LD, TWA = NP * LDW;
+    static constexpr int PER_WARP_D = TA1 + TWA;  // doubles (even)
+    static constexpr int PER_WARP_I = 2 * NP + 8; // piv[NP], flag[NP], spare
     static constexpr size_t bytes(int wpc) { return (size_t)wpc * (sizeof(double) * PER_WARP_D + sizeof(int) * PER_WARP_I) + sizeof(int) * 2 * NP; }
 };
 
@@ -47,129 +55,155 @@ __device__ __forceinline__ double cw_max_nonneg(double v) {
     return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
 }
 
-// global row-major rows x (columns [col_lo, col_hi)) -> zero-padded NP x LDT tile, one row per step (NP, LDT <= 36)
-template <int NP, int LDT>
-__device__ __forceinline__ void cw_load(double* __restrict__ dst, const double* __restrict__ src, int rows, int col_lo, int col_hi, int ldg, int lane) {
-    static_assert(LDT <= 64, "two lanes' worth of columns at most");
-#pragma unroll 4
-    for (int r = 0; r < NP; ++r) {
+// global row-major `rows` x (columns [col_lo, col_hi)) -> `width` columns of a tile with leading dimension ldt, zero padded to
+// NP rows; one row per step (width <= 64)
+template <int NP>
+__device__ __noinline__ void cw_load(double* __restrict__ dst, int ldt, int width, const double* __restrict__ src, int rows, int col_lo, int col_hi, int ldg,
+                                     int lane) {
+    for (int c = lane; c < width; c += 32) {
+        const int gc = col_lo + c;
+        const bool colok = gc < col_hi;
+#pragma unroll 1
+        for (int r0 = 0; r0 < NP; r0 += 8) {  // eight loads in flight per lane
+            double v[8];
 #pragma unroll
-        for (int h = 0; h < (LDT + 31) / 32; ++h) {
-            const int c = lane + 32 * h;
-            const int gc = col_lo + c;
-            const double v = (r < rows && gc < col_hi) ? src[(size_t)r * ldg + gc] : 0.0;
-            if (c < LDT) dst[r * LDT + c] = v;
+            for (int e = 0; e < 8; ++e) v[e] = (colok && r0 + e < rows) ? src[(size_t)(r0 + e) * ldg + gc] : 0.0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dst[(r0 + e) * ldt + c] = v[e];
         }
     }
 }
 
-template <int NP, int LDT>
-__device__ __forceinline__ void cw_zero(double* __restrict__ dst, int lane) {
-    for (int i = lane; i < NP * LDT; i += 32) dst[i] = 0.0;
-}
-
-// max absolute column sum of an NP x LDT tile whose padding is zero; every lane gets the result; NaN-propagating
-template <int NP, int LDT>
-__device__ __forceinline__ double cw_norm1(const double* __restrict__ M, int lane) {
+// max absolute column sum over `rows` rows x `width` columns (leading dimension ldt); every lane gets it; NaN-propagating
+static __device__ __noinline__ double cw_norm1(const double* __restrict__ M, int ldt, int rows, int width, int lane) {
     double mx = 0.0;
-#pragma unroll
-    for (int h = 0; h < (LDT + 31) / 32; ++h) {
-        const int c = lane + 32 * h;
-        double s = 0.0;
-        if (c < LDT) {
-#pragma unroll 8
-            for (int i = 0; i < NP; ++i) s += fabs(M[i * LDT + c]);
+    for (int c = lane; c < width; c += 32) {
+        double s0 = 0.0, s1 = 0.0;
+        int i = 0;
+        for (; i + 1 < rows; i += 2) {
+            s0 += fabs(M[i * ldt + c]);
+            s1 += fabs(M[(i + 1) * ldt + c]);
         }
+        if (i < rows) s0 += fabs(M[i * ldt + c]);
+        const double s = s0 + s1;
         mx = (s > mx || s != s) ? s : mx;
     }
     return cw_max_nonneg(mx);
 }
 
-// Blocked Gauss-Jordan by ONE warp: [Xa | Xb] <- M^-1 [Xa | Xb].  M is read from Ms during the first block step and
-// worked on in Md afterwards (Ms == Md allowed); Xa (nta column tiles, leading dimension LDA) and Xb (ntb, LDB) are
-// transformed in place.  Pivoting, panel arithmetic and the update formula are those of gj_solve_blocked (linalg.cuh):
-// rows are never swapped, solution row j ends up in row s_piv[j].  Returns false on a zero / non-finite pivot.
-template <int NP, int LDA, int LDB>
-__device__ __forceinline__ bool cw_gj(const double* Ms, double* Md, double* Xa, int nta, double* Xb, int ntb, int n, int* __restrict__ s_piv,
-                                      int* __restrict__ s_flag, int lane) {
-    constexpr int LD = NP + 4, NS = NP / 8;
+// Blocked Gauss-Jordan by ONE warp on the augmented tile WA = [M | Xa | Xb] (NP rows, leading dimension LDW): the
+// right-hand-side blocks (nta / ntb column tiles at column offsets XA / XB) are replaced by M^-1 [Xa | Xb]; M is destroyed.
+// Pivoting, panel arithmetic and the update formula are those of gj_solve_blocked (linalg.cuh): partial pivoting (largest
+// |.| among the rows not used yet, lowest row on ties), rows are never swapped, solution row j ends up in row s_piv[j].
+// Returns false on a zero / non-finite pivot (the blocks then hold garbage).
+template <int NP, int C>
+__device__ __noinline__ bool cw_gj(double* __restrict__ WA, int nta, int ntb, int n, int* __restrict__ s_piv, int* __restrict__ s_flag, int lane) {
+    using K = CwCfg<NP, C>;
+    constexpr int LDW = K::LDW, NS = K::NS;
     constexpr unsigned IDXBITS = 5u, IDXMASK = 31u;
     const int g = lane >> 2, q = lane & 3;
     const int nblk = (n + 7) >> 3;
     bool used = (lane >= n);
+    unsigned fail = 0u;
+#pragma unroll 1
     for (int kb = 0; kb < nblk; ++kb) {
         const int c0 = 8 * kb;
-        const bool first = (kb == 0);
-        const double* Mc = first ? Ms : Md;
         // ------------------------------------------------------------------------------------------ panel (lane = row)
+        // The row's 8 panel entries live in registers.  Per pivot step every row publishes [1 / a_u, other entries] in its own
+        // panel columns of WA (they are dead until the write-back below), the pivot row is found with one redux.sync and read
+        // back by every lane with four broadcast 16-byte loads: 10 shared-memory instructions instead of 18 shuffles and
+        // the 16 moves that reassemble doubles from them.  Steps are unrolled by four; the two register halves swap in between.
         {
             const int jmax = min(8, n - c0);
+            double* prow = WA + (lane < NP ? lane : 0) * LDW + c0;
             double a[8];
 #pragma unroll
             for (int c = 0; c < 8; c += 2) {
                 double2 t = make_double2(0.0, 0.0);
-                if (lane < NP) t = *reinterpret_cast<const double2*>(Mc + lane * LD + c0 + c);
+                if (lane < NP) t = *reinterpret_cast<const double2*>(prow + c);
                 a[c] = t.x;
                 a[c + 1] = t.y;
             }
             bool inP = false;
-            unsigned fail = 0u;
-            int myr = 0;
             double myinv = 1.0;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                if (jj < jmax) {  // warp-uniform
-                    const unsigned kk = ((unsigned)__double2hiint(fabs(a[jj])) & ~IDXMASK) | (IDXMASK - (unsigned)lane);
-                    const unsigned key = used ? 0u : kk;
-                    const double invo = rcp_nr(a[jj]);
-                    const unsigned best = __reduce_max_sync(0xffffffffu, key);
-                    const int r = (int)(IDXMASK - (best & IDXMASK));
-                    fail |= ((best >> IDXBITS) == 0u || best >= 0x7ff00000u) ? 1u : 0u;
-                    const double inv = shfl_f64(invo, r);
-                    double pr[8];
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = 4 * h + u;
+                    if (jj < jmax) {  // warp-uniform
+                        const unsigned kk = ((unsigned)__double2hiint(fabs(a[u])) & ~IDXMASK) | (IDXMASK - (unsigned)lane);
+                        const unsigned key = used ? 0u : kk;
+                        const double invo = rcp_nr2(a[u]);  // every row's own reciprocal: no division after the pivot search
+                        if (lane < NP) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c != jj) pr[c] = shfl_f64(a[c], r);
-                    const bool is_r = (lane == r);
-                    const double m = is_r ? 0.0 : a[jj] * inv;
+                            for (int c = 0; c < 8; c += 2)
+                                *reinterpret_cast<double2*>(prow + c) = make_double2(c == u ? invo : a[c], c + 1 == u ? invo : a[c + 1]);
+                        }
+                        const unsigned best = __reduce_max_sync(0xffffffffu, key);
+                        const int r = (int)(IDXMASK - (best & IDXMASK));
+                        fail |= ((best >> IDXBITS) == 0u || best >= 0x7ff00000u) ? 1u : 0u;  // zero / subnormal / inf / NaN pivot
+                        __syncwarp();
+                        double pv[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c != jj) a[c] = fma(-m, pr[c], a[c]);
-                    a[jj] = is_r ? 1.0 : -m;
-                    myinv = is_r ? inv : myinv;
-                    used = used || is_r;
-                    inP = inP || is_r;
-                    if (lane == jj) myr = r;
+                        for (int c = 0; c < 8; c += 2) {
+                            const double2 t = *reinterpret_cast<const double2*>(WA + r * LDW + c0 + c);
+                            pv[c] = t.x;
+                            pv[c + 1] = t.y;
+                        }
+                        __syncwarp();  // the next step's publication overwrites these rows
+                        const bool is_r = (lane == r);
+                        const double m = is_r ? 0.0 : a[u] * pv[u];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c != u) a[c] = fma(-m, pv[c], a[c]);
+                        a[u] = is_r ? 1.0 : -m;
+                        myinv = is_r ? pv[u] : myinv;
+                        used = used || is_r;
+                        inP = inP || is_r;
+                        if (lane == 0) s_piv[c0 + jj] = r;
+                    } else if (lane == 0) {
+                        s_piv[c0 + jj] = 0;  // padding column: any valid row (its coefficient is zero)
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double t = a[c];
+                    a[c] = a[c + 4];
+                    a[c + 4] = t;
                 }
             }
-            if (fail) return false;  // warp-uniform
+            // pivot rows are scaled by 1 / pivot once, here (commutes with the later eliminations acting on them)
             if (lane < NP) {
 #pragma unroll
-                for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(Md + lane * LD + c0 + c) = make_double2(a[c] * myinv, a[c + 1] * myinv);
+                for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(prow + c) = make_double2(a[c] * myinv, a[c + 1] * myinv);
                 s_flag[lane] = inP ? 1 : 0;
             }
-            if (lane < 8) s_piv[c0 + lane] = myr;
         }
         __syncwarp();
         // ------------------------------------------------------------------------------------------ update (DMMA, k = 8)
+        // every live column tile: rows <- [not a pivot row of this panel] old rows + W_panel . old pivot rows
         double a0[NS], a1[NS];
         bool keep[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const int r = 8 * s + g;
-            a0[s] = Md[r * LD + c0 + q];
-            a1[s] = Md[r * LD + c0 + 4 + q];
+            a0[s] = WA[r * LDW + c0 + q];
+            a1[s] = WA[r * LDW + c0 + 4 + q];
             keep[s] = (s_flag[r] == 0);
         }
-        const int p0 = s_piv[c0 + q], p1 = s_piv[c0 + 4 + q];
-        // one 8-column tile: rows <- [not a pivot row] old rows + W . old pivot rows
-        auto upd = [&](const double* src, double* dst, int ld, bool inplace) {
-            const double b0 = src[p0 * ld + g], b1 = src[p1 * ld + g];
+        const int p0 = s_piv[c0 + q] * LDW + g, p1 = s_piv[c0 + 4 + q] * LDW + g;
+        const int ro = g * LDW + 2 * q;
+#pragma unroll 1
+        for (int ct = kb + 1; ct < NS + 2 * C; ++ct) {
+            if (ct < NS ? (ct >= nblk) : (ct < NS + C ? (ct - NS >= nta) : (ct - NS - C >= ntb))) continue;  // warp-uniform
+            double* tile = WA + 8 * ct;
+            const double b0 = tile[p0], b1 = tile[p1];
             double acc[NS][2];
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 double2 o = make_double2(0.0, 0.0);
-                if (keep[s]) o = *reinterpret_cast<const double2*>(src + (8 * s + g) * ld + 2 * q);
+                if (keep[s]) o = *reinterpret_cast<const double2*>(tile + 8 * s * LDW + ro);
                 acc[s][0] = o.x;
                 acc[s][1] = o.y;
             }
@@ -177,24 +211,20 @@ __device__ __forceinline__ bool cw_gj(const double* Ms, double* Md, double* Xa, 
             for (int s = 0; s < NS; ++s) dmma884(acc[s][0], acc[s][1], a0[s], b0);
 #pragma unroll
             for (int s = 0; s < NS; ++s) dmma884(acc[s][0], acc[s][1], a1[s], b1);
-            if (inplace) __syncwarp();
+            __syncwarp();  // in place: every lane has read the pivot rows before anybody overwrites them
 #pragma unroll
-            for (int s = 0; s < NS; ++s) *reinterpret_cast<double2*>(dst + (8 * s + g) * ld + 2 * q) = make_double2(acc[s][0], acc[s][1]);
-        };
-        const bool m_inplace = !(first && Ms != Md);
-        for (int ct = kb + 1; ct < nblk; ++ct) upd(Mc + 8 * ct, Md + 8 * ct, LD, m_inplace);
-        for (int ct = 0; ct < nta; ++ct) upd(Xa + 8 * ct, Xa + 8 * ct, LDA, true);
-        for (int ct = 0; ct < ntb; ++ct) upd(Xb + 8 * ct, Xb + 8 * ct, LDB, true);
+            for (int s = 0; s < NS; ++s) *reinterpret_cast<double2*>(tile + 8 * s * LDW + ro) = make_double2(acc[s][0], acc[s][1]);
+        }
         __syncwarp();
     }
-    return true;
+    return fail == 0u;
 }
 
 // acc[s][ct] += af[s][ks] * X[rowmap(kbase + 4 ks + q)][8 ct + g]  for ks < nks, ct < nct: the product of a matrix whose
-// A-operand fragments are in registers with the rows of a packed tile, read through the pivot-row map (rows >= n read row 0
-// against a zero fragment).
-template <int NP, int C, int LDX>
-__device__ __forceinline__ void cw_prod(double (&acc)[NP / 8][C][2], const double (&af)[NP / 8][2 * C], const double* __restrict__ X,
+// A-operand fragments are in registers with the rows of a packed block (leading dimension ldx), read through the pivot-row
+// map (rows >= n read row 0 against a zero fragment).
+template <int NP, int C>
+__device__ __forceinline__ void cw_prod(double (&acc)[NP / 8][C][2], const double (&af)[NP / 8][2 * C], const double* __restrict__ X, int ldx,
                                         const int* __restrict__ rowmap, int kbase, int nks, int nct, int n, int lane) {
     constexpr int NS = NP / 8, KS = 2 * C;
     const int g = lane >> 2, q = lane & 3;
@@ -203,7 +233,7 @@ __device__ __forceinline__ void cw_prod(double (&acc)[NP / 8][C][2], const doubl
         if (ks < nks) {
             const int k = kbase + 4 * ks + q;
             const int row = (k < n) ? (rowmap ? rowmap[k] : k) : 0;
-            const double* xr = X + row * LDX + g;
+            const double* xr = X + row * ldx + g;
 #pragma unroll
             for (int ct = 0; ct < C; ++ct) {
                 if (ct < nct) {
@@ -224,21 +254,21 @@ __device__ __forceinline__ void cw_acc_zero(double (&acc)[NS][C][2]) {
         for (int ct = 0; ct < C; ++ct) acc[s][ct][0] = acc[s][ct][1] = 0.0;
 }
 
-// acc-layout element (row 8 s + g, packed columns 8 ct + 2 q + {0,1}) of a packed tile
-template <int NS, int C, int LDX>
-__device__ __forceinline__ void cw_acc_store_neg(const double (&acc)[NS][C][2], double* __restrict__ X, int nct, int lane) {
+// packed block <- -acc   (accumulator layout: row 8 s + g, packed columns 8 ct + 2 q + {0,1})
+template <int NS, int C>
+__device__ __forceinline__ void cw_acc_store_neg(const double (&acc)[NS][C][2], double* __restrict__ X, int ldx, int nct, int lane) {
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
         for (int ct = 0; ct < C; ++ct)
-            if (ct < nct) *reinterpret_cast<double2*>(X + (8 * s + g) * LDX + 8 * ct + 2 * q) = make_double2(-acc[s][ct][0], -acc[s][ct][1]);
+            if (ct < nct) *reinterpret_cast<double2*>(X + (8 * s + g) * ldx + 8 * ct + 2 * q) = make_double2(-acc[s][ct][0], -acc[s][ct][1]);
 }
 
-// M[:, off + packed column] -= acc  (full-width tile, leading dimension LD; off even; columns >= NP skipped: they hold zeros)
+// M[:, off + packed column] -= acc  (full-width matrix with leading dimension ldm; off even; columns >= NP skipped: zeros)
 template <int NP, int C>
-__device__ __forceinline__ void cw_sub_into(double* __restrict__ M, const double (&acc)[NP / 8][C][2], int off, int nct, int lane) {
-    constexpr int LD = NP + 4, NS = NP / 8;
+__device__ __forceinline__ void cw_sub_into(double* __restrict__ M, int ldm, const double (&acc)[NP / 8][C][2], int off, int nct, int lane) {
+    constexpr int NS = NP / 8;
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int ct = 0; ct < C; ++ct) {
@@ -247,7 +277,7 @@ __device__ __forceinline__ void cw_sub_into(double* __restrict__ M, const double
             if (col < NP) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    double2* ptr = reinterpret_cast<double2*>(M + (8 * s + g) * LD + col);
+                    double2* ptr = reinterpret_cast<double2*>(M + (8 * s + g) * ldm + col);
                     double2 v = *ptr;
                     v.x -= acc[s][ct][0];
                     v.y -= acc[s][ct][1];
@@ -256,6 +286,48 @@ __device__ __forceinline__ void cw_sub_into(double* __restrict__ M, const double
             }
         }
     }
+}
+
+// Is rho(Z) < 1 provable by a power of Z having 1-norm < 1?  Z: s x s (s <= 8 C) in a tile of leading dimension LDC whose
+// padding (up to 8 ceil(s/8) rows and columns) is zero; Zb: scratch tile of the same shape (zeroed here).  Repeated squaring
+// on the tensor path, norms inspected at the start and after every second squaring; growing powers / NaN give up.
+template <int C>
+__device__ __noinline__ bool cw_power_bound(double* Z, double* Zb, int s, int lane) {
+    constexpr int LDC = 8 * C + 4;
+    if (s == 0) return true;
+    const int g = lane >> 2, q = lane & 3;
+    const int nk = (s + 3) >> 2, nc = (s + 7) >> 3;
+    for (int i = lane; i < 8 * nc * LDC; i += 32) Zb[i] = 0.0;
+    __syncwarp();
+#pragma unroll 1
+    for (int sq = 0; sq <= 14; ++sq) {
+        if ((sq & 1) == 0 || sq == 14) {
+            const double nrm = cw_norm1(Z, LDC, s, s, lane);
+            if (nrm < 1.0) return true;
+            if (!(nrm < 1e100) || sq == 14) return false;
+        }
+#pragma unroll 1
+        for (int st = 0; st < nc; ++st) {  // row strip st of Zb = Z Z
+            double acc[C][2];
+#pragma unroll
+            for (int ct = 0; ct < C; ++ct) acc[ct][0] = acc[ct][1] = 0.0;
+            for (int ks = 0; ks < nk; ++ks) {
+                const int kk = 4 * ks + q;
+                const double a = Z[(8 * st + g) * LDC + kk];
+#pragma unroll
+                for (int ct = 0; ct < C; ++ct)
+                    if (ct < nc) dmma884(acc[ct][0], acc[ct][1], a, Z[kk * LDC + 8 * ct + g]);
+            }
+#pragma unroll
+            for (int ct = 0; ct < C; ++ct)
+                if (ct < nc) *reinterpret_cast<double2*>(Zb + (8 * st + g) * LDC + 8 * ct + 2 * q) = make_double2(acc[ct][0], acc[ct][1]);
+        }
+        __syncwarp();
+        double* t = Z;
+        Z = Zb;
+        Zb = t;
+    }
+    return false;
 }
 
 // resident CTAs of WPC warps per SM that shared memory allows: the register allocator is held to that (at most 255 registers,
@@ -270,14 +342,14 @@ constexpr int cw_min_ctas() {
 template <int NP, int C, int WPC>
 __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_kernel(const gecon_cr_args p, const cw_ranges rg) {
     using K = CwCfg<NP, C>;
-    constexpr int LD = K::LD, LDC = K::LDC, NS = K::NS, KS = K::KS, TW = K::TW, TC = K::TC;
+    constexpr int LD = K::LD, LDW = K::LDW, LDC = K::LDC, NS = K::NS, KS = K::KS, XA = K::XA, XB = K::XB;
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     double* A1 = sm + (size_t)warp * K::PER_WARP_D;
-    double* W = A1 + TW;
-    double* X0 = W + TW;
-    double* X2 = X0 + TC;
+    double* WA = A1 + K::TA1;
+    double* X0 = WA + XA;  // packed lag-column block  (leading dimension LDW)
+    double* X2 = WA + XB;  // packed lead-column block
     int* ibase = reinterpret_cast<int*>(sm + (size_t)WPC * K::PER_WARP_D);
     int* s_piv = ibase + warp * K::PER_WARP_I;
     int* s_flag = s_piv + NP;
@@ -299,6 +371,7 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
     const int kd = (p.D && p.R) ? k : 0;
     const int ntd = (kd + 7) >> 3;
     const long long stride = (long long)gridDim.x * WPC;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
     for (long long draw = (long long)blockIdx.x * WPC + warp; draw < p.N; draw += stride) {
         const double* gA = p.A + (size_t)draw * n * n;
@@ -316,33 +389,38 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
                 }
             }
         }
-        cw_load<NP, LD>(A1, gB, n, 0, n, n, lane);
-        cw_load<NP, LDC>(X0, gA, n, o0, o0 + w0, n, lane);
-        cw_load<NP, LDC>(X2, gC, n, o2, o2 + w2, n, lane);
+        cw_load<NP>(A1, LD, LD, gB, n, 0, n, n, lane);
+        cw_load<NP>(X0, LDW, 8 * C, gA, n, o0, o0 + w0, n, lane);
+        cw_load<NP>(X2, LDW, 8 * C + 4, gC, n, o2, o2 + w2, n, lane);  // (+ 4: the tile's padding columns)
         double H[NS][C][2];  // sum of A2 X0 over the iterations: A1hat = B - H on the lag columns
         cw_acc_zero<NS, C>(H);
         __syncwarp();
 
         int status = 0;
-        bool converged = false;
+        bool converged = false, gj_failed = false;
         int it = 0;
         double a0n = 0.0, a2n = 0.0;
-        bool gj_failed = false;
+#pragma unroll 1
         while (it < p.max_iter) {
             ++it;
-            // A-operand fragments of A0, A2 (the solve below overwrites the tiles with X0, X2)
+            // A-operand fragments of A0, A2 (the solve below overwrites the blocks with X0, X2), and W <- A1
             double a0f[NS][KS], a2f[NS][KS];
 #pragma unroll
             for (int s = 0; s < NS; ++s)
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    a0f[s][ks] = X0[(8 * s + g) * LDC + 4 * ks + q];
-                    a2f[s][ks] = X2[(8 * s + g) * LDC + 4 * ks + q];
+                    a0f[s][ks] = X0[(8 * s + g) * LDW + 4 * ks + q];
+                    a2f[s][ks] = X2[(8 * s + g) * LDW + 4 * ks + q];
                 }
+#pragma unroll 2
+            for (int i = lane; i < NP * (NP / 2); i += 32) {
+                const int r = i / (NP / 2), c2 = i - r * (NP / 2);
+                *reinterpret_cast<double2*>(WA + r * LDW + 2 * c2) = *reinterpret_cast<const double2*>(A1 + r * LD + 2 * c2);
+            }
             __syncwarp();
-            const bool ok = cw_gj<NP, LDC, LDC>(A1, W, X0, nt0, X2, nt2, n, s_piv, s_flag, lane);
-            if (!ok) {  // LAPACK: singular U -> inf / NaN in getrs -> NaN norm -> the loop stops (cycle_reduction.py:170-176)
-                a0n = __longlong_as_double(0x7ff8000000000000ll);
+            if (!cw_gj<NP, C>(WA, nt0, nt2, n, s_piv, s_flag, lane)) {
+                // LAPACK: singular U -> inf / NaN in getrs -> NaN norm -> the loop stops (cycle_reduction.py:170-176)
+                a0n = qnan;
                 status |= GECON_ST_CR_NAN;
                 gj_failed = true;
                 break;
@@ -351,7 +429,7 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
             {
                 double m20[NS][C][2];
                 cw_acc_zero<NS, C>(m20);
-                cw_prod<NP, C, LDC>(m20, a2f, X0, s_piv, o2, nk2, nt0, n, lane);
+                cw_prod<NP, C>(m20, a2f, X0, LDW, s_piv, o2, nk2, nt0, n, lane);
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -359,26 +437,30 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
                         H[s][ct][0] += m20[s][ct][0];
                         H[s][ct][1] += m20[s][ct][1];
                     }
-                cw_sub_into<NP, C>(A1, m20, o0, nt0, lane);
+                cw_sub_into<NP, C>(A1, LD, m20, o0, nt0, lane);
             }
             __syncwarp();  // the two read-modify-write passes over A1 may touch the same elements from different lanes
             {
                 double m02[NS][C][2];
                 cw_acc_zero<NS, C>(m02);
-                cw_prod<NP, C, LDC>(m02, a0f, X2, s_piv, o0, nk0, nt2, n, lane);
-                cw_sub_into<NP, C>(A1, m02, o2, nt2, lane);
+                cw_prod<NP, C>(m02, a0f, X2, LDW, s_piv, o0, nk0, nt2, n, lane);
+                cw_sub_into<NP, C>(A1, LD, m02, o2, nt2, lane);
             }
             cw_acc_zero<NS, C>(m00);
             cw_acc_zero<NS, C>(m22);
-            cw_prod<NP, C, LDC>(m00, a0f, X0, s_piv, o0, nk0, nt0, n, lane);
-            cw_prod<NP, C, LDC>(m22, a2f, X2, s_piv, o2, nk2, nt2, n, lane);
+            cw_prod<NP, C>(m00, a0f, X0, LDW, s_piv, o0, nk0, nt0, n, lane);
+            cw_prod<NP, C>(m22, a2f, X2, LDW, s_piv, o2, nk2, nt2, n, lane);
             __syncwarp();  // every lane is done reading X0, X2
-            cw_acc_store_neg<NS, C, LDC>(m00, X0, nt0, lane);
-            cw_acc_store_neg<NS, C, LDC>(m22, X2, nt2, lane);
+            cw_acc_store_neg<NS, C>(m00, X0, LDW, nt0, lane);
+            cw_acc_store_neg<NS, C>(m22, X2, LDW, nt2, lane);
             __syncwarp();
-            a0n = cw_norm1<NP, LDC>(X0, lane);
+            a0n = cw_norm1(X0, LDW, NP, 8 * C, lane);
             if (a0n < p.tol) {
-                a2n = cw_norm1<NP, LDC>(X2, lane);
+                if (p.scan_semantics) {  // the scan twin tests ||A0||_1 only (cycle_reduction.py:268-273)
+                    converged = true;
+                    break;
+                }
+                a2n = cw_norm1(X2, LDW, NP, 8 * C, lane);
                 if (a2n < p.tol) {
                     converged = true;
                     break;
@@ -388,12 +470,13 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
                 break;
             }
         }
+        if (p.scan_semantics && (status & GECON_ST_CR_NAN)) it = p.max_iter;  // the scan keeps stepping on NaNs to the end
         double a1n = 0.0;
         if (!converged) {
             status |= GECON_ST_CR_NOT_CONVERGED;
             if (p.norms) {  // diagnostics of the numpy twin's failure tuple (cycle_reduction.py:101-109)
-                a2n = cw_norm1<NP, LDC>(X2, lane);
-                a1n = cw_norm1<NP, LD>(A1, lane);
+                a2n = cw_norm1(X2, LDW, NP, 8 * C, lane);
+                a1n = cw_norm1(A1, LD, NP, NP, lane);
                 if (gj_failed) a2n = a1n = a0n;  // a failed solve NaN-fills everything downstream (LAPACK: inf / NaN from getrs)
             }
         }
@@ -404,50 +487,47 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
         }
         __syncwarp();
 
-        // ---- tail.  The iterated A0, A1, A2 are dead; the four regions are reused:
-        //   W   B - H (= A1hat), then B + C T       X0  A (right-hand side), then C's lead columns
-        //   X2  T (natural row order)                A1  D -> R, then certificate scratch
-        // T = -A1hat^-1 A (cycle_reduction.py:181); 0 if not converged.  T's non-zero columns are the lag columns: packed tile.
-        double* Tt = X2;
-        bool t_nan = false;
-        if (converged) {
-            cw_load<NP, LD>(W, gB, n, 0, n, n, lane);
-            cw_load<NP, LDC>(X0, gA, n, o0, o0 + w0, n, lane);
+        // ---- tail.  The iterated A0, A1, A2 are dead; the two regions are reused:
+        //   WA   [B - H | A] -> solve -> T;  then [B + C T | D | C] -> solve -> R, W^-1 C        A1 region   T (packed, LDC)
+        // T = -A1hat^-1 A (cycle_reduction.py:181); 0 if not converged.  T's non-zero columns are the lag columns.
+        double* Tt = A1;
+        bool t_nan = (p.scan_semantics && gj_failed);                         // (... from NaN-filled matrices after a failed solve)
+        const bool solve_t = converged || (p.scan_semantics && !gj_failed);  // the scan twin always solves for T
+        if (solve_t) {
+            cw_load<NP>(WA, LDW, NP, gB, n, 0, n, n, lane);
+            cw_load<NP>(X0, LDW, 8 * C, gA, n, o0, o0 + w0, n, lane);
             __syncwarp();
-            cw_sub_into<NP, C>(W, H, o0, nt0, lane);
+            cw_sub_into<NP, C>(WA, LDW, H, o0, nt0, lane);
             __syncwarp();
-            const bool ok = cw_gj<NP, LDC, LDC>(W, W, X0, nt0, nullptr, 0, n, s_piv, s_flag, lane);
-            if (!ok) {
+            if (!cw_gj<NP, C>(WA, nt0, 0, n, s_piv, s_flag, lane)) {
                 status |= GECON_ST_SINGULAR;
                 t_nan = true;
             }
         }
-        {
-            const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-            for (int i = lane; i < TC; i += 32) {
-                const int r = i / LDC, c = i - r * LDC;
-                double v = 0.0;
-                if (t_nan) v = qnan;
-                else if (converged && r < n) v = -X0[s_piv[r] * LDC + c];  // natural row order and the sign
-                Tt[i] = v;
-            }
+#pragma unroll 1
+        for (int i = lane; i < NP * LDC; i += 32) {
+            const int r = i / LDC, c = i - r * LDC;
+            double v = 0.0;
+            if (t_nan) v = qnan;
+            else if (solve_t && r < n && c < 8 * C) v = -X0[s_piv[r] * LDW + c];  // natural row order and the sign
+            Tt[i] = v;
         }
         __syncwarp();
 
         // ---- W = B + C T (only the lag columns differ from B); resid = sum((A + W T)^2) = sum((A + B T + C T T)^2)
-        cw_load<NP, LD>(W, gB, n, 0, n, n, lane);
-        cw_load<NP, LDC>(X0, gC, n, o2, o2 + w2, n, lane);
+        cw_load<NP>(WA, LDW, NP, gB, n, 0, n, n, lane);
+        cw_load<NP>(X2, LDW, 8 * C, gC, n, o2, o2 + w2, n, lane);
         __syncwarp();
         {
             double cf[NS][KS];
 #pragma unroll
             for (int s = 0; s < NS; ++s)
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) cf[s][ks] = -X0[(8 * s + g) * LDC + 4 * ks + q];
+                for (int ks = 0; ks < KS; ++ks) cf[s][ks] = -X2[(8 * s + g) * LDW + 4 * ks + q];
             double ct[NS][C][2];
             cw_acc_zero<NS, C>(ct);
-            cw_prod<NP, C, LDC>(ct, cf, Tt, nullptr, o2, nk2, nt0, n, lane);  // -(C T)
-            cw_sub_into<NP, C>(W, ct, o0, nt0, lane);
+            cw_prod<NP, C>(ct, cf, Tt, LDC, nullptr, o2, nk2, nt0, n, lane);  // -(C T)
+            cw_sub_into<NP, C>(WA, LDW, ct, o0, nt0, lane);
         }
         __syncwarp();
         double resid;
@@ -464,11 +544,12 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
                         e[s][ct][h] = (r < n && pc < w0) ? gA[(size_t)r * n + o0 + pc] : 0.0;  // (L2-resident: read above)
                     }
             const int nkn = (n + 3) >> 2;
+#pragma unroll 1
             for (int ks = 0; ks < nkn; ++ks) {
                 const int kk = 4 * ks + q;
                 double a[NS];
 #pragma unroll
-                for (int s = 0; s < NS; ++s) a[s] = W[(8 * s + g) * LD + kk];
+                for (int s = 0; s < NS; ++s) a[s] = WA[(8 * s + g) * LDW + kk];
                 const double* xr = Tt + kk * LDC + g;
 #pragma unroll
                 for (int ct = 0; ct < C; ++ct) {
@@ -494,31 +575,34 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
         {
             double* gT = p.T + (size_t)draw * (p.t_stride ? (size_t)p.t_stride : (size_t)no * no);
             const int ldt = p.t_ld ? p.t_ld : no;
-            const double fill = t_nan ? __longlong_as_double(0x7ff8000000000000ll) : 0.0;
-            for (int i = lane; i < no * no; i += 32) {
-                const int r = i / no, c = i - r * no;
-                const int pc = s_perm[c] - o0;
-                gT[(size_t)r * ldt + c] = (pc >= 0 && pc < w0) ? Tt[s_perm[r] * LDC + pc] : fill;
+            const double fill = t_nan ? qnan : 0.0;
+#pragma unroll 1
+            for (int r = 0; r < no; ++r) {
+                const double* trow = Tt + s_perm[r] * LDC;
+                for (int c = lane; c < no; c += 32) {
+                    const int pc = s_perm[c] - o0;
+                    gT[(size_t)r * ldt + c] = (pc >= 0 && pc < w0) ? trow[pc] : fill;
+                }
             }
         }
 
         // ---- R = -W^-1 D (shared.py:74-75) and, for the Blanchard-Kahn certificate, W^-1 C on the lead columns (= -F):
-        // one solve, right-hand sides D (packed tile in the A1 region) and C's lead columns (already in X0)
+        // one solve, right-hand sides D (Xa block) and C's lead columns (already in the Xb block)
         const bool want_cert = p.lead_idx && converged && !t_nan;
         bool have_F = false;
-        double* Dt = A1;
         if (kd || want_cert) {
-            if (kd) cw_load<NP, LDC>(Dt, gD, n, 0, kd, k, lane);
+            if (kd) cw_load<NP>(X0, LDW, 8 * C, gD, n, 0, kd, k, lane);
             __syncwarp();
-            const bool ok = cw_gj<NP, LDC, LDC>(W, W, Dt, ntd, X0, want_cert ? nt2 : 0, n, s_piv, s_flag, lane);
+            const bool ok = cw_gj<NP, C>(WA, ntd, want_cert ? nt2 : 0, n, s_piv, s_flag, lane);
             if (!ok) status |= GECON_ST_SINGULAR;
             have_F = ok && want_cert;
             if (kd) {
                 double* gR = p.R + (size_t)draw * (p.r_stride ? (size_t)p.r_stride : (size_t)no * k);
-                const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-                for (int i = lane; i < no * k; i += 32) {
-                    const int r = i / k, c = i - r * k;
-                    gR[(size_t)r * k + c] = ok ? -Dt[s_piv[s_perm[r]] * LDC + c] : qnan;
+#pragma unroll 1
+                for (int r = lane; r < no; r += 32) {  // one row per lane (k is small)
+                    const double* xrow = X0 + s_piv[s_perm[r]] * LDW;
+#pragma unroll 1
+                    for (int c = 0; c < k; ++c) gR[(size_t)r * k + c] = ok ? -xrow[c] : qnan;
                 }
             }
         }
@@ -526,89 +610,45 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
             if (p.resid) p.resid[draw] = resid;
             if (p.n_iter) p.n_iter[draw] = it;
         }
-        __syncwarp();
 
-        // ---- Blanchard-Kahn certificate: rho(T_LL) < 1 and rho(F_FF) < 1 by repeated squaring (see gecon_cr_args.lead_idx).
-        // Z1 = T[lag][:, lag] -> W region, Z2 = (W^-1 C)[lead][:, lead] -> A1 region; their sources (X2, X0) become the
-        // ping-pong buffers once copied.
+        // ---- Blanchard-Kahn certificate: rho(T_LL) < 1 and rho(F_FF) < 1, each by a power with 1-norm < 1 (see
+        // gecon_cr_args.lead_idx).  T_LL = the lag block of T (rows o0.., packed columns 0..), F_FF = (W^-1 C)[lead][:, lead].
         bool certified = false;
-        if (p.lead_idx) {
-            if (have_F) {
-                const int s1 = min(w0, n - o0);  // the lag block sits at rows o0.. / packed columns 0.. of T
-                double* Z1 = W;
-                double* Z2 = A1;
-                double* Z1b = X2;
-                double* Z2b = X0;
-                for (int i = lane; i < TC; i += 32) {
-                    const int r = i / LDC, c = i - r * LDC;
-                    Z1[i] = (r < s1 && c < s1) ? Tt[(o0 + r) * LDC + c] : 0.0;
-                    double z = 0.0;
-                    if (r < nl && c < nl) {
-                        const int pc = s_lead[c] - o2;
-                        z = (pc >= 0 && pc < w2) ? X0[s_piv[s_lead[r]] * LDC + pc] : 0.0;
-                    }
-                    Z2[i] = z;
+        if (have_F) {
+            const int s1 = min(w0, n - o0);
+            // F_FF -> registers first (its source, the Xb block, is where the scratch tiles go)
+            constexpr int PERZ = (8 * C * LDC + 31) / 32;
+            double zf[PERZ];
+#pragma unroll
+            for (int e = 0; e < PERZ; ++e) {
+                const int i = lane + 32 * e;
+                const int r = i / LDC, c = i - r * LDC;
+                double z = 0.0;
+                if (r < nl && c < nl) {
+                    const int pc = s_lead[c] - o2;
+                    z = (pc >= 0 && pc < w2) ? X2[s_piv[s_lead[r]] * LDW + pc] : 0.0;
                 }
-                __syncwarp();
-                cw_zero<NP, LDC>(Z1b, lane);
-                cw_zero<NP, LDC>(Z2b, lane);
-                __syncwarp();
-                const int k1 = (s1 + 3) >> 2, c1 = (s1 + 7) >> 3, k2 = (nl + 3) >> 2, c2 = (nl + 7) >> 3;
-                bool ok1 = (s1 == 0), ok2 = (nl == 0);
-                // Zb = Z Z on the leading nc x nc tiles
-                auto square = [&](const double* Z, double* Zb, int nk, int nc) {
-                    double acc[NS][C][2];
-                    cw_acc_zero<NS, C>(acc);
-                    for (int ks = 0; ks < nk; ++ks) {
-                        const int kk = 4 * ks + q;
-                        double a[NS];
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) a[s] = (s < nc) ? Z[(8 * s + g) * LDC + kk] : 0.0;
-#pragma unroll
-                        for (int ct = 0; ct < C; ++ct) {
-                            if (ct < nc) {
-                                const double b = Z[kk * LDC + 8 * ct + g];
-#pragma unroll
-                                for (int s = 0; s < NS; ++s)
-                                    if (s < nc) dmma884(acc[s][ct][0], acc[s][ct][1], a[s], b);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int s = 0; s < NS; ++s)
-#pragma unroll
-                        for (int ct = 0; ct < C; ++ct)
-                            if (s < nc && ct < nc) *reinterpret_cast<double2*>(Zb + (8 * s + g) * LDC + 8 * ct + 2 * q) = make_double2(acc[s][ct][0], acc[s][ct][1]);
-                };
-                for (int sq = 0; sq <= 14; ++sq) {
-                    // the norms are only inspected after every second squaring (and at the start)
-                    const bool look = (sq & 1) == 0 || sq == 14;
-                    const double n1 = (ok1 || !look) ? (ok1 ? 0.0 : 2.0) : cw_norm1<NP, LDC>(Z1, lane);
-                    const double n2 = (ok2 || !look) ? (ok2 ? 0.0 : 2.0) : cw_norm1<NP, LDC>(Z2, lane);
-                    ok1 = ok1 || (n1 < 1.0);
-                    ok2 = ok2 || (n2 < 1.0);
-                    if (ok1 && ok2) {
-                        certified = true;
-                        break;
-                    }
-                    if (!(n1 < 1e100) || !(n2 < 1e100) || sq == 14) break;  // growing powers / NaN: leave it to bk_count
-                    if (!ok1) {
-                        square(Z1, Z1b, k1, c1);
-                        double* t = Z1;
-                        Z1 = Z1b;
-                        Z1b = t;
-                    }
-                    if (!ok2) {
-                        square(Z2, Z2b, k2, c2);
-                        double* t = Z2;
-                        Z2 = Z2b;
-                        Z2b = t;
-                    }
-                    __syncwarp();
-                }
+                zf[e] = z;
             }
-            if (certified) status |= GECON_ST_BK_CERTIFIED;
+            __syncwarp();
+            double* Z = WA;  // two 8 C x LDC tiles inside WA; F_FF goes where T was once its lag block has been copied out
+            double* Zb = WA + 8 * C * LDC;
+            double* Zf = A1;
+#pragma unroll 1
+            for (int i = lane; i < 8 * C * LDC; i += 32) {
+                const int r = i / LDC, c = i - r * LDC;
+                Z[i] = (r < s1 && c < s1) ? Tt[(o0 + r) * LDC + c] : 0.0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < PERZ; ++e) {
+                const int i = lane + 32 * e;
+                if (i < 8 * C * LDC) Zf[i] = zf[e];
+            }
+            __syncwarp();
+            certified = cw_power_bound<C>(Z, Zb, s1, lane) && cw_power_bound<C>(Zf, Z, nl, lane);
         }
+        if (certified) status |= GECON_ST_BK_CERTIFIED;
         if (lane == 0) {
             p.status[draw] = p.accumulate ? (p.status[draw] | status) : status;
             if (p.lead_idx && p.n_unstable) p.n_unstable[draw] = certified ? nl : -1;

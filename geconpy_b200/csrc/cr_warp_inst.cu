@@ -11,9 +11,11 @@
 
 namespace gecon {
 
-template <int NP, int C>
-static int launch_cw(const gecon_cr_args& a, const cw_ranges& rg, cudaStream_t st, int* info) {
-    constexpr int WPC = 4;
+// WPC = warps (draws in flight) per CTA.  The kernel has no CTA-wide synchronisation after its set-up, so the CTA shape only
+// decides the granularity at which shared memory and registers are handed out: GECON_CW_WPC=13 (experiment hook) runs one
+// CTA of 13 warps per SM where four-warp CTAs fit three times (12 warps).
+template <int NP, int C, int WPC>
+static int launch_cw_w(const gecon_cr_args& a, const cw_ranges& rg, cudaStream_t st, int* info) {
     const size_t smem = CwCfg<NP, C>::bytes(WPC);
     int grid = 0, per_sm = 0;
     int rc = persistent_grid(cr_warp_kernel<NP, C, WPC>, WPC * 32, smem, (a.N + WPC - 1) / WPC, &grid, &per_sm, "GECON_CR_CTAS_PER_SM");
@@ -28,6 +30,18 @@ static int launch_cw(const gecon_cr_args& a, const cw_ranges& rg, cudaStream_t s
     g_launch_count++;
     GECON_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int NP, int C>
+static int launch_cw(const gecon_cr_args& a, const cw_ranges& rg, cudaStream_t st, int* info) {
+#ifdef GECON_CW_EXPERIMENT_WPC
+    if (const char* e = getenv("GECON_CW_WPC")) {
+        if (atoi(e) == GECON_CW_EXPERIMENT_WPC) {
+            if constexpr (CwCfg<NP, C>::bytes(GECON_CW_EXPERIMENT_WPC) <= 227 * 1024) return launch_cw_w<NP, C, GECON_CW_EXPERIMENT_WPC>(a, rg, st, info);
+        }
+    }
+#endif
+    return launch_cw_w<NP, C, 4>(a, rg, st, info);
 }
 
 #define GECON_CW_CASE(c)                                             \

@@ -233,6 +233,18 @@ __device__ __forceinline__ double rcp_nr(double x) {
     return y;
 }
 
+// two Newton steps: MUFU.RCP64H is good to ~2^-20, so 2^-40 after one step and below half an ulp after two (what the CUDA
+// math library's own reciprocal does on its fast path); used where the reciprocal sits on a dependent chain
+__device__ __forceinline__ double rcp_nr2(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
 // 64-bit shuffle as two explicit 32-bit shuffles (the double overload of __shfl_sync costs three extra LOP3 per value)
 __device__ __forceinline__ double shfl_f64(double v, int src) {
     const int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src);

@@ -119,6 +119,9 @@ def statespace_target(statespace, Y, fixed_tail, phi: float = 1.0):
     def f(theta):
         full = torch.cat([theta, fixed_tail.expand(theta.shape[0], -1)], dim=1)
         ll, grad, _st = statespace.loglik_and_grad_device(full, Y)
-        return phi * ll, phi * grad[:, : theta.shape[1]]
+        # gated draws stay -inf for every phi (0 * -inf would be NaN and slip through the isfinite tests as "alive = False"
+        # only by accident): the support of the target does not depend on the temperature
+        lp = torch.where(torch.isfinite(ll), phi * ll, torch.full_like(ll, float("-inf")))
+        return lp, phi * grad[:, : theta.shape[1]]
 
     return f

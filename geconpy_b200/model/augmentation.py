@@ -195,21 +195,27 @@ class StateAugmentation:
 
 
 def prepare_mixed_frequency_data(low_freq_data, high_freq: str, aggregation_period: int = 4, observation_position: str = "last"):
-    """Expand low-frequency data to the model's frequency with NaN at the unobserved periods (the filter masks them).
-    Same signature and placement rule as gEconpy/model/statespace.py:1432-1509."""
+    """Low-frequency observations on the model's (higher-frequency) calendar: each observation sits at the first or last period of
+    its window of ``aggregation_period`` model periods, every other period is NaN (the filter masks NaN rows), and the frame
+    ends at the last observation.  Signature and placement rule of gEconpy/model/statespace.py:1432-1509; the placement is
+    computed for all observations at once (one sorted search of the observation dates in the model calendar)."""
     import pandas as pd
 
     if observation_position not in ("first", "last"):
         raise ValueError("observation_position must be 'first' or 'last'")
-    pos = 0 if observation_position == "first" else aggregation_period - 1
-    hf_index = pd.date_range(start=low_freq_data.index.min(), periods=len(low_freq_data) * aggregation_period, freq=high_freq)
-    out = pd.DataFrame(np.nan, index=hf_index, columns=list(low_freq_data.columns))
-    for lf_date, row in low_freq_data.iterrows():
-        window = hf_index[hf_index >= lf_date][:aggregation_period]
-        if len(window) > pos:
-            out.loc[window[pos]] = row
-    last = out.last_valid_index()
-    if last is not None:
-        out = out.loc[:last]
+    offset = 0 if observation_position == "first" else int(aggregation_period) - 1
+    n_hf = len(low_freq_data) * int(aggregation_period)
+    calendar = pd.date_range(start=low_freq_data.index.min(), periods=n_hf, freq=high_freq)
+    window_start = calendar.searchsorted(low_freq_data.index, side="left")  # first model period on or after each observation date
+    target = window_start + offset
+    placed = target < n_hf                                                  # windows cut short by the end of the calendar are dropped
+    grid = np.full((n_hf, low_freq_data.shape[1]), np.nan)
+    values = low_freq_data.to_numpy(dtype=np.float64)
+    for t, row in zip(target[placed], values[placed]):  # in observation order: a later observation wins a shared slot
+        grid[t] = row
+    seen = np.flatnonzero(~np.isnan(grid).all(axis=1))
+    if seen.size:
+        grid, calendar = grid[: seen[-1] + 1], calendar[: seen[-1] + 1]
+    out = pd.DataFrame(grid, index=calendar, columns=list(low_freq_data.columns))
     out.index.freq = out.index.inferred_freq
     return out

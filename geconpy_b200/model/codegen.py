@@ -418,24 +418,37 @@ class LinearizedModel:
                         sym_entries.append(e)
                         where.append((m, i, j))
         subs, red = sp.cse(sym_entries, symbols=sp.numbered_symbols("j_tmp_"), optimizations="basic") if sym_entries else ([], [])
-        emit("    // Jacobian entries: shared CSE temporaries, then scatter (rows eq_order, columns var_order)")
+        emit("    // Jacobian entries: shared CSE temporaries, then scatter (rows eq_order, columns var_order).  GECON_ST stores either")
+        emit("    // into the dense matrices or into the compact vector of structural non-zeros (entries grouped A, B, C, D; row-major)")
         for s, e in subs:
             emit(f"    const double {s.name} = {cc(e)};")
         emit("    double v; bool fin = true;")
         width = {"A": n, "B": n, "C": n, "D": k}
+        nz = self.nonzero_structure()
+        slot = {key: ci for ci, key in enumerate(nz)}
         for (m, i, j), e in zip(where, red):
             scale = f" * sc{j}" if (m != "D" and self.scale_kind[j] != "one") else ""
-            emit(f"    v = ({cc(e)}){scale}; fin = fin && (fabs(v) <= 1.7e308); {m}[{i * width[m] + j}] = v;")
+            emit(f"    v = ({cc(e)}){scale}; fin = fin && (fabs(v) <= 1.7e308); GECON_ST({m}, {i * width[m] + j}, {slot[(m, i, j)]}, v);")
         emit("    // constant entries")
         for m, i, j, val in const_entries:
             scale = f" * sc{j}" if (m != "D" and self.scale_kind[j] != "one") else ""
             if scale:
-                emit(f"    v = {val!r}{scale}; fin = fin && (fabs(v) <= 1.7e308); {m}[{i * width[m] + j}] = v;")
+                emit(f"    v = {val!r}{scale}; fin = fin && (fabs(v) <= 1.7e308); GECON_ST({m}, {i * width[m] + j}, {slot[(m, i, j)]}, v);")
             else:
-                emit(f"    {m}[{i * width[m] + j}] = {val!r};")
+                emit(f"    GECON_ST({m}, {i * width[m] + j}, {slot[(m, i, j)]}, {val!r});")
         body = "\n".join(lines)
         ident = re.sub(r"[^0-9A-Za-z_]", "_", self.name)
-        return _TEMPLATE.format(name=ident, n=n, k=k, n_theta=self.n_theta, body=body, vjp_body=self.vjp_body())
+        offs = [sum(1 for key in nz if "ABCD".index(key[0]) < q) for q in range(5)]
+        table = ", ".join(str((i << 16) | j) for (_m, i, j) in nz) or "0"
+        return _TEMPLATE.format(name=ident, n=n, k=k, n_theta=self.n_theta, body=body, vjp_body=self.vjp_body(), nnz=len(nz),
+                                nnz_alloc=max(1, len(nz)), table=table, offs=", ".join(map(str, offs)),
+                                lag_lo=self.col_ranges[0], lag_hi=self.col_ranges[1], lead_lo=self.col_ranges[2], lead_hi=self.col_ranges[3],
+                                n_lead=len(self.permuted_lead_var_idx), lead_list=", ".join(map(str, self.permuted_lead_var_idx)) or "0")
+
+    def nonzero_structure(self):
+        """Structural non-zeros of A, B, C, D in solver order as a list of (matrix, row, col), grouped by matrix and row-major inside
+        each: the layout of the compact Jacobian vector (``gecon_model_jacobian_compact``) the fused pipeline consumes."""
+        return [(m, i, j) for m in "ABCD" for i, row in enumerate(self.entries[m]) for j, e in enumerate(row) if not (e.is_number and e == 0)]
 
 
 _TEMPLATE = r"""// GENERATED by geconpy_b200/model/codegen.py for model "{name}" -- do not edit.
@@ -459,10 +472,26 @@ _TEMPLATE = r"""// GENERATED by geconpy_b200/model/codegen.py for model "{name}"
 #define GECON_MODEL_NTHETA {n_theta}
 #define GECON_ST_JAC_NONFINITE 0x200
 
-__device__ __forceinline__ bool gecon_model_eval(const double* __restrict__ th, double* __restrict__ A, double* __restrict__ B,
-                                                 double* __restrict__ C, double* __restrict__ D, double* __restrict__ xss) {{
+#define GECON_MODEL_NNZ {nnz}
+// structural non-zeros of A, B, C, D (row << 16 | col), grouped by matrix: entries of matrix q are [off[q], off[q + 1])
+static const int32_t gecon_nz_table_h[{nnz_alloc}] = {{{table}}};
+static const int32_t gecon_nz_off_h[5] = {{{offs}}};
+static const int32_t gecon_lead_idx_h[{n_lead} > 0 ? {n_lead} : 1] = {{{lead_list}}};
+
+// COMPACT: store into vals[GECON_MODEL_NNZ] (A, B, C, D unused) instead of the dense, zero-filled matrices
+#define GECON_ST(M, DI, CI, V) do {{ if (COMPACT) vals[CI] = (V); else M[DI] = (V); }} while (0)
+template <bool COMPACT>
+__device__ __forceinline__ bool gecon_model_eval_t(const double* __restrict__ th, double* __restrict__ A, double* __restrict__ B,
+                                                   double* __restrict__ C, double* __restrict__ D, double* __restrict__ xss,
+                                                   double* __restrict__ vals) {{
 {body}
     return fin;
+}}
+#undef GECON_ST
+
+__device__ __forceinline__ bool gecon_model_eval(const double* __restrict__ th, double* __restrict__ A, double* __restrict__ B,
+                                                 double* __restrict__ C, double* __restrict__ D, double* __restrict__ xss) {{
+    return gecon_model_eval_t<false>(th, A, B, C, D, xss, nullptr);
 }}
 
 // theta_bar = sum over the entries of <M_bar, dM/dtheta> (+ <xss_bar, dx_ss/dtheta>): reverse mode over the same program
@@ -517,6 +546,50 @@ __global__ void __launch_bounds__(128) gecon_model_vjp_kernel(const double* __re
                         Db + (size_t)i * GECON_MODEL_N * GECON_MODEL_K, xssb ? xssb + (size_t)i * GECON_MODEL_N : nullptr,
                         theta_bar + (size_t)i * GECON_MODEL_NTHETA);
     }}
+}}
+
+__global__ void __launch_bounds__(128) gecon_model_jacobian_compact_kernel(const double* __restrict__ theta, long long theta_stride, long long N,
+                                                                           double* __restrict__ vals, double* __restrict__ xss,
+                                                                           int* __restrict__ status) {{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {{
+        const bool fin = gecon_model_eval_t<true>(theta + (size_t)i * theta_stride, nullptr, nullptr, nullptr, nullptr,
+                                                  xss ? xss + (size_t)i * GECON_MODEL_N : nullptr, vals + (size_t)i * GECON_MODEL_NNZ);
+        if (status) status[i] = fin ? 0 : GECON_ST_JAC_NONFINITE;
+    }}
+}}
+
+// DEVICE pointers.  The compact Jacobian: vals[N][GECON_MODEL_NNZ], the structural non-zeros of A, B, C, D only (layout:
+// gecon_model_structure).  theta rows may be strided (theta_stride >= n_theta doubles: the free parameters are the leading
+// columns of a wider parameter vector).  No memsets, one kernel on `stream`.
+extern "C" int gecon_model_jacobian_compact(const double* theta, int64_t theta_stride, int64_t N, double* vals, double* xss, int32_t* status,
+                                            void* stream) {{
+    if (N <= 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (N + 127) / 128;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    gecon_model_jacobian_compact_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(theta, theta_stride, N, vals, xss, status);
+    return (int)cudaGetLastError();
+}}
+
+// Structure of the model as the solver kernels need it (HOST arrays owned by the library): number of structural non-zeros, their
+// (row << 16 | col) table grouped by matrix with offsets off[5], the contiguous lag / lead column ranges
+// {{lag_lo, lag_hi, lead_lo, lead_hi}} (solver order) and the positions of the structural lead variables.
+extern "C" int gecon_model_structure(int32_t* nnz, const int32_t** table, const int32_t** off, int32_t* col_ranges, int32_t* n_lead,
+                                     const int32_t** lead_idx) {{
+    if (nnz) *nnz = GECON_MODEL_NNZ;
+    if (table) *table = gecon_nz_table_h;
+    if (off) *off = gecon_nz_off_h;
+    if (col_ranges) {{
+        col_ranges[0] = {lag_lo};
+        col_ranges[1] = {lag_hi};
+        col_ranges[2] = {lead_lo};
+        col_ranges[3] = {lead_hi};
+    }}
+    if (n_lead) *n_lead = {n_lead};
+    if (lead_idx) *lead_idx = gecon_lead_idx_h;
+    return 0;
 }}
 
 // DEVICE pointers: theta_bar[N][n_theta] = vector-Jacobian product of (A_bar, B_bar, C_bar, D_bar, xss_bar or NULL)

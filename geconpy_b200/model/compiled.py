@@ -151,6 +151,13 @@ class BatchedStateSpace:
         observation_equations: dict | None = None,
         full_shock_covariance: bool = False,
         mask_intercept: bool = False,
+        constant_params=None,
+        mode=None,
+        verbose: bool = True,
+        use_adjoint_gradients: bool = True,
+        use_direct_lyapunov: bool = False,
+        add_bk_check: bool | None = None,
+        add_solver_success_check: bool = True,
     ):
         """Same meaning as ``DSGEStateSpace.configure`` (gEconpy/model/statespace.py:822-1090) for the arguments it
         shares: ``temporal_aggregation`` {"sum" | "mean" | "first" | "last"} with ``aggregation_period`` adds cumulator
@@ -163,10 +170,34 @@ class BatchedStateSpace:
         intercept is not masked at missing entries (SURVEY A.5's restatement of the upstream filter: a missing entry then
         contributes -(d_i^2 / jitter + log jitter) / 2, which matters as soon as ``ss_obs_intercept`` meets missing data);
         True = missing entries contribute nothing.  ``tests/golden/make_kalman_goldens.py`` records which one the installed
-        pymc_extras follows."""
+        pymc_extras follows.
+
+        ``solver`` (statespace.py:197-222): ``"cycle_reduction"``; ``"gensys"`` (the same kernel: T from cycle reduction,
+        determinacy from the Blanchard-Kahn count); ``"scan_cycle_reduction"`` (the scan twin's conventions:
+        only ||A0||_1 is tested and T is always solved for; the per-draw step count is what the reference publishes as
+        ``n_cycle_steps``, here ``out_n_iter``); ``"backward_direct"`` (models without leads: T = -B^-1 A, R = -B^-1 D, no
+        iteration, no Blanchard-Kahn check).  ``constant_params`` (list, or ``"auto"`` = every parameter without a prior):
+        held at their defaults and dropped from the parameter vector (statespace.py:741-753).  ``mode`` (a pytensor
+        compilation mode), ``use_adjoint_gradients`` (the gradient path is always adjoint-based) and ``use_direct_lyapunov``
+        (P0 comes from Smith doubling, which agrees with both of the reference's Lyapunov solvers to rounding) are accepted for
+        signature compatibility.  ``add_bk_check`` / ``add_solver_success_check``: the two ``pm.Potential(-inf)`` gates of
+        ``build_statespace_graph`` (statespace.py:1206-1215).  The reference defaults both to False; here both default to
+        True because a population of prior draws always contains draws the solver rejects -- pass False, False to reproduce
+        the reference's default graph (non-finite steady states and failed solves are gated either way: their logp is NaN in
+        the reference, -inf here).  ``check_bk`` is the older name of ``add_bk_check``."""
         m = self.model
-        if solver not in ("cycle_reduction", "gensys"):
-            raise NotImplementedError(f"solver={solver!r}: the B200 path solves by cycle reduction (gensys maps to CR + BK flag)")
+        if solver not in ("cycle_reduction", "gensys", "scan_cycle_reduction", "backward_direct"):
+            raise NotImplementedError(f"solver={solver!r}: expected cycle_reduction, gensys, scan_cycle_reduction or backward_direct")
+        if solver == "backward_direct" and len(m.permuted_lead_var_idx):
+            raise ValueError("solver='backward_direct' needs a model without forward-looking variables (backward_looking.py:8-60)")
+        self.solver = solver
+        if add_bk_check is not None:
+            check_bk = add_bk_check
+        if solver == "backward_direct":
+            check_bk = False
+        self.add_solver_success_check = bool(add_solver_success_check)
+        self.mode, self.verbose = mode, verbose
+        self.use_adjoint_gradients, self.use_direct_lyapunov = bool(use_adjoint_gradients), bool(use_direct_lyapunov)
         observation_equations = dict(observation_equations or {})
         unknown_keys = [k_ for k_ in observation_equations if k_ not in observed_states]
         if unknown_keys:
@@ -269,8 +300,27 @@ class BatchedStateSpace:
         self.mask_intercept = bool(mask_intercept)
         self._n_cov = m.k * m.k if self.full_covariance else m.k
         cov_names = [f"state_cov[{i},{j}]" for i in range(m.k) for j in range(m.k)] if self.full_covariance else [f"sigma_{s}" for s in m.shock_names]
-        self.param_names = list(m.param_names) + cov_names + [f"error_sigma_{v}" for v in measurement_error]
+        all_names = list(m.param_names) + cov_names + [f"error_sigma_{v}" for v in measurement_error]
+        # constant parameters (statespace.py:741-753): held at the spec's defaults, not part of the parameter vector
+        if constant_params == "auto":
+            constant_params = [p_ for p_ in m.param_names if p_ not in m.lin.spec.get("bounds", {})]
+        constant_params = list(constant_params or [])
+        unknown = [p_ for p_ in constant_params if p_ not in m.param_names]
+        if unknown:
+            raise ValueError(f"unknown constant_params {unknown}; model parameters: {list(m.param_names)}")
+        self.constant_params = constant_params
+        self._n_param_full = len(all_names)
+        self._free_cols = np.array([i for i, nm in enumerate(all_names) if nm not in constant_params], dtype=np.int64)
+        self._const_row = np.zeros(self._n_param_full)
+        self._const_row[: m.n_theta] = m.theta_vector()
+        self.param_names = [all_names[i] for i in self._free_cols]
         self.n_param = len(self.param_names)
+        # gate: the reference's two Potentials + what makes its logp NaN anyway
+        self.gate_mask = L.ST_JAC_NONFINITE | L.ST_CR_NAN | L.ST_SINGULAR
+        if check_bk:
+            self.gate_mask |= L.ST_BK | L.ST_BK_INCONCLUSIVE
+        if self.add_solver_success_check:
+            self.gate_mask |= L.ST_RESID | L.ST_CR_NOT_CONVERGED
         self.configured = True
         self._ws = None
         self._ws_extra = {}  # per-stream workspaces of the multi-stream pipeline: shapes depend on the configuration
@@ -324,6 +374,16 @@ class BatchedStateSpace:
         self._ws = ws
         return ws
 
+    def _expand_params(self, theta):
+        """[N, n_param] -> [N, n_param_full]: constant parameters filled in at their defaults (no-op without any)."""
+        if theta.shape[1] != self.n_param:
+            raise ValueError(f"theta has {theta.shape[1]} columns, expected {self.n_param}: {self.param_names}")
+        if not self.constant_params:
+            return theta
+        full = torch.as_tensor(self._const_row, dtype=torch.float64, device=theta.device).repeat(theta.shape[0], 1)
+        full[:, torch.as_tensor(self._free_cols, device=theta.device)] = theta
+        return full
+
     # ------------------------------------------------------------------------------------------------ evaluation
     def loglik_device(self, theta_full, Y, out_ll=None, out_status=None, out_n_iter=None, events=None):
         """theta_full: torch CUDA tensor [N, n_param]; Y: torch CUDA tensor [Tobs, p].  Returns (ll, status) on device.
@@ -336,8 +396,7 @@ class BatchedStateSpace:
         lib = L.load_library()
         dev = theta_full.device
         N = theta_full.shape[0]
-        if theta_full.shape[1] != self.n_param:
-            raise ValueError(f"theta has {theta_full.shape[1]} columns, expected {self.n_param}: {self.param_names}")
+        theta_full = self._expand_params(theta_full)
         Y = Y.to(torch.float64).contiguous().reshape(-1, self.p)
         Tobs = Y.shape[0]
         ll = out_ll if out_ll is not None else torch.empty((N,), dtype=torch.float64, device=dev)
@@ -396,7 +455,8 @@ class BatchedStateSpace:
                 if rc != 0:
                     raise L.GeconLibraryError(f"gecon_obs_batched failed with CUDA error {rc}")
             cr = L.CrArgs(
-                struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
+                struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(),
+                C=(None if self.solver == "backward_direct" else ws["C"].data_ptr()), scan_semantics=int(self.solver == "scan_cycle_reduction"),
                 D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
                 resid_tol=self.solver_tol, unperm=ws["subset"].data_ptr(), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
                 status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
@@ -430,7 +490,7 @@ class BatchedStateSpace:
                 Y=Y.data_ptr(), P0=None, N=cnt, n=self.n_aug, k=m.k, p=self.p,
                 Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
                 mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
-                gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),
+                gate_mask=self.gate_mask, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),
                 ll_t=None, mask_intercept=int(self.mask_intercept),
             )  # fmt: skip
             e = mark("kalman_ll")
@@ -463,14 +523,13 @@ class BatchedStateSpace:
         lib = L.load_library()
         dev = theta_full.device
         N = theta_full.shape[0]
-        if theta_full.shape[1] != self.n_param:
-            raise ValueError(f"theta has {theta_full.shape[1]} columns, expected {self.n_param}: {self.param_names}")
+        theta_full = self._expand_params(theta_full)
         Y = Y.to(torch.float64).contiguous().reshape(-1, self.p)
         Tobs = Y.shape[0]
         f64 = dict(dtype=torch.float64, device=dev)
         ll = torch.empty((N,), **f64)
         status = torch.empty((N,), dtype=torch.int32, device=dev)
-        grad = torch.zeros((N, self.n_param), **f64)
+        grad = torch.zeros((N, self._n_param_full), **f64)
         nc = min(self.chunk, N)  # (full-size adjoints per draw: ~50 KB per draw at n = 24, 3 GB per 65,536-draw chunk)
         ws = self._workspace(dev, nc)
         g = self._grad_ws
@@ -519,7 +578,8 @@ class BatchedStateSpace:
                 if rc != 0:
                     raise L.GeconLibraryError(f"gecon_obs_batched failed with CUDA error {rc}")
             cr = L.CrArgs(
-                struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(),
+                struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(),
+                C=(None if self.solver == "backward_direct" else ws["C"].data_ptr()), scan_semantics=int(self.solver == "scan_cycle_reduction"),
                 D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
                 resid_tol=self.solver_tol, unperm=None, T=g["Tfull"].data_ptr(), R=g["Rfull"].data_ptr(),
                 status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
@@ -551,7 +611,7 @@ class BatchedStateSpace:
                 Z_bar=(g["Zb"].data_ptr() if self._obs_lib is not None else None),
                 Y=Y.data_ptr(), N=cnt, n=self.n_aug, k=m.k, p=self.p, Tobs=Tobs, jitter=self.cov_jitter,
                 missing_fill=self.missing_fill_value, mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0,
-                status_in=st.data_ptr(), gate_mask=GATE_MASK, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(),
+                status_in=st.data_ptr(), gate_mask=self.gate_mask, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(),
                 status=status[lo : lo + cnt].data_ptr(), T_bar=g["Tb_f"].data_ptr(), R_bar=g["Rb_f"].data_ptr(),
                 q_bar=g["qb"].data_ptr(), h_bar=g["hb"].data_ptr(), d_bar=g["db"].data_ptr(), mask_intercept=int(self.mask_intercept),
             )  # fmt: skip
@@ -599,6 +659,8 @@ class BatchedStateSpace:
                 out[:, m.n_theta + m.k :] = g["hb"][:cnt].index_select(1, g["err_pos"])
             bad = (status[lo : lo + cnt] != 0) | (g["st2"][:cnt] != 0)
             out.masked_fill_(bad[:, None], 0.0)
+        if self.constant_params:
+            grad = grad.index_select(1, torch.as_tensor(self._free_cols, device=dev))
         return ll, grad, status
 
     def loglik_and_grad(self, theta_full, Y, device="cuda:0"):

@@ -41,12 +41,33 @@ def solvability_check(
     theta = np.tile(model.theta_vector(), (N, 1))
     for c in samples.columns:
         theta[:, model.param_names.index(c)] = samples[c].to_numpy(dtype=np.float64)
-    A, B, C, D, _xss, st_j = model.jacobian(theta)
+    # Everything between the parameter frame and the three result columns stays on the device: theta -> A, B, C, D (generated
+    # kernel) -> cycle reduction + residual norms -> Blanchard-Kahn count, in chunks that bound the workspace; only
+    # (status, two norms) per draw come back (16 bytes per draw instead of the 14.6 KB Jacobians of a medium model).
+    L.require_device()
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n, k = model.n, model.k
     lead = model.permuted_lead_var_idx
-    res = batched.cr_solve(A, B, C, D, max_iter=max_iter, tol=tol, lead_idx=lead, solvability_norms=True, trunc_tol=tol)
-    status = res.status | st_j
-    nu, status = batched.bk_count(A, B, C, lead, status=status, skip_mask=L.ST_BK_CERTIFIED | L.ST_JAC_NONFINITE, n_unstable=res.n_unstable)
-    nd, ns = res.solv_norms[:, 0].copy(), res.solv_norms[:, 1].copy()
+    chunk = min(N, 32768) or 1
+    f64 = dict(dtype=torch.float64, device=dev)
+    ws = [torch.empty((chunk, n, n), **f64) for _ in range(3)] + [torch.empty((chunk, n, k), **f64)]
+    st_j = torch.empty((chunk,), dtype=torch.int32, device=dev)
+    status = np.empty(N, dtype=np.int32)
+    norms = np.empty((N, 2))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for lo in range(0, N, chunk):
+        cnt = min(chunk, N - lo)
+        th_d = torch.as_tensor(theta[lo : lo + cnt], device=dev)
+        A, B, C, D = (w[:cnt] for w in ws)
+        model.jacobian_device(th_d, A, B, C, D, None, st_j[:cnt], stream)
+        res = batched.cr_solve(A, B, C, D, max_iter=max_iter, tol=tol, lead_idx=lead, solvability_norms=True, trunc_tol=tol)
+        st = res.status | st_j[:cnt]
+        _nu, st = batched.bk_count(A, B, C, lead, status=st, skip_mask=L.ST_BK_CERTIFIED | L.ST_JAC_NONFINITE, n_unstable=res.n_unstable)
+        status[lo : lo + cnt] = st.cpu().numpy()
+        norms[lo : lo + cnt] = res.solv_norms.cpu().numpy()
+    nd, ns = norms[:, 0].copy(), norms[:, 1].copy()
     step = np.full(N, None, dtype=object)
     reached = np.ones(N, dtype=bool)
 
@@ -73,3 +94,42 @@ def solvability_check(
     out["norm_deterministic"] = nd
     out["norm_stochastic"] = ns
     return out
+
+
+def prior_solvability_check(model: CompiledModel, n_samples: int, *, seed=None, param_subset=None, method: str = "lhs", hdi_prob: float = 0.99,
+                            **kwargs):
+    """Sample the free parameters over their prior bounds and check solvability (perturbation_diagnostics.py:526-579).
+
+    The model spec carries each prior's bounds (``spec["bounds"]``, written by tests/golden/make_models.py from the GCN's
+    priors), not the preliz distributions themselves, so the space-filling methods the reference recommends are available --
+    ``"lhs"``, ``"sobol"``, ``"halton"``, ``"poisson_disk"`` (``scipy.stats.qmc`` over the bounds, as ``sample_uniform`` does,
+    model/sampling.py:72-145) and ``"random"`` as independent uniforms on the same box -- while the inverse-CDF methods
+    (``"*_ppf"``) need the distributions and raise.  ``hdi_prob`` is accepted for signature compatibility (the bounds are fixed
+    in the spec).  Parameters outside ``param_subset`` (or without bounds) stay at their defaults.  ``**kwargs`` go to
+    ``solvability_check``."""
+    import pandas as pd
+
+    from scipy.stats import qmc
+
+    bounds = dict(model.lin.spec.get("bounds", {}))
+    if param_subset is not None:
+        unknown = sorted(set(param_subset) - set(bounds))
+        if unknown:
+            raise ValueError(f"param_subset contains names not found in model.param_priors: {unknown}")
+        bounds = {k_: v for k_, v in bounds.items() if k_ in param_subset}
+    if not bounds:
+        raise ValueError(f"model {model.name} has no priors (spec['bounds'] is empty): nothing to sample")
+    if method.endswith("_ppf"):
+        raise NotImplementedError(f"method={method!r} needs the prior distributions; the model spec only carries their bounds")
+    names = list(bounds)
+    lo = np.array([bounds[p][0] for p in names], dtype=np.float64)
+    hi = np.array([bounds[p][1] for p in names], dtype=np.float64)
+    if method == "random":
+        u = np.random.default_rng(seed).random((n_samples, len(names)))
+    else:
+        engines = {"lhs": qmc.LatinHypercube, "sobol": qmc.Sobol, "halton": qmc.Halton, "poisson_disk": qmc.PoissonDisk}
+        if method not in engines:
+            raise ValueError(f"unknown sampling method {method!r}; expected one of {sorted(engines)} or 'random'")
+        u = engines[method](d=len(names), seed=seed).random(n_samples)
+    samples = pd.DataFrame(qmc.scale(u, lo, hi), columns=names)
+    return solvability_check(model, samples, **kwargs)

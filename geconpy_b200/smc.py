@@ -2,10 +2,12 @@
 
 Per stage every rank (one process per GPU) mutates its shard with one random-walk Metropolis step -- the step that
 costs a batched likelihood evaluation, i.e. the four kernels of ``BatchedStateSpace.loglik_device`` -- reweights by the
-tempering increment, exchanges the particles with ONE ``all_gather_into_tensor`` (log-weight, log-likelihood and theta
-packed in a single [N_local, 2 + d] buffer; NCCL over NVLink), and then every rank draws the same systematic-resampling
-ancestors from the gathered weights (shared seed, computed redundantly on the device), keeping the slice that is its
-shard.  No scatter, no host round trip.  The likelihood evaluation is the data path and has no collective in it.
+tempering increment, all-gathers (log-weight, log-likelihood, status) -- 24 bytes per particle, what the north star names --
+with ONE ``all_gather_into_tensor`` (NCCL over NVLink), and then every rank draws the same systematic-resampling ancestors
+from the gathered weights (shared seed, computed redundantly on the device) and keeps the slice that is its shard; the
+surviving parameter rows that live on other ranks are fetched with one ``all_to_all_single`` (``parallel.fetch_rows``: the
+ancestors are sorted, so at most N_local rows arrive, most of them from the rank itself).  No scatter, no host round trip.
+The likelihood evaluation is the data path and has no collective in it.
 
 The prior is uniform on a box (``lo``, ``hi``); what the reference would run instead is PyMC's ``sample_smc`` calling the
 compiled logp particle by particle.  torch is used for the plumbing (random numbers,
@@ -17,27 +19,9 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 
 import torch
-import torch.distributed as dist
 
-
-def _world():
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
-    return 0, 1
-
-
-def systematic_ancestors(log_weights: torch.Tensor, seed: int) -> torch.Tensor:
-    """Systematic resampling on the device the weights live on; deterministic in (weights, seed), so every rank that
-    holds the same gathered weights obtains the same ancestors."""
-    lw = torch.nan_to_num(log_weights.to(torch.float64), nan=float("-inf"))
-    n = lw.numel()
-    w = torch.exp(lw - lw.max())
-    cdf = torch.cumsum(w, 0)
-    cdf = cdf / cdf[-1].clone()
-    gen = torch.Generator(device="cpu").manual_seed(int(seed))
-    u0 = float(torch.rand(1, generator=gen, dtype=torch.float64))
-    positions = (u0 + torch.arange(n, dtype=torch.float64, device=lw.device)) / n
-    return torch.searchsorted(cdf, positions).clamp_(max=n - 1)
+from . import parallel
+from .parallel import systematic_ancestors  # noqa: F401  (re-exported: the resampler of the sweep)
 
 
 @dataclass
@@ -52,7 +36,9 @@ class SMCStageStats:
 @dataclass
 class TemperedSMC:
     """statespace: a configured ``BatchedStateSpace``; lo/hi: prior box of the free parameters (device tensors, [d]);
-    fixed_tail: the trailing columns of the full parameter vector that are not sampled (shock / measurement sigmas)."""
+    fixed_tail: the trailing columns of the full parameter vector that are not sampled (shock / measurement sigmas).
+    ``exchange``: "rows" (default: gather 3 doubles per particle, then fetch only the surviving parameter rows) or "allgather"
+    (round 1: all-gather the parameter rows as well; kept for the timing comparison in bench.py)."""
 
     statespace: object
     lo: torch.Tensor
@@ -61,21 +47,24 @@ class TemperedSMC:
     Y: torch.Tensor
     step_scale: float = 0.02
     seed: int = 0
+    exchange: str = "rows"
     stats: list = field(default_factory=list)
 
     def initialise(self, theta_local: torch.Tensor):
         """theta_local: this rank's shard of the initial (prior) population, [N_local, d] on the device."""
-        self.rank, self.world = _world()
+        self.rank, self.world = parallel.world()
         self.theta = theta_local.clone()
         self.n_local, self.d = self.theta.shape
+        parallel.equal_shards(self.n_local)
         dev = self.theta.device
         self.gen = torch.Generator(device=dev).manual_seed(self.seed * 1000003 + self.rank)
         self.ll = torch.empty(self.n_local, dtype=torch.float64, device=dev)
         self.status = torch.empty(self.n_local, dtype=torch.int32, device=dev)
         self._ll_prop = torch.empty_like(self.ll)
         self._st_prop = torch.empty_like(self.status)
-        self._pack = torch.empty((self.n_local, 2 + self.d), dtype=torch.float64, device=dev)
-        self._gath = torch.empty((self.world * self.n_local, 2 + self.d), dtype=torch.float64, device=dev)
+        width = 3 + (self.d if self.exchange == "allgather" else 0)
+        self._pack = torch.empty((self.n_local, width), dtype=torch.float64, device=dev)
+        self._gath = torch.empty((self.world * self.n_local, width), dtype=torch.float64, device=dev) if self.world > 1 else None
         self.phi = 0.0
         self._eval(self.theta, self.ll, self.status)
         return self
@@ -100,26 +89,27 @@ class TemperedSMC:
         self.theta = torch.where(accept[:, None], prop, self.theta)
         self.ll = torch.where(accept, self._ll_prop, self.ll)
         self.status = torch.where(accept, self._st_prop, self.status)
-        # ---- reweighting and the stage's only collective
+        # ---- reweighting and the stage's collective: (log-weight, log-likelihood, status) of every particle, 24 bytes each.
+        # (phi' - phi) * ll with ll = -inf is -inf, except at phi' = phi where it is NaN: the resampler maps NaN to -inf
         self._pack[:, 0] = (phi_next - self.phi) * self.ll
         self._pack[:, 1] = self.ll
-        self._pack[:, 2:] = self.theta
-        if self.world > 1:
-            dist.all_gather_into_tensor(self._gath, self._pack)
-            gath = self._gath
-        else:
-            gath = self._pack
-        lw = torch.nan_to_num(gath[:, 0], nan=float("-inf"))
+        self._pack[:, 2] = self.status.to(torch.float64)  # (int32 bit field: exact in a double)
+        if self.exchange == "allgather":
+            self._pack[:, 3:] = self.theta
+        gath = parallel.gather_rows(self._pack, self._gath)
+        lw = torch.nan_to_num(gath[:, 0], nan=float("-inf"), neginf=float("-inf"), posinf=float("inf"))
         w = torch.exp(lw - lw.max())
         ess = float(w.sum() ** 2 / (w * w).sum())
-        # ---- resampling: same ancestors on every rank, each keeps its slice
-        anc = systematic_ancestors(lw, seed=self.seed * 7919 + stage_index)
+        # ---- resampling: same (sorted) ancestors on every rank, each keeps its slice; only surviving rows travel
+        anc = parallel.systematic_ancestors(lw, seed=self.seed * 7919 + stage_index)
         mine = anc[self.rank * self.n_local : (self.rank + 1) * self.n_local]
         self.ll = gath[mine, 1].contiguous()
-        self.theta = gath[mine, 2:].contiguous()
+        self.status = gath[mine, 2].to(torch.int32)
+        self.theta = gath[mine, 3:].contiguous() if self.exchange == "allgather" else parallel.fetch_rows(self.theta, anc)
         self.phi = float(phi_next)
+        fin = torch.isfinite(self.ll)
         st = SMCStageStats(phi=self.phi, ess=ess, accept_rate=float(accept.double().mean()),
-                           mean_ll=float(self.ll[torch.isfinite(self.ll)].mean()), n_failed=int((~torch.isfinite(self.ll)).sum()))
+                           mean_ll=float(self.ll[fin].mean()) if bool(fin.any()) else float("nan"), n_failed=int((~fin).sum()))
         self.stats.append(st)
         return st
 

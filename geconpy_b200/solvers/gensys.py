@@ -15,7 +15,8 @@ asserts that this T equals the cycle-reduction T to 1e-8 (tests/model/test_pertu
 
 The pure bookkeeping helpers of the module (pencil assembly, eigenvalue classification, return-code messages) are
 host code and are provided with the reference's signatures.  ``gensys`` / ``build_u_v_d`` (the QZ + SVD machinery with
-its f_mat / f_wt / y_wt / gev outputs) stay CPU-only in the reference and raise ``NotImplementedError`` here.
+its f_mat / f_wt / y_wt / gev outputs) stay CPU-only in the reference.  ``gensys`` itself is provided for the pencils
+``_gensys_setup`` assembles (the only ones its callers build); a general pencil and ``build_u_v_d`` raise ``NotImplementedError``.
 """
 
 from __future__ import annotations
@@ -135,16 +136,75 @@ def gensys_batched(A, B, C, D, lead_idx=None, tol: float = 1e-8, max_iter: int =
     return out.T, out.R, success
 
 
+def _pencil_to_model(g0, g1, psi, pi, tol):
+    """Recognise a Sims pencil assembled by ``_gensys_setup`` (gensys.py:568-614) and recover ``(A, B, C, D, lead)``; None if the
+    pencil does not have that block structure."""
+    g0, g1, psi, pi = (np.asarray(x, dtype=np.float64) for x in (g0, g1, psi, pi))
+    m = g0.shape[0]
+    nl = pi.shape[1] if pi.ndim == 2 else 0
+    n = m - nl
+    if g0.shape != (m, m) or g1.shape != (m, m) or n < 1 or psi.shape[0] != m or pi.shape[0] != m:
+        return None
+    sel = g0[n:, :n]
+    ok = (
+        np.array_equal(g1[n:, n:], np.eye(nl)) and not g1[:n, n:].any() and not g1[n:, :n].any() and not g0[n:, n:].any()
+        and not psi[n:].any() and not pi[:n].any() and np.array_equal(pi[n:], np.eye(nl))
+        and np.array_equal(sel.sum(axis=1), np.ones(nl)) and np.isin(sel, (0.0, 1.0)).all()
+    )  # fmt: skip
+    if not ok:
+        return None
+    lead = sel.argmax(axis=1).astype(np.int32)
+    C = np.zeros((n, n))
+    C[:, lead] = -g0[:n, n:]
+    return np.ascontiguousarray(g1[:n, :n]), np.ascontiguousarray(-g0[:n, :n]), C, np.ascontiguousarray(psi[:n]), lead
+
+
 def gensys(g0, g1, c, psi, pi, div=None, tol=1e-8, return_all_matrices=True):
-    raise NotImplementedError(
-        "The QZ-based gensys (with its f_mat / f_wt / y_wt / gev outputs) is outside the B200 hot path (SURVEY.md 8a, row a7); "
-        "use solve_policy_function_with_gensys / gensys_batched (cycle reduction + Blanchard-Kahn count) for T, R and the "
-        "existence/uniqueness codes."
-    )
+    """``gensys(g0, g1, c, psi, pi, div, tol, return_all_matrices)`` (gensys.py:398-521) for the pencils this package's callers
+    build: ``g0, g1, c, psi, pi = _gensys_setup(A, B, C, D)``.  The block structure is recognised, the model matrices are
+    recovered and the system is solved by cycle reduction + the Blanchard-Kahn count; the result is embedded
+    in the pencil's coordinates ``y_t = [x_t ; E_t x_{t+1, lead}]``:
+
+        G_1 = [[T, 0], [(T T)[lead], 0]],   impact = [[R], [(T R)[lead]]],   C = 0,   eu as in ``solve_policy_function_with_gensys``.
+
+    ``f_mat, f_wt, y_wt, gev, loose`` (by-products of the complex QZ + SVD machinery) are None.  A pencil WITHOUT that structure
+    needs Sims' general algorithm, which is not on the B200 path: ``NotImplementedError``."""
+    rec = _pencil_to_model(g0, g1, psi, pi, tol)
+    if rec is None:
+        raise NotImplementedError(
+            "gensys on a general pencil needs the complex QZ + SVD algorithm, which is outside the B200 hot path (SURVEY.md 8a, "
+            "row a7). Supported: pencils assembled by _gensys_setup(A, B, C, D); or call solve_policy_function_with_gensys / "
+            "gensys_batched with the model matrices."
+        )
+    A, B, C, D, lead = rec
+    n, m = A.shape[0], np.shape(g0)[0]
+    out = solve_policy_function_with_gensys(A, B, C, D, tol=tol, return_all_matrices=True)
+    T, R, eu = out[0], out[2], out[7]
+    if T is None:
+        return (None, None, None, None, None, None, None, eu, None) if return_all_matrices else (None, None, None, eu)
+    TT, TR = batched.gemm(T, T), pt_free_matmul(T, R)
+    G_1 = np.zeros((m, m))
+    G_1[:n, :n], G_1[n:, :n] = T, TT[lead]
+    impact = np.vstack([R, TR[lead]])
+    const = np.zeros((m, 1))
+    if return_all_matrices:
+        return G_1, const, impact, None, None, None, None, eu, None
+    return G_1, const, impact, eu
+
+
+def pt_free_matmul(T, R):
+    """(n, n) @ (n, k) on the GPU through the square-product kernel (R zero-padded to n columns)."""
+    n, k = R.shape
+    Rp = np.zeros((n, n))
+    Rp[:, :k] = R
+    return batched.gemm(T, Rp)[:, :k]
 
 
 def build_u_v_d(eta, realsmall=2.2204460492503131e-16):
-    raise NotImplementedError("build_u_v_d belongs to the CPU-only QZ/SVD machinery of gensys (SURVEY.md 8a, row a7)")
+    raise NotImplementedError(
+        "build_u_v_d (the rank-revealing SVD of Q2 Pi inside Sims' gensys, gensys.py:128-172) belongs to the CPU-only QZ/SVD "
+        "machinery; the B200 path decides existence / uniqueness from the Blanchard-Kahn count (SURVEY.md 8a, row a7)"
+    )
 
 
 # ---------------------------------------------------------------------------------------------------- pytensor layer
@@ -161,8 +221,11 @@ class GensysWrapper(Op):
         super().__init__()
 
     def make_node(self, A, B, C, D):
+        from .cycle_reduction import linalg_output_dtype
+
         inputs = list(map(pt.as_tensor, [A, B, C, D]))
-        outputs = [pt.tensor("T", dtype="float64", shape=inputs[0].type.shape), pt.scalar("success", dtype="bool")]
+        o_dtype = linalg_output_dtype(*(inp.type.dtype for inp in inputs))
+        outputs = [pt.tensor("T", dtype=o_dtype, shape=inputs[0].type.shape), pt.scalar("success", dtype="bool")]
         return Apply(self, inputs, outputs)
 
     def infer_shape(self, fgraph, node, input_shapes):
@@ -172,15 +235,14 @@ class GensysWrapper(Op):
         A, B, C, D = (np.ascontiguousarray(x, dtype=np.float64) for x in inputs)
         lead, n, k = A.shape[:-2], A.shape[-1], D.shape[-1]
         T, _R, ok = gensys_batched(A.reshape(-1, n, n), B.reshape(-1, n, n), C.reshape(-1, n, n), D.reshape(-1, n, k), tol=self.tol)
-        outputs[0][0] = np.asarray(T).reshape(*lead, n, n)
+        outputs[0][0] = np.asarray(T, dtype=node.outputs[0].type.dtype).reshape(*lead, n, n)
         outputs[1][0] = np.asarray(ok).reshape(lead) if lead else np.bool_(np.asarray(ok).reshape(-1)[0])
 
     def pullback(self, inputs, outputs, cotangents):
-        from .shared import o1_policy_function_adjoints
+        from .cycle_reduction import _linear_policy_jvp
 
-        A, B, C, D = inputs
-        A_bar, B_bar, C_bar = o1_policy_function_adjoints(A, B, C, outputs[0], cotangents[0])
-        return [A_bar, B_bar, C_bar, pt.zeros_like(D)]
+        A_bar, B_bar, C_bar = _linear_policy_jvp(inputs, outputs, cotangents)
+        return [A_bar, B_bar, C_bar, pt.zeros_like(inputs[3])]
 
 
 def gensys_pt(A, B, C, D, tol=1e-8):

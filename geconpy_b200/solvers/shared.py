@@ -37,16 +37,13 @@ def pt_compute_selection_matrix(B, C, D, T):
 def o1_policy_function_adjoints(A, B, C, T, T_bar):
     """Adjoint of the matrix quadratic ``A + B T + C T T = 0``: returns ``[A_bar, B_bar, C_bar]`` (shared.py:12-71).
 
-    Symbolic inputs build the reference's pytensor expression (the n^2 x n^2 Kronecker system).  Numeric inputs (numpy /
-    torch CUDA, optionally with a leading draw axis) run on the GPU, where the multipliers S come from the equivalent
-    Stein equation ``S = Q + G S T'`` by doubling instead of the Kronecker solve (``gecon_policy_adjoint_*``)."""
+    The reference solves an n^2 x n^2 Kronecker system for the multipliers S; here they come from the equivalent Stein
+    equation ``S = Q + G S T'`` by doubling (``gecon_policy_adjoint_*``).  Numeric inputs (numpy / torch CUDA, optionally
+    with a leading draw axis) call the kernel directly; symbolic inputs go through the ``PolicyAdjoint`` Op, whose
+    ``perform`` makes the same call -- so the pullback of every solver Op reaches the GPU kernel."""
     if _is_symbolic(A, B, C, T, T_bar):
-        vec_T_bar = T_bar.T.ravel()
-        n = A.shape[0]
-        eye = pt.eye(n)
-        M = pt.linalg.kron(T, C.T) + pt.linalg.kron(eye, T.T @ C.T) + pt.linalg.kron(eye, B.T)
-        vec_S = pt.linalg.solve(stabilize(M), -vec_T_bar, assume_a="gen", check_finite=False)
-        S = vec_S.reshape((n, n)).T
-        return [S, S @ T.T, S @ T.T @ T.T]
+        from .cycle_reduction import PolicyAdjoint
+
+        return list(PolicyAdjoint()(A, B, C, T, T_bar))
     A_bar, B_bar, C_bar, _D_bar, _st = batched.policy_adjoints(A, B, C, T, T_bar)
     return [A_bar, B_bar, C_bar]

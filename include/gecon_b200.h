@@ -113,7 +113,11 @@ typedef struct gecon_cr_args {
     int32_t lag_hi;
     int32_t lead_lo;
     int32_t lead_hi;
-    int32_t reserved1;
+    int32_t scan_semantics; /* 0: _cycle_reduction_core (converged = ||A0||_1 < tol AND ||A2||_1 < tol; T = 0 otherwise).
+                               1: the scan twin (cycle_reduction.py:246-294): the iteration stops as soon as ||A0||_1 < tol (A2 is
+                               not tested), T = -A1hat^-1 A is ALWAYS computed (no zeroing), n_iter = the steps actually taken
+                               (the `n_steps` output of scan_cycle_reduction); GECON_ST_CR_NOT_CONVERGED then only says that
+                               max_iter passed without ||A0||_1 < tol */
 } gecon_cr_args;
 
 int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream);
@@ -346,6 +350,18 @@ typedef struct gecon_policy_adjoint_args {
 
 int gecon_policy_adjoint_batched(const gecon_policy_adjoint_args* args, void* stream);
 int gecon_policy_adjoint_host(const gecon_policy_adjoint_args* args);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Eigenvalues of batched real general matrices M[N][m][m] (balancing, Householder Hessenberg reduction, Francis double-shift
+ * QR; one warp per matrix, m <= 160).  Replaces the numpy.linalg.eig call of RealEig.perform (gEconpy/pytensorf/real_eig.py:
+ * 29-36) and, applied to M = (-Gamma0_sel + 1e-8 I)^-1 Gamma1_sel, compute_bk_eigenvalues_pt (gEconpy/model/perturbation.py:
+ * 448-505).  re / im [N][m] come out in deflation order (complex pairs adjacent, positive imaginary part first); callers
+ * sort by modulus as the reference does.  status: 0, GECON_ST_LL_NONFINITE (non-finite input) or GECON_ST_BK_INCONCLUSIVE
+ * (the QR iteration did not converge); outputs are NaN-filled then.  balance != 0: scale by powers of two first (as dgeev).
+ * ------------------------------------------------------------------------------------------------------------- */
+int gecon_real_eig_batched(const double* M, int64_t N, int32_t m, int32_t balance, double* re, double* im, int32_t* status,
+                           void* stream);
+int gecon_real_eig_host(const double* M, int64_t N, int32_t m, int32_t balance, double* re, double* im, int32_t* status);
 
 /* library / device information */
 int gecon_abi_version(void);

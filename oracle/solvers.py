@@ -68,6 +68,31 @@ def cycle_reduction_core(A0, A1, A2, max_iter=1000, tol=1e-9):
     return T, converged, n_iter
 
 
+def cycle_reduction_scan(A, B, C, max_iter=50, tol=1e-7):
+    """gEconpy/solvers/cycle_reduction.py:246-294 ``_scan_cycle_reduction`` (the scan twin) as a plain loop.
+
+    A fixed ``max_iter``-step scan whose step is ``ifelse(norm < tol, noop, cycle_step)``: only ||A0||_1 is tested, the
+    step counter advances on real steps only, 1e-16 is added to the diagonal before every solve (shared.py:6-9), and
+    ``T = -solve(stabilize(A1_hat), A)`` is ALWAYS computed (there is no convergence flag).  Returns (T, n_steps)."""
+    A0, A1, A2 = (np.asarray(x, dtype=np.float64) for x in (A, B, C))
+    A1_hat = A1
+    n = A0.shape[0]
+    norm, n_steps = 1e9, 0
+    eye = np.eye(n) * 1e-16
+    with np.errstate(all="ignore"):
+        for _ in range(int(max_iter)):
+            if norm < tol:
+                continue
+            tmp = np.vstack([A0, A2]) @ _solve_nanfill(A1 + eye, np.hstack([A0, A2]))
+            A1 = A1 - tmp[:n, n:] - tmp[n:, :n]
+            A1_hat = A1_hat - tmp[n:, :n]
+            A0, A2 = -tmp[:n, :n], -tmp[n:, n:]
+            norm = _l1(A0)
+            n_steps += 1
+        T = -_solve_nanfill(A1_hat + eye, np.asarray(A, dtype=np.float64))
+    return T, n_steps
+
+
 def cycle_reduction_numpy(A0, A1, A2, max_iter=1000, tol=1e-7):
     """gEconpy/solvers/cycle_reduction.py:23-114 ``cycle_reduction_numpy`` (result-string twin).
 

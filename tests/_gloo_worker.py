@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from geconpy_b200.parallel import gather_loglik, shard_bounds, systematic_resample  # noqa: E402
+from geconpy_b200.parallel import fetch_rows, gather_loglik, gather_rows, shard_bounds, systematic_ancestors  # noqa: E402
 
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -19,8 +19,8 @@ assert all_bounds[0][0] == 0 and all_bounds[-1][1] == N and all(a[1] == b[0] for
 local = -torch.arange(lo, hi, dtype=torch.float64)
 full = gather_loglik(local, N)
 assert full.shape == (N,) and torch.equal(full, -torch.arange(N, dtype=torch.float64)), full[:5]
-idx = systematic_resample(full, seed=7)
-idx2 = systematic_resample(full, seed=7)
+idx = systematic_ancestors(full, seed=7)
+idx2 = systematic_ancestors(full, seed=7)
 assert torch.equal(idx, idx2) and idx.shape == (N,) and int(idx.min()) >= 0 and int(idx.max()) < N
 # every rank derives the same ancestors from the gathered weights: no scatter needed
 gathered = [torch.empty_like(idx) for _ in range(world)]
@@ -38,6 +38,20 @@ anc = systematic_ancestors(full, seed=11)
 gathered = [torch.empty_like(anc) for _ in range(world)]
 dist.all_gather(gathered, anc)
 assert all(torch.equal(g, anc) for g in gathered) and int(anc.max()) < N
+# surviving rows only: all_to_all_single with split sizes derived from the (sorted) ancestors == slicing the all-gathered rows
+n_loc = 37
+rows = torch.arange(rank * n_loc, (rank + 1) * n_loc, dtype=torch.float64)[:, None] * torch.tensor([[1.0, 10.0, 100.0]], dtype=torch.float64)
+lw = torch.sin(torch.arange(world * n_loc, dtype=torch.float64))  # same on every rank
+anc2 = systematic_ancestors(lw, seed=3)
+assert bool((anc2[1:] >= anc2[:-1]).all())
+got = fetch_rows(rows, anc2)
+ref = gather_rows(rows)[anc2[rank * n_loc : (rank + 1) * n_loc]]
+assert torch.equal(got, ref), (rank, got[:3], ref[:3])
+try:
+    systematic_ancestors(torch.full((8,), float("-inf"), dtype=torch.float64), seed=1)
+    raise AssertionError("expected a RuntimeError")
+except RuntimeError as e:
+    assert "finite weight" in str(e)
 if rank == 0:
     print("gloo sharding ok")
 dist.destroy_process_group()

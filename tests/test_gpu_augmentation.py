@@ -101,6 +101,36 @@ def test_augmented_pipeline_matches_oracle(name, observed, ta, period, intercept
     assert n_ok >= N // 2
 
 
+@pytest.mark.parametrize("mask_intercept", [True, False])
+def test_mixed_frequency_data_with_a_steady_state_intercept(mask_intercept):
+    """``ss_obs_intercept`` together with NaN data ("last" aggregation: three of four quarters missing) through
+    the whole pipeline, in both conventions for the intercept at missing entries (``configure(mask_intercept=...)``).  In the
+    unmasked convention every missing entry is scored as d_i^2 / jitter: ll ~ -1e8, compared relatively."""
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    name, observed, ta, period, intercept = "rbc", ["Y", "C"], {"Y": "last"}, 4, ["Y", "C"]
+    mod = model(name)
+    cm = CompiledModel(name)
+    ss = BatchedStateSpace(cm).configure(observed_states=observed, measurement_error=observed, tol=1e-9, max_iter=200, temporal_aggregation=ta,
+                                         aggregation_period=period, ss_obs_intercept=intercept, mask_intercept=mask_intercept)  # fmt: skip
+    N = 12
+    th = draws(mod, N, seed=52, width=0.002, valid=True)
+    Y = _aggregated_data(mod, observed, ta, period, intercept, 48, seed=9, dense=False)
+    assert np.isnan(Y[:, 0]).sum() == 36 and not np.isnan(Y[:, 1]).any()
+    sig = np.full((N, mod.k), SIGMA_SHOCK)
+    err = np.full((N, len(observed)), SIGMA_ERR)
+    ll, st = ss.loglik(np.hstack([th, sig, err]), Y)
+    ll_g, grad, st_g = ss.loglik_and_grad(np.hstack([th, sig, err]), Y)
+    for i in range(N):
+        ref = oss.loglik_augmented(mod, th[i], Y, observed, sig[i], err[i], temporal_aggregation=ta, aggregation_period=period,
+                                   ss_obs_intercept=intercept, tol=1e-9, max_iter=200, mask_intercept=mask_intercept)  # fmt: skip
+        assert ref["ok"] and st[i] == 0 and st_g[i] == 0
+        tol = max(TOL_LL, abs(ref["ll"]) * 1e-12)
+        assert abs(ll[i] - ref["ll"]) <= tol and abs(ll_g[i] - ref["ll"]) <= tol, (i, ll[i], ll_g[i], ref["ll"])
+    assert np.isfinite(grad).all()
+    assert (np.abs(ll) < 1e5).all() if mask_intercept else (ll < -1e6).all()
+
+
 def test_measurement_error_positions_follow_the_reference():
     """statespace.py:800-808: error variances fill positions 0..len(error_states)-1 of diag(H)."""
     from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel

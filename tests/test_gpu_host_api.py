@@ -144,8 +144,9 @@ def test_check_bk_condition_api():
     mod = model("rbc_linearized")
     A, B, C, D = mod.jacobians(mod.theta_vector())
     assert check_bk_condition(A, B, C, D, verbose=False, return_value="bool") is True
-    df = check_bk_condition(A, B, C, D, verbose=False)
-    assert int(df["n_forward"][0]) == int(df["n_unstable"][0]) and bool(df["satisfied"][0])
+    df = check_bk_condition(A, B, C, D, verbose=False)  # the reference's per-eigenvalue table (perturbation.py:576-582)
+    assert list(df.columns) == ["Modulus", "Real", "Imaginary"] and len(df) == mod.n + len(mod.permuted_lead_var_idx)
+    assert int((df["Modulus"] > 1).sum()) == len(mod.permuted_lead_var_idx)
     ok, n_fwd, n_unst = check_bk_condition_pt(A, B, C, D, mod.permuted_lead_var_idx)
     assert bool(ok) and n_fwd == int(n_unst)
     bad = model("pert_fails")

@@ -277,6 +277,39 @@ def test_kalman_missing_data_no_measurement_error_and_intercept(B):
             assert abs(ll2[i] - ref2) <= TOL_LL, (i, ll2[i], ref2)
 
 
+@pytest.mark.parametrize("n,p", [(10, 3), (30, 4)])  # one warp per draw / one CTA per draw
+@pytest.mark.parametrize("mask_intercept", [False, True])
+def test_kalman_intercept_meets_missing_data(B, rng, n, p, mask_intercept):
+    """a non-zero observation intercept together with missing entries, in both conventions
+    (gecon_kalman_args.mask_intercept): forward kernels (selector and dense Z) and the gradient kernel against the oracle."""
+    from oracle import adjoints as oad
+
+    N, Tobs, k = 3, 40, 3
+    T, R = _random_statespace(rng, N, n, k)
+    q = 0.5 + rng.random((N, k))
+    h = 0.1 + rng.random((N, p))
+    obs = np.sort(rng.choice(n, size=p, replace=False)).astype(np.int32)
+    Z = np.zeros((p, n))
+    Z[np.arange(p), obs] = 1.0
+    d = 0.5 + 0.1 * rng.standard_normal((N, p))
+    Y = rng.standard_normal((Tobs, p)) + d[0]
+    Y[rng.random(Y.shape) < 0.25] = np.nan
+    Y[4] = np.nan
+    jit = 1e-6  # (at 1e-8 the unmasked convention scores d^2 / jitter ~ 1e7 per missing entry: the comparison loses digits)
+    for kw in (dict(obs_idx=obs), dict(Z=Z)):
+        ll, st = B.kalman_loglik(T, R, q, Y, hdiag=h, d=d, jitter=jit, mask_intercept=mask_intercept, **kw)
+        for i in range(N):
+            ref = oss.kalman_loglik(Y, T[i], R[i], np.diag(q[i]), Z, np.diag(h[i]), d=d[i], jitter=jit, mask_intercept=mask_intercept)
+            assert st[i] == 0 and abs(ll[i] - ref) <= max(TOL_LL, abs(ref) * 1e-12), (n, kw.keys(), i, ll[i], ref)
+    if n <= 48:
+        out = B.kalman_loglik_grad(T, R, q, Y, obs_idx=obs, hdiag=h, d=d, jitter=jit, mask_intercept=mask_intercept)
+        for i in range(N):
+            ref = oad.kalman_loglik_adjoints(Y, T[i], R[i], q[i], Z, h[i], d=d[i], jitter=jit, mask_intercept=mask_intercept)
+            assert abs(out["ll"][i] - ref["ll"]) <= max(TOL_LL, abs(ref["ll"]) * 1e-12)
+            for key in ("T", "R", "q", "h", "d"):
+                assert np.abs(out[key][i] - ref[key]).max() <= 1e-7 * max(1.0, np.abs(ref[key]).max()), (key, i)
+
+
 def _random_statespace(rng, N, n, k, rho=0.9):
     T = rng.standard_normal((N, n, n))
     if n > 1:

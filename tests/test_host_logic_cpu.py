@@ -179,6 +179,20 @@ def test_draw_sharding_and_allgather_world_size_2():
     assert "gloo sharding ok" in r.stdout
 
 
+def test_tempered_smc_stage_world_size_2():
+    """TemperedSMC.stage under two gloo ranks with a stub likelihood: pack / all-gather of (weight, ll, status) / sorted
+    ancestors / all_to_all of the surviving rows, both exchange modes identical, status resampled with its particle."""
+    script = ROOT / "tests" / "_gloo_smc_worker.py"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29579")
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", "29579", str(script)],
+        env=env, capture_output=True, text=True, timeout=300,
+    )  # fmt: skip
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "gloo smc ok" in r.stdout
+
+
 def test_gradient_entry_points_reject_bad_arguments_and_accept_empty_batches():
     """Argument checks of gecon_kalman_grad_* / gecon_policy_adjoint_* run before anything touches a device."""
     from geconpy_b200 import _lib

@@ -10,6 +10,7 @@ from pathlib import Path
 
 import numpy as np
 import pytest
+import scipy.linalg
 import scipy.stats
 
 from helpers import SIGMA_SHOCK, model
@@ -218,6 +219,91 @@ def test_kalman_missing_rows_equal_dropping_them_from_the_joint_density():
     # coordinate observed at 0: it adds -(log 2 pi + log jitter)/2 (a constant in theta) to the exact density
     n_partial_missing = 2
     assert abs(ll - (exact - 0.5 * (np.log(2 * np.pi) + np.log(jit)) * n_partial_missing)) < 1e-6
+
+
+def _joint_cov(T, R, Q, Z, H, n_obs, jitter):
+    """Covariance of (y_1..y_T) for the model the jittered filter is EXACT for (jitter I added to H inside F and to
+    every filtered covariance): observation noise H + j I, and an extra N(0, j I) disturbance of the filtered state before
+    each prediction, i.e. state noise R Q R' + j T T'; the first predicted covariance is dlyap(T, R Q R') of the original model."""
+    n, p = T.shape[0], Z.shape[0]
+    Sig = [oss.dlyap(T, R @ Q @ R.T)]
+    for _ in range(n_obs - 1):
+        Sig.append(T @ Sig[-1] @ T.T + R @ Q @ R.T + jitter * T @ T.T)
+    big = np.zeros((n_obs * p, n_obs * p))
+    for s in range(n_obs):
+        for t in range(n_obs):
+            Cx = np.linalg.matrix_power(T, s - t) @ Sig[t] if s >= t else Sig[s] @ np.linalg.matrix_power(T, t - s).T
+            big[s * p : (s + 1) * p, t * p : (t + 1) * p] = Z @ Cx @ Z.T + ((H + jitter * np.eye(p)) if s == t else 0)
+    return big
+
+
+def _gauss_logpdf(y, cov):
+    """log N(y; 0, cov) by Cholesky (scipy's multivariate_normal truncates eigenvalues: not accurate enough here)."""
+    c = scipy.linalg.cholesky(cov, lower=True)
+    z = scipy.linalg.solve_triangular(c, y, lower=True)
+    return -0.5 * (len(y) * np.log(2.0 * np.pi) + 2.0 * np.log(np.diag(c)).sum() + z @ z)
+
+
+@pytest.mark.parametrize("jitter", [1e-8, 1e-3])
+def test_kalman_jitter_placement_known_answer(jitter):
+    """Known answer at the production jitter (1e-8; 1e-3 makes a misplaced jitter visible).  SURVEY A.5 puts the jitter on H
+    inside F and on every filtered covariance, while the Joseph term K H K' uses H WITHOUT it (as upstream does).  Expanding
+    the Joseph form with P Z' = K F gives the equivalent statement
+        P+ = P - K F K' - j K K' + j I,      F = Z P Z' + H + j I,
+    i.e. the textbook update of the model with observation noise H + j I, minus j K K', plus j I.  That form is written out
+    here independently (no Joseph form, no symmetrisation, explicit inverse) and must reproduce the oracle; at j = 1e-8 the
+    exact joint Gaussian density of the inflated model (noise H + j I, state noise R Q R' + j T T') agrees with both to 1e-7
+    on this regular problem, which is NOT true of the benchmark configurations -- there the placement moves ll by 1e-2 ... 1
+    (see DESIGN.md section 4), so the recursion above is what parity means."""
+    rng = np.random.default_rng(11)
+    n, k, p, n_obs = 4, 2, 2, 14
+    T = 0.5 * rng.standard_normal((n, n))
+    T *= 0.85 / max(abs(np.linalg.eigvals(T)))
+    R = rng.standard_normal((n, k))
+    Q = np.diag(rng.random(k) + 0.5)
+    Z = rng.standard_normal((p, n))
+    H = np.diag([0.05, 0.0])  # one observable without measurement error
+    Y = rng.standard_normal((n_obs, p))
+    ll = oss.kalman_loglik(Y, T, R, Q, Z, H, jitter=jitter)
+    a, P, ref = np.zeros(n), oss.dlyap(T, R @ Q @ R.T), 0.0
+    for t in range(n_obs):
+        F = Z @ P @ Z.T + H + jitter * np.eye(p)
+        Fi = np.linalg.inv(F)
+        K = P @ Z.T @ Fi
+        v = Y[t] - Z @ a
+        ref += -0.5 * (p * np.log(2 * np.pi) + np.log(np.linalg.det(F)) + v @ Fi @ v)
+        a = T @ (a + K @ v)
+        P = T @ (P - K @ F @ K.T - jitter * K @ K.T + jitter * np.eye(n)) @ T.T + R @ Q @ R.T
+    assert abs(ll - ref) < 1e-9
+    if jitter == 1e-8:
+        assert abs(ll - _gauss_logpdf(Y.ravel(), _joint_cov(T, R, Q, Z, H, n_obs, jitter))) < 1e-7
+
+
+@pytest.mark.parametrize("mask_intercept", [False, True])
+def test_kalman_intercept_at_missing_entries(mask_intercept):
+    """a non-zero intercept d meets missing data.  mask_intercept=True: missing entries drop out of the density
+    altogether; False (SURVEY A.5's restatement of upstream): each missing entry of a partially observed row is scored as
+    v_i = -d_i against F_ii = jitter, i.e. adds -(d_i^2 / jitter) / 2 on top."""
+    rng = np.random.default_rng(12)
+    n, k, p, n_obs, jit = 3, 2, 2, 9, 1e-6
+    T = 0.4 * rng.standard_normal((n, n))
+    R = rng.standard_normal((n, k))
+    Q, Z, H = np.eye(k), rng.standard_normal((p, n)), 0.1 * np.eye(p)
+    d = np.array([0.3, -0.2])
+    Y = rng.standard_normal((n_obs, p)) + d
+    Ym = Y.copy()
+    Ym[2, 0] = np.nan
+    Ym[5] = np.nan
+    Ym[7, 1] = np.nan
+    ll = oss.kalman_loglik(Ym, T, R, Q, Z, H, d=d, jitter=jit, mask_intercept=mask_intercept)
+    keep = ~np.isnan(Ym).ravel()
+    big = _joint_cov(T, R, Q, Z, H, n_obs, jit)
+    mean = np.tile(d, n_obs)
+    exact = _gauss_logpdf((Y.ravel() - mean)[keep], big[np.ix_(keep, keep)])
+    extra = -0.5 * (np.log(2 * np.pi) + np.log(jit)) * 2  # two masked entries in partially observed rows (see the test above)
+    if not mask_intercept:
+        extra += -0.5 * (d[0] ** 2 + d[1] ** 2) / jit
+    assert abs(ll - (exact + extra)) < 1e-5 * max(1.0, abs(extra) * 1e-6)
 
 
 def test_dlyap_fixed_point():
