@@ -53,6 +53,10 @@ class GeconLibraryError(RuntimeError):
     pass
 
 
+class CompactJac(C.Structure):
+    _fields_ = [("vals", C.c_void_p), ("stride", C.c_int64), ("table", C.c_void_p), ("off", C.c_int32 * 5), ("reserved", C.c_int32)]
+
+
 class CrArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_size_t),
@@ -88,6 +92,50 @@ class CrArgs(C.Structure):
         ("lead_lo", C.c_int32),
         ("lead_hi", C.c_int32),
         ("scan_semantics", C.c_int32),
+        ("compact", C.c_void_p),
+    ]
+
+
+class PipelineArgs(C.Structure):
+    """gecon_pipeline_args (the fused theta -> log-likelihood entry point)."""
+
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("jacobian", C.c_void_p),
+        ("nz_table", C.c_void_p),
+        ("nz_off", C.c_void_p),
+        ("nnz", C.c_int32),
+        ("n", C.c_int32),
+        ("k", C.c_int32),
+        ("n_theta", C.c_int32),
+        ("n_err", C.c_int32),
+        ("p", C.c_int32),
+        ("n_filter", C.c_int32),
+        ("n_lead", C.c_int32),
+        ("filter_vars", C.c_void_p),
+        ("obs_idx", C.c_void_p),
+        ("lead_idx", C.c_void_p),
+        ("col_ranges", C.c_int32 * 4),
+        ("theta", C.c_void_p),
+        ("theta_stride", C.c_int64),
+        ("N", C.c_int64),
+        ("Y", C.c_void_p),
+        ("Tobs", C.c_int32),
+        ("max_iter", C.c_int32),
+        ("tol", C.c_double),
+        ("solver_tol", C.c_double),
+        ("jitter", C.c_double),
+        ("missing_fill", C.c_double),
+        ("mvn_const_mode", C.c_int32),
+        ("mask_intercept", C.c_int32),
+        ("gate_mask", C.c_int32),
+        ("check_bk", C.c_int32),
+        ("scan_semantics", C.c_int32),
+        ("timing", C.c_int32),
+        ("chunk", C.c_int64),
+        ("ll", C.c_void_p),
+        ("status", C.c_void_p),
+        ("n_iter", C.c_void_p),
     ]
 
 
@@ -107,6 +155,7 @@ class BkArgs(C.Structure):
         ("status", C.c_void_p),
         ("skip_mask", C.c_int32),
         ("reserved0", C.c_int32),
+        ("compact", C.c_void_p),
     ]
 
 
@@ -161,6 +210,8 @@ class KalmanArgs(C.Structure):
         ("z_stride", C.c_int64),
         ("qfull", C.c_void_p),
         ("qfull_stride", C.c_int64),
+        ("h_count", C.c_int32),
+        ("reserved3", C.c_int32),
         ("mask_intercept", C.c_int32),
         ("reserved2", C.c_int32),
     ]
@@ -237,6 +288,7 @@ class PropagateArgs(C.Structure):
 EXPORTS = {
     # name: (restype, argtypes)
     "gecon_abi_version": (C.c_int, []),
+    "gecon_fp64_peak": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gecon_device_count": (C.c_int, []),
     "gecon_get_last_error": (C.c_char_p, []),
     "gecon_launch_count": (C.c_int64, []),
@@ -262,6 +314,8 @@ EXPORTS = {
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p],
     ),
     "gecon_gemm_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
+    "gecon_loglik_pipeline": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gecon_pipeline_stage_ms": (C.c_int, [C.c_void_p]),
     "gecon_real_eig_batched": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gecon_real_eig_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

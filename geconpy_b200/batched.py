@@ -506,5 +506,13 @@ def kernel_info(which: str, n: int, p: int = 1, Tobs: int = 1) -> dict:
     return {"ctas_per_sm": a.value, "smem_bytes": b.value, "threads": c.value}
 
 
+def fp64_peak() -> dict:
+    """Measured fp64 peaks of the current device (``gecon_fp64_peak``): {"dfma_tflops", "dmma_tflops"}."""
+    L.require_device()
+    a, b = C.c_double(), C.c_double()
+    L.check(L.load_library().gecon_fp64_peak(C.byref(a), C.byref(b)), "gecon_fp64_peak")
+    return {"dfma_tflops": a.value, "dmma_tflops": b.value}
+
+
 def launch_count() -> int:
     return int(L.load_library().gecon_launch_count())

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 MODEL_LIBDIR = LIBDIR / "models"
 CORE_LIB = LIBDIR / "libgecon_b200.so"
-CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu", "grad.cu", "eig.cu"]
+CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu", "grad.cu", "eig.cu", "pipeline.cu"]
 # the Kalman kernel is instantiated for (NP, p) in 8 x 8 combinations: one object per padded dimension NP, built in parallel
 KALMAN_INST = "kalman_inst.cu"
 KALMAN_NPS = [8, 16, 24, 32, 40, 48, 56, 64]
@@ -97,10 +97,12 @@ def build_core(force: bool = False, verbose: bool = False) -> Path:
 def build_model(name: str, source: str, force: bool = False) -> Path:
     """Compile one generated model source (a string of CUDA C++) into its own shared library."""
     MODEL_LIBDIR.mkdir(parents=True, exist_ok=True)
-    dig = hashlib.sha256((source + " ".join(NVCC_FLAGS)).encode()).hexdigest()[:16]
+    header = (PKG.parent / "include" / "gecon_b200.h").read_text()  # the generated source includes it (gecon_pipeline_args)
+    dig = hashlib.sha256((source + header + " ".join(NVCC_FLAGS)).encode()).hexdigest()[:16]
     lib = MODEL_LIBDIR / f"libgecon_model_{name}_{dig}.so"
     if lib.exists() and not force:
         return lib
+    build_core()  # the model library links against it
     # several ranks (one process per GPU) may build the same model at once: write source and library under process-private
     # names and move them into place atomically, so that nobody ever dlopens a half-written file
     tag = f".{os.getpid()}.tmp"
@@ -109,7 +111,10 @@ def build_model(name: str, source: str, force: bool = False) -> Path:
     tmp_src.write_text(source)
     nvcc = find_nvcc()
     try:
-        _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-o", str(tmp_lib), str(tmp_src), "-lcudart"])
+        # (the fused entry point gecon_model_loglik calls gecon_loglik_pipeline of the core library: link it, found at run time
+        # next door through $ORIGIN)
+        link = ["-L", str(LIBDIR), "-lgecon_b200", "-Xlinker", "-rpath=$ORIGIN/.."]
+        _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-o", str(tmp_lib), str(tmp_src), *link, "-lcudart"])
         os.replace(tmp_src, src)
         os.replace(tmp_lib, lib)
     finally:

@@ -24,7 +24,7 @@ struct BkSmem {
 };
 
 template <int NP>
-__global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk_args p) {
+__global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk_args p, const gecon_compact_jac cj, double* __restrict__ scratch) {
     using C = Cfg<NP>;
     constexpr int LD = C::LD, NT = C::NT;
     extern __shared__ __align__(16) double sm[];
@@ -44,9 +44,18 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk
 
     for (long long draw = blockIdx.x; draw < p.N; draw += gridDim.x) {
         if (p.accumulate && (p.status[draw] & p.skip_mask)) continue;  // uniform: already decided upstream
-        const double* gA = p.A + (size_t)draw * n * n;
-        const double* gB = p.B + (size_t)draw * n * n;
-        const double* gC = p.C + (size_t)draw * n * n;
+        const double *gA, *gB, *gC;
+        if (cj.vals) {  // compact Jacobian: expand A, B, C of this draw into the CTA's dense scratch
+            double* sc = scratch + (size_t)blockIdx.x * (size_t)3 * n * n;
+            expand_compact(sc, cj, draw, n, 0, 0, 2);
+            gA = sc;
+            gB = sc + (size_t)n * n;
+            gC = sc + (size_t)2 * n * n;
+        } else {
+            gA = p.A + (size_t)draw * n * n;
+            gB = p.B + (size_t)draw * n * n;
+            gC = p.C + (size_t)draw * n * n;
+        }
         // W = (Gamma1 + G)',  X = (Gamma1 - G)'   (element [r][c] of the transpose = element (c, r))
         for (int i = threadIdx.x; i < C::TILE; i += NT) {
             const int r = i / LD, c = i - r * LD;
@@ -137,9 +146,17 @@ static int launch_bk(const gecon_bk_args& a, cudaStream_t st) {
     int grid = 0;
     int rc = persistent_grid(bk_count_kernel<NP>, Cfg<NP>::NT, BkSmem<NP>::bytes, a.N, &grid, nullptr);
     if (rc) return rc;
-    bk_count_kernel<NP><<<grid, Cfg<NP>::NT, BkSmem<NP>::bytes, st>>>(a);
+    gecon_compact_jac cj{};
+    double* scratch = nullptr;
+    if (a.compact) {
+        cj = *a.compact;
+        GECON_CUDA(cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)grid * (size_t)3 * a.n * a.n, st));
+    }
+    bk_count_kernel<NP><<<grid, Cfg<NP>::NT, BkSmem<NP>::bytes, st>>>(a, cj, scratch);
     g_launch_count++;
-    GECON_CUDA(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, st);
+    GECON_CUDA(le);
     return 0;
 }
 
@@ -160,7 +177,7 @@ static int check_bk_args(const gecon_bk_args* a) {
         set_last_error("gecon_bk_args: bad struct_size");
         return GECON_E_BADARG;
     }
-    if (!a->A || !a->B || !a->C || !a->status || a->N < 0 || a->n < 1 || a->n_lead < 0 || a->n_lead > a->n || (a->n_lead > 0 && !a->lead_idx)) {
+    if ((!a->compact && (!a->A || !a->B || !a->C)) || (a->compact && (!a->compact->vals || !a->compact->table)) || !a->status || a->N < 0 || a->n < 1 || a->n_lead < 0 || a->n_lead > a->n || (a->n_lead > 0 && !a->lead_idx)) {
         set_last_error("gecon_bk_args: null pointer or bad dimension");
         return GECON_E_BADARG;
     }
@@ -183,6 +200,10 @@ extern "C" int gecon_bk_count_batched(const gecon_bk_args* args, void* stream) {
 extern "C" int gecon_bk_count_host(const gecon_bk_args* a) {
     int rc = check_bk_args(a);
     if (rc) return rc;
+    if (a->compact) {
+        set_last_error("gecon_bk_count_host: compact Jacobians are a device-entry-point feature");
+        return GECON_E_BADARG;
+    }
     if (a->N == 0) return 0;
     const size_t N = (size_t)a->N, n = a->n, bm = N * n * n * 8;
     DevBuf dA, dB, dC, dL, dU, dS;

@@ -97,6 +97,45 @@ static int launch_gemm(const double* A, const double* B, long long N, int n, int
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ fp64 peak probe
+// Register-resident DFMA and DMMA (mma.sync.m8n8k4.f64) chains with enough independent accumulators to fill the pipe: the
+// denominators of the roofline fractions bench.py reports, measured on the device the run is on (MEASURED_PEAKS.json has no
+// fp64 figure).  Same kernels as profiles/microbench/fp64_peak.cu.
+constexpr int PEAK_ITERS = 4096;
+
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 8
+    for (int i = 0; i < PEAK_ITERS; ++i) {
+        x0 = fma(x0, a, b);
+        x1 = fma(x1, a, b);
+        x2 = fma(x2, a, b);
+        x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b);
+        x5 = fma(x5, a, b);
+        x6 = fma(x6, a, b);
+        x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, double a, double b) {
+    double c[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        c[j][0] = threadIdx.x + j;
+        c[j][1] = j;
+    }
+    for (int i = 0; i < PEAK_ITERS; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(c[j][0], c[j][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += c[j][0] + c[j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int cr_kernel_info(int n, int* ctas, int* smem, int* threads);
 int kf_kernel_info(int n, int p, int Tobs, int* ctas, int* smem, int* threads);
 int lyap_kernel_info(int n, int* ctas, int* smem, int* threads);
@@ -118,6 +157,41 @@ extern "C" int gecon_device_count(void) {
 }
 
 extern "C" const char* gecon_get_last_error(void) { return t_err; }
+
+extern "C" int gecon_fp64_peak(double* dfma_tflops, double* dmma_tflops) {
+    const int sms = sm_count();
+    if (sms < 1) return GECON_E_NO_DEVICE;
+    const int blocks = sms * 8, threads = 256;
+    double* out = nullptr;
+    GECON_CUDA(cudaMalloc((void**)&out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best[2] = {0.0, 0.0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 6; ++rep) {  // the first repetitions warm the clocks up; best of the rest
+            cudaEventRecord(e0, nullptr);
+            if (which == 0) peak_dfma_kernel<<<blocks, threads>>>(out, 0.999999, 1e-9);
+            else peak_dmma_kernel<<<blocks, threads>>>(out, 0.999999, 1e-9);
+            cudaEventRecord(e1, nullptr);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            // DFMA: 8 chains x 2 flops per thread and iteration; DMMA: 4 products of 8 x 8 x 4 x 2 flops per warp and iteration
+            const double flops = which == 0 ? (double)blocks * threads * PEAK_ITERS * 16.0 : (double)blocks * (threads / 32) * PEAK_ITERS * 4.0 * 512.0;
+            const double tf = flops / (ms * 1e-3) / 1e12;
+            if (rep >= 2 && tf > best[which]) best[which] = tf;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const cudaError_t le = cudaGetLastError();
+    cudaFree(out);
+    GECON_CUDA(le);
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
+    return 0;
+}
 
 extern "C" int64_t gecon_launch_count(void) { return (int64_t)g_launch_count.load(); }
 

@@ -27,6 +27,23 @@ inline int fail_cuda(cudaError_t e, const char* what) {
 
 inline int round_up8(int n) { return (n + 7) / 8 * 8; }
 
+// The stream-ordered allocator gives freed memory back to the driver at the next synchronisation unless its pool is told to
+// keep it: the per-call workspaces (cudaMallocAsync / cudaFreeAsync around every launch) would be re-mapped on every step.
+// Called once per device before the first cudaMallocAsync.
+inline void keep_mempool(void) {
+    static std::atomic<unsigned> done{0u};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+    const unsigned bit = 1u << dev;
+    if (done.load() & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done.fetch_or(bit);
+}
+
 // number of SMs of the current device (cached per device would be nicer; the query is cheap)
 inline int sm_count() {
     int dev = 0, sms = 0;

@@ -43,7 +43,8 @@ constexpr int cr_min_ctas() {
 }
 
 template <int NP>
-__global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kernel(const gecon_cr_args p, double* __restrict__ ws) {
+__global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kernel(const gecon_cr_args p, double* __restrict__ ws,
+                                                                                  const gecon_compact_jac cj, double* __restrict__ scratch) {
     using C = Cfg<NP>;
     constexpr int LD = C::LD;
     extern __shared__ __align__(16) double sm[];
@@ -72,11 +73,21 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
     for (int i = threadIdx.x; i < nl; i += C::NT) s_lead[i] = p.lead_idx[i];
 
     for (long long draw = blockIdx.x; draw < p.N; draw += gridDim.x) {
-        const double* gA = p.A + (size_t)draw * n * n;
-        const double* gB = p.B + (size_t)draw * n * n;
-        const double* gC = p.C ? p.C + (size_t)draw * n * n : nullptr;
-        const double* gD = p.D ? p.D + (size_t)draw * n * k : nullptr;
-        {   // the next draw of this CTA: pull its A, B, C (freshly written by the Jacobian kernel, i.e. in HBM) into L2 now, so
+        const double *gA, *gB, *gC, *gD;
+        if (cj.vals) {  // compact Jacobian: expand this draw into the CTA's dense scratch (L2-resident) and read that
+            double* sc = scratch + (size_t)blockIdx.x * ((size_t)3 * n * n + (size_t)n * k);
+            expand_compact(sc, cj, draw, n, k, 0, 3);
+            gA = sc;
+            gB = sc + (size_t)n * n;
+            gC = (cj.off[3] > cj.off[2]) ? sc + (size_t)2 * n * n : nullptr;  // no lead entries at all: backward-looking system
+            gD = (p.R && cj.off[4] > cj.off[3]) ? sc + (size_t)3 * n * n : nullptr;
+        } else {
+            gA = p.A + (size_t)draw * n * n;
+            gB = p.B + (size_t)draw * n * n;
+            gC = p.C ? p.C + (size_t)draw * n * n : nullptr;
+            gD = p.D ? p.D + (size_t)draw * n * k : nullptr;
+        }
+        if (!cj.vals) {   // the next draw of this CTA: pull its A, B, C (freshly written by the Jacobian kernel, i.e. in HBM) into L2 now, so
             // that its tile loads ~150 us from now do not wait on DRAM (12.5 % of the stall samples were those loads)
             const long long nxt = draw + gridDim.x;
             if (nxt < p.N) {
@@ -377,7 +388,12 @@ static int check_cr_args(const gecon_cr_args* a) {
         set_last_error("gecon_cr_args: bad struct_size");
         return GECON_E_BADARG;
     }
-    if (!a->A || !a->B || !a->T || !a->status || a->N < 0 || a->n < 1 || a->k < 0 || (a->R && !a->D)) {
+    const bool cmp = a->compact != nullptr;
+    if (cmp && (!a->compact->vals || !a->compact->table || a->compact->stride < a->compact->off[4] || a->compact->off[0] != 0)) {
+        set_last_error("gecon_cr_args: malformed compact Jacobian descriptor");
+        return GECON_E_BADARG;
+    }
+    if ((!cmp && (!a->A || !a->B)) || !a->T || !a->status || a->N < 0 || a->n < 1 || a->k < 0 || (!cmp && a->R && !a->D)) {
         set_last_error("gecon_cr_args: null pointer or bad dimension");
         return GECON_E_BADARG;
     }
@@ -412,12 +428,18 @@ static int launch_cr(const gecon_cr_args& a, cudaStream_t st) {
     int grid = 0;
     int rc = persistent_grid(cr_solve_kernel<NP>, Cfg<NP>::NT, CrSmem<NP>::bytes, a.N, &grid, nullptr, "GECON_CR_CTAS_PER_SM");
     if (rc) return rc;
-    double* ws = nullptr;
+    double *ws = nullptr, *scratch = nullptr;
     if (cr_a1h_global<NP>()) GECON_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)grid * Cfg<NP>::TILE, st));
-    cr_solve_kernel<NP><<<grid, Cfg<NP>::NT, CrSmem<NP>::bytes, st>>>(a, ws);
+    gecon_compact_jac cj{};
+    if (a.compact) {
+        cj = *a.compact;
+        GECON_CUDA(cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)grid * ((size_t)3 * a.n * a.n + (size_t)a.n * a.k), st));
+    }
+    cr_solve_kernel<NP><<<grid, Cfg<NP>::NT, CrSmem<NP>::bytes, st>>>(a, ws, cj, scratch);
     g_launch_count++;
     const cudaError_t le = cudaGetLastError();
     if (ws) cudaFreeAsync(ws, st);
+    if (scratch) cudaFreeAsync(scratch, st);
     GECON_CUDA(le);
     return 0;
 }
@@ -443,7 +465,8 @@ using namespace gecon;
 // GECON_CR_KERNEL=cta|warp overrides the choice (warp: wherever it is eligible).
 static bool cr_warp_eligible(const gecon_cr_args& a, cw_ranges* rg, int* c_out) {
     const int np = round_up8(a.n);
-    if (!a.C || np > 32 || a.solv_norms) return false;
+    const bool has_c = a.compact ? (a.compact->off[3] > a.compact->off[2]) : (a.C != nullptr);
+    if (!has_c || np > 32 || a.solv_norms) return false;
     const char* e = getenv("GECON_CR_KERNEL");
     if (e && strcmp(e, "cta") == 0) return false;
     const bool hint = (a.lag_hi > a.lag_lo) || (a.lead_hi > a.lead_lo);
@@ -451,7 +474,7 @@ static bool cr_warp_eligible(const gecon_cr_args& a, cw_ranges* rg, int* c_out) 
     rg->w0 = hint ? a.lag_hi - rg->o0 : a.n;
     rg->o2 = hint ? (a.lead_lo & ~1) : 0;
     rg->w2 = hint ? a.lead_hi - rg->o2 : a.n;
-    const int kd = (a.D && a.R) ? a.k : 0;
+    const int kd = ((a.D || a.compact) && a.R) ? a.k : 0;
     const int nl = a.lead_idx ? a.n_lead : 0;
     int w = rg->w0 > rg->w2 ? rg->w0 : rg->w2;
     w = kd > w ? kd : w;
@@ -460,8 +483,8 @@ static bool cr_warp_eligible(const gecon_cr_args& a, cw_ranges* rg, int* c_out) 
     if (c < 1) c = 1;
     if (8 * c > np) return false;
     *c_out = c;
-    if (e && strcmp(e, "warp") == 0) return true;
-    return np <= 24;
+    // measured (r02): 33.8 vs 52.8 ms per 262,144 draws at NP = 24, 26.1 vs 52.3 ms per 131,072 at NP = 32, 2.5 vs 4.5 ms per 65,536 at NP = 16
+    return true;
 }
 
 static int launch_cr_warp(const gecon_cr_args& a, const cw_ranges& rg, int c, cudaStream_t st, int* info) {
@@ -494,8 +517,8 @@ extern "C" int gecon_cr_solve_host(const gecon_cr_args* args) {
     int rc = check_cr_args(args);
     if (rc) return rc;
     if (args->N == 0) return 0;
-    if (args->t_stride || args->r_stride || args->t_ld) {
-        set_last_error("gecon_cr_solve_host: strided outputs are a device-entry-point feature");
+    if (args->t_stride || args->r_stride || args->t_ld || args->compact) {
+        set_last_error("gecon_cr_solve_host: strided outputs and compact Jacobians are device-entry-point features");
         return GECON_E_BADARG;
     }
     const size_t N = (size_t)args->N, n = args->n, k = args->k;

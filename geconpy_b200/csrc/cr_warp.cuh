@@ -74,6 +74,25 @@ __device__ __noinline__ void cw_load(double* __restrict__ dst, int ldt, int widt
     }
 }
 
+// The same from a compact Jacobian (gecon_compact_jac): matrix q (0 = A, 1 = B, 2 = C, 3 = D) of draw `draw`, columns
+// [col_lo, col_hi) -> `width` columns of a zeroed NP-row tile.  The structural non-zeros are ~5 % of the dense entries, so
+// this is a handful of scattered stores instead of NP row loads.
+template <int NP>
+__device__ __noinline__ void cw_load_compact(double* __restrict__ dst, int ldt, int width, const gecon_compact_jac& cj, long long draw, int q, int col_lo,
+                                             int col_hi, int lane) {
+    for (int c = lane; c < width; c += 32) {
+#pragma unroll 4
+        for (int r = 0; r < NP; ++r) dst[r * ldt + c] = 0.0;
+    }
+    __syncwarp();
+    const double* v = cj.vals + (size_t)draw * cj.stride;
+    for (int e = cj.off[q] + lane; e < cj.off[q + 1]; e += 32) {
+        const int rc = cj.table[e];
+        const int c = (rc & 0xffff) - col_lo;
+        if (c >= 0 && (rc & 0xffff) < col_hi && c < width) dst[(rc >> 16) * ldt + c] = v[e];
+    }
+}
+
 // max absolute column sum over `rows` rows x `width` columns (leading dimension ldt); every lane gets it; NaN-propagating
 static __device__ __noinline__ double cw_norm1(const double* __restrict__ M, int ldt, int rows, int width, int lane) {
     double mx = 0.0;
@@ -340,7 +359,8 @@ constexpr int cw_min_ctas() {
 }
 
 template <int NP, int C, int WPC>
-__global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_kernel(const gecon_cr_args p, const cw_ranges rg) {
+__global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_kernel(const gecon_cr_args p, const cw_ranges rg,
+                                                                                      const gecon_compact_jac cj) {
     using K = CwCfg<NP, C>;
     constexpr int LD = K::LD, LDW = K::LDW, LDC = K::LDC, NS = K::NS, KS = K::KS, XA = K::XA, XB = K::XB;
     extern __shared__ __align__(16) double sm[];
@@ -368,17 +388,26 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
     const int o0 = rg.o0, w0 = rg.w0, o2 = rg.o2, w2 = rg.w2;
     const int nt0 = (w0 + 7) >> 3, nt2 = (w2 + 7) >> 3;   // column tiles of the packed ranges
     const int nk0 = (w0 + 3) >> 2, nk2 = (w2 + 3) >> 2;   // k-steps
-    const int kd = (p.D && p.R) ? k : 0;
+    const int kd = ((p.D || cj.vals) && p.R) ? k : 0;
     const int ntd = (kd + 7) >> 3;
     const long long stride = (long long)gridDim.x * WPC;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
     for (long long draw = (long long)blockIdx.x * WPC + warp; draw < p.N; draw += stride) {
-        const double* gA = p.A + (size_t)draw * n * n;
-        const double* gB = p.B + (size_t)draw * n * n;
-        const double* gC = p.C + (size_t)draw * n * n;
-        const double* gD = p.D ? p.D + (size_t)draw * n * k : nullptr;
-        {   // this warp's next draw: pull A, B, C into L2 now (they were just written by the Jacobian kernel, i.e. sit in HBM)
+        const bool cmp = cj.vals != nullptr;
+        const double* gA = cmp ? nullptr : p.A + (size_t)draw * n * n;
+        const double* gB = cmp ? nullptr : p.B + (size_t)draw * n * n;
+        const double* gC = cmp ? nullptr : p.C + (size_t)draw * n * n;
+        const double* gD = (cmp || !p.D) ? nullptr : p.D + (size_t)draw * n * k;
+        // matrix q (A, B, C, D) of this draw, columns [lo, hi) -> tile: dense rows or compact scatter
+        auto load = [&](double* dst, int ldt, int width, int q, const double* src, int lo, int hi, int ldg) {
+            if (cmp) cw_load_compact<NP>(dst, ldt, width, cj, draw, q, lo, hi, lane);
+            else cw_load<NP>(dst, ldt, width, src, n, lo, hi, ldg, lane);
+        };
+        if (cmp) {  // this warp's next draw: its compact vector (a few cache lines) into L2
+            const long long nxt = draw + stride;
+            if (nxt < p.N && lane * 16 < cj.off[4]) prefetch_l2(cj.vals + (size_t)nxt * cj.stride + lane * 16);
+        } else {   // this warp's next draw: pull A, B, C into L2 now (they were just written by the Jacobian kernel, i.e. sit in HBM)
             const long long nxt = draw + stride;
             if (nxt < p.N) {
                 const size_t bytes = (size_t)n * n * sizeof(double);
@@ -389,9 +418,9 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
                 }
             }
         }
-        cw_load<NP>(A1, LD, LD, gB, n, 0, n, n, lane);
-        cw_load<NP>(X0, LDW, 8 * C, gA, n, o0, o0 + w0, n, lane);
-        cw_load<NP>(X2, LDW, 8 * C + 4, gC, n, o2, o2 + w2, n, lane);  // (+ 4: the tile's padding columns)
+        load(A1, LD, LD, 1, gB, 0, n, n);
+        load(X0, LDW, 8 * C, 0, gA, o0, o0 + w0, n);
+        load(X2, LDW, 8 * C + 4, 2, gC, o2, o2 + w2, n);  // (+ 4: the tile's padding columns)
         double H[NS][C][2];  // sum of A2 X0 over the iterations: A1hat = B - H on the lag columns
         cw_acc_zero<NS, C>(H);
         __syncwarp();
@@ -494,8 +523,8 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
         bool t_nan = (p.scan_semantics && gj_failed);                         // (... from NaN-filled matrices after a failed solve)
         const bool solve_t = converged || (p.scan_semantics && !gj_failed);  // the scan twin always solves for T
         if (solve_t) {
-            cw_load<NP>(WA, LDW, NP, gB, n, 0, n, n, lane);
-            cw_load<NP>(X0, LDW, 8 * C, gA, n, o0, o0 + w0, n, lane);
+            load(WA, LDW, NP, 1, gB, 0, n, n);
+            load(X0, LDW, 8 * C, 0, gA, o0, o0 + w0, n);
             __syncwarp();
             cw_sub_into<NP, C>(WA, LDW, H, o0, nt0, lane);
             __syncwarp();
@@ -515,8 +544,9 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
         __syncwarp();
 
         // ---- W = B + C T (only the lag columns differ from B); resid = sum((A + W T)^2) = sum((A + B T + C T T)^2)
-        cw_load<NP>(WA, LDW, NP, gB, n, 0, n, n, lane);
-        cw_load<NP>(X2, LDW, 8 * C, gC, n, o2, o2 + w2, n, lane);
+        load(WA, LDW, NP, 1, gB, 0, n, n);
+        load(X2, LDW, 8 * C, 2, gC, o2, o2 + w2, n);
+        load(X0, LDW, 8 * C, 0, gA, o0, o0 + w0, n);  // A again, for the residual (the Xa block is free: T lives in the A1 region)
         __syncwarp();
         {
             double cf[NS][KS];
@@ -539,10 +569,7 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
 #pragma unroll
                 for (int ct = 0; ct < C; ++ct)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int r = 8 * s + g, pc = 8 * ct + 2 * q + h;
-                        e[s][ct][h] = (r < n && pc < w0) ? gA[(size_t)r * n + o0 + pc] : 0.0;  // (L2-resident: read above)
-                    }
+                    for (int h = 0; h < 2; ++h) e[s][ct][h] = X0[(8 * s + g) * LDW + 8 * ct + 2 * q + h];
             const int nkn = (n + 3) >> 2;
 #pragma unroll 1
             for (int ks = 0; ks < nkn; ++ks) {
@@ -591,7 +618,7 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
         const bool want_cert = p.lead_idx && converged && !t_nan;
         bool have_F = false;
         if (kd || want_cert) {
-            if (kd) cw_load<NP>(X0, LDW, 8 * C, gD, n, 0, kd, k, lane);
+            if (kd) load(X0, LDW, 8 * C, 3, gD, 0, kd, k);
             __syncwarp();
             const bool ok = cw_gj<NP, C>(WA, ntd, want_cert ? nt2 : 0, n, s_piv, s_flag, lane);
             if (!ok) status |= GECON_ST_SINGULAR;

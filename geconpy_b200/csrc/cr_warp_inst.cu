@@ -26,7 +26,9 @@ static int launch_cw_w(const gecon_cr_args& a, const cw_ranges& rg, cudaStream_t
         info[2] = WPC * 32;
         return 0;
     }
-    cr_warp_kernel<NP, C, WPC><<<grid, WPC * 32, smem, st>>>(a, rg);
+    gecon_compact_jac cj{};
+    if (a.compact) cj = *a.compact;
+    cr_warp_kernel<NP, C, WPC><<<grid, WPC * 32, smem, st>>>(a, rg, cj);
     g_launch_count++;
     GECON_CUDA(cudaGetLastError());
     return 0;

@@ -25,16 +25,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __global__ void __launch_bounds__(32) real_eig_kernel(const double* __restrict__ M, long long N, int m, int balance, double* __restrict__ re,
                                                       double* __restrict__ im, int* __restrict__ status) {
+    // (m, H, wr, wi are re-pointed at the active block of the balanced matrix while a matrix is being worked on)
     extern __shared__ __align__(16) double sm_eig[];
     const int ld = m | 1;  // odd leading dimension: rows and columns are both conflict-free
     double* H = sm_eig;
     double* ort = H + (size_t)m * ld;  // [m] Householder vector
     double* wr = ort + m;              // [m]
     double* wi = wr + m;               // [m]
+    const int m_in = m;
     const int lane = threadIdx.x;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
     for (long long mat = blockIdx.x; mat < N; mat += gridDim.x) {
+        m = m_in;
         const double* g = M + (size_t)mat * m * m;
         bool finite = true;
         for (int idx = lane; idx < m * m; idx += 32) {
@@ -49,7 +52,71 @@ __global__ void __launch_bounds__(32) real_eig_kernel(const double* __restrict__
         if (!finite) {
             st = GECON_ST_LL_NONFINITE;
         } else {
-            // ---- 1. balancing (scaling by powers of two only; eigenvalues are invariant)
+            // ---- 1. balancing, as dgebal: first PERMUTE so that rows / columns which isolate an eigenvalue move to the bottom / top
+            // (their eigenvalues are then diagonal entries, exact), then scale the remaining block [lo, hi] by powers of two
+            int lo = 0, hi = m - 1;
+            if (balance) {
+                auto exchange = [&](int a, int b) {  // similarity permutation: swap rows a, b and columns a, b
+                    if (a == b) return;
+                    for (int j = lane; j < m; j += 32) {
+                        const double t = H[a * ld + j];
+                        H[a * ld + j] = H[b * ld + j];
+                        H[b * ld + j] = t;
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < m; i += 32) {
+                        const double t = H[i * ld + a];
+                        H[i * ld + a] = H[i * ld + b];
+                        H[i * ld + b] = t;
+                    }
+                    __syncwarp();
+                };
+                bool again = true;
+                while (again && hi > lo) {  // rows with zero off-diagonal part inside the active block -> bottom
+                    again = false;
+                    for (int j = hi; j >= lo; --j) {
+                        double r = 0.0;
+                        for (int i = lo + lane; i <= hi; i += 32)
+                            if (i != j) r += fabs(H[j * ld + i]);
+                        if (warp_sum(r) == 0.0) {
+                            exchange(j, hi);
+                            --hi;
+                            again = true;
+                            break;
+                        }
+                    }
+                }
+                again = true;
+                while (again && hi > lo) {  // columns with zero off-diagonal part inside the active block -> top
+                    again = false;
+                    for (int j = lo; j <= hi; ++j) {
+                        double c = 0.0;
+                        for (int i = lo + lane; i <= hi; i += 32)
+                            if (i != j) c += fabs(H[i * ld + j]);
+                        if (warp_sum(c) == 0.0) {
+                            exchange(j, lo);
+                            ++lo;
+                            again = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            for (int i = lane; i < m; i += 32) {  // isolated eigenvalues (overwritten below for the active block)
+                wr[i] = H[i * ld + i];
+                wi[i] = 0.0;
+            }
+            __syncwarp();
+            double* const Hfull = H;
+            double* const wr_full = wr;
+            double* const wi_full = wi;
+            (void)Hfull;
+            // everything below works on the active block only
+            H = Hfull + lo * ld + lo;
+            wr = wr_full + lo;
+            wi = wi_full + lo;
+            const int m_full = m;
+            m = hi - lo + 1;
             if (balance) {
                 for (int pass = 0; pass < 20; ++pass) {
                     bool last = true;
@@ -276,6 +343,10 @@ __global__ void __launch_bounds__(32) real_eig_kernel(const double* __restrict__
                 } while (l < nn - 1 && !failed);
             }
             if (failed) st = GECON_ST_BK_INCONCLUSIVE;
+            H = Hfull;
+            wr = wr_full;
+            wi = wi_full;
+            m = m_full;
         }
         __syncwarp();
         for (int i = lane; i < m; i += 32) {

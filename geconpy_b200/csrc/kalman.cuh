@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, kf_min_ctas<NP>()) kalman_ll_kern
             s_q[tid] = p.sigma_inputs ? qv * qv : qv;
         }
         if (tid < PT) {
-            const double hv = p.hdiag ? p.hdiag[(size_t)draw * p.h_stride + tid] : 0.0;
+            const double hv = (p.hdiag && (p.h_count <= 0 || (int)tid < p.h_count)) ? p.hdiag[(size_t)draw * p.h_stride + tid] : 0.0;
             s_h[tid] = p.sigma_inputs ? hv * hv : hv;
             s_d[tid] = p.d ? p.d[(size_t)draw * p.d_stride + tid] : 0.0;
         }

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
         double hv[PT], dv0[PT];
 #pragma unroll
         for (int a = 0; a < PT; ++a) {
-            const double h = p.hdiag ? p.hdiag[(size_t)draw * p.h_stride + a] : 0.0;
+            const double h = (p.hdiag && (p.h_count <= 0 || a < p.h_count)) ? p.hdiag[(size_t)draw * p.h_stride + a] : 0.0;
             hv[a] = p.sigma_inputs ? h * h : h;
             dv0[a] = p.d ? p.d[(size_t)draw * p.d_stride + a] : 0.0;
         }

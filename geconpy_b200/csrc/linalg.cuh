@@ -16,6 +16,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "../../include/gecon_b200.h"
+
 namespace gecon {
 
 template <int NP>
@@ -93,6 +95,29 @@ __device__ __forceinline__ void gemm_acc(Acc<NP>& acc, const double* __restrict_
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// Compact Jacobian (gecon_compact_jac) -> dense row-major scratch in global memory, by the whole CTA: matrices `first..last`
+// (0 = A, 1 = B, 2 = C: n x n; 3 = D: n x k) at dst + q * n * n.  The CTA-per-draw kernels expand the draw they are about to
+// work on into a per-CTA scratch (it stays in L2) and then read it exactly like caller-provided dense matrices.
+// Contains barriers: every thread of the CTA must call it.
+__device__ __forceinline__ void expand_compact(double* __restrict__ dst, const gecon_compact_jac& cj, long long draw, int n, int k, int first,
+                                               int last) {
+    const int nt = blockDim.x;
+    const size_t total = (size_t)(last < 3 ? (last - first + 1) * n * n : (3 - first) * n * n + n * k);
+    double* base = dst + (size_t)first * n * n;
+    for (size_t i = threadIdx.x; i < total; i += nt) base[i] = 0.0;
+    __syncthreads();
+    const double* v = cj.vals + (size_t)draw * cj.stride;
+    for (int q = first; q <= last; ++q) {
+        const int ldq = (q == 3) ? k : n;
+        double* m = dst + (size_t)q * n * n;
+        for (int e = cj.off[q] + threadIdx.x; e < cj.off[q + 1]; e += nt) {
+            const int rc = cj.table[e];
+            m[(rc >> 16) * ldq + (rc & 0xffff)] = v[e];
+        }
+    }
+    __syncthreads();
+}
 
 // ------------------------------------------------------------------------------------------------ tile helpers
 template <int NP>

@@ -465,12 +465,15 @@ _TEMPLATE = r"""// GENERATED by geconpy_b200/model/codegen.py for model "{name}"
 #define __restrict__
 #else
 #include <cuda_runtime.h>
+#include "gecon_b200.h"
 #endif
 
 #define GECON_MODEL_N {n}
 #define GECON_MODEL_K {k}
 #define GECON_MODEL_NTHETA {n_theta}
+#ifndef GECON_ST_JAC_NONFINITE
 #define GECON_ST_JAC_NONFINITE 0x200
+#endif
 
 #define GECON_MODEL_NNZ {nnz}
 // structural non-zeros of A, B, C, D (row << 16 | col), grouped by matrix: entries of matrix q are [off[q], off[q + 1])
@@ -590,6 +593,28 @@ extern "C" int gecon_model_structure(int32_t* nnz, const int32_t** table, const 
     if (n_lead) *n_lead = {n_lead};
     if (lead_idx) *lead_idx = gecon_lead_idx_h;
     return 0;
+}}
+
+// The fused theta -> log-likelihood entry point of this model (include/gecon_b200.h, gecon_pipeline_args): fills in the model's
+// own kernel and structure tables and runs the core library's pipeline.
+extern "C" int gecon_model_loglik(gecon_pipeline_args* a, void* stream) {{
+    if (!a) return -1;
+    a->jacobian = gecon_model_jacobian_compact;
+    a->nz_table = gecon_nz_table_h;
+    a->nz_off = gecon_nz_off_h;
+    a->nnz = GECON_MODEL_NNZ;
+    a->n = GECON_MODEL_N;
+    a->k = GECON_MODEL_K;
+    a->n_theta = GECON_MODEL_NTHETA;
+    a->col_ranges[0] = {lag_lo};
+    a->col_ranges[1] = {lag_hi};
+    a->col_ranges[2] = {lead_lo};
+    a->col_ranges[3] = {lead_hi};
+    if (a->check_bk && !a->lead_idx) {{
+        a->lead_idx = gecon_lead_idx_h;
+        a->n_lead = {n_lead};
+    }}
+    return gecon_loglik_pipeline(a, stream);
 }}
 
 // DEVICE pointers: theta_bar[N][n_theta] = vector-Jacobian product of (A_bar, B_bar, C_bar, D_bar, xss_bar or NULL)

@@ -51,6 +51,12 @@ class CompiledModel:
         self._vjp_dev = self._lib.gecon_model_vjp_batched
         self._vjp_dev.restype = C.c_int
         self._vjp_dev.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        self._loglik = self._lib.gecon_model_loglik  # the fused theta -> log-likelihood entry point (gecon_pipeline_args)
+        self._loglik.restype = C.c_int
+        self._loglik.argtypes = [C.POINTER(L.PipelineArgs), C.c_void_p]
+        self._jac_compact = self._lib.gecon_model_jacobian_compact
+        self._jac_compact.restype = C.c_int
+        self._jac_compact.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         n, k, nt = C.c_int32(), C.c_int32(), C.c_int32()
         self.launches = 0  # kernel launches made through this model library (bench.py's gpu_launches)
         self._lib.gecon_model_info(C.byref(n), C.byref(k), C.byref(nt))
@@ -84,6 +90,24 @@ class CompiledModel:
         self.launches += 1
         if rc != 0:
             raise L.GeconLibraryError(f"gecon_model_jacobian_batched({self.name}) failed with CUDA error {rc}")
+
+    def structure(self):
+        """``gecon_model_structure``: (nnz, table[nnz], off[5], col_ranges[4], lead_idx) of the generated library -- the layout of the
+        compact Jacobian and the structural ranges, as numpy arrays (copied)."""
+        nnz, nlead = C.c_int32(), C.c_int32()
+        table, off, lead = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        rng = (C.c_int32 * 4)()
+        self._lib.gecon_model_structure(C.byref(nnz), C.byref(table), C.byref(off), rng, C.byref(nlead), C.byref(lead))
+        return (nnz.value, np.array([table[i] for i in range(nnz.value)], dtype=np.int32), np.array([off[i] for i in range(5)], dtype=np.int32),
+                tuple(int(v) for v in rng), np.array([lead[i] for i in range(nlead.value)], dtype=np.int32))
+
+    def jacobian_compact_device(self, theta, vals, status, stream, theta_stride=None) -> None:
+        """theta [N, >= n_theta] (torch CUDA, rows may be wider than n_theta) -> vals [N, nnz]: structural non-zeros only."""
+        rc = self._jac_compact(theta.data_ptr(), int(theta_stride or theta.shape[1]), theta.shape[0], vals.data_ptr(), None,
+                               status.data_ptr() if status is not None else None, C.c_void_p(stream))
+        self.launches += 1
+        if rc != 0:
+            raise L.GeconLibraryError(f"gecon_model_jacobian_compact({self.name}) failed with CUDA error {rc}")
 
     def vjp_device(self, theta, A_bar, B_bar, C_bar, D_bar, xss_bar, theta_bar, stream) -> None:
         """theta_bar[N, n_theta] = <(A_bar, B_bar, C_bar, D_bar[, xss_bar]), d(A, B, C, D[, x_ss])/dtheta> on device pointers: the
@@ -152,6 +176,7 @@ class BatchedStateSpace:
         full_shock_covariance: bool = False,
         mask_intercept: bool = False,
         constant_params=None,
+        fused: bool | None = None,
         mode=None,
         verbose: bool = True,
         use_adjoint_gradients: bool = True,
@@ -321,6 +346,14 @@ class BatchedStateSpace:
             self.gate_mask |= L.ST_BK | L.ST_BK_INCONCLUSIVE
         if self.add_solver_success_check:
             self.gate_mask |= L.ST_RESID | L.ST_CR_NOT_CONVERGED
+        # the fused C entry point (gecon_model_loglik) covers plain state spaces; everything else runs the Python pipeline
+        eligible = (self.dense_Z is None and self._obs_lib is None and not self.ss_obs_intercept and not self.full_covariance
+                    and self.n_aug == self.n_filter and self.solver != "backward_direct" and self.n_streams == 1)  # fmt: skip
+        if fused and not eligible:
+            raise ValueError("fused=True needs a plain state space: selector observations, diagonal shock covariance, no state "
+                             "augmentation / observation equations / steady-state intercept, a forward-looking solver")
+        self.fused = eligible if fused is None else bool(fused)
+        self.fused = self.fused and os.environ.get("GECON_FUSED", "1") != "0"
         self.configured = True
         self._ws = None
         self._ws_extra = {}  # per-stream workspaces of the multi-stream pipeline: shapes depend on the configuration
@@ -401,6 +434,8 @@ class BatchedStateSpace:
         Tobs = Y.shape[0]
         ll = out_ll if out_ll is not None else torch.empty((N,), dtype=torch.float64, device=dev)
         status = out_status if out_status is not None else torch.empty((N,), dtype=torch.int32, device=dev)
+        if self.fused and max(1, int(getattr(self, "n_streams", 1))) == 1:
+            return self._loglik_fused(theta_full, Y, ll, status, out_n_iter, events)
         nc = min(self.chunk, N)
         n_err = len(self.measurement_error)
         n_streams = max(1, int(getattr(self, "n_streams", 1)))
@@ -504,6 +539,39 @@ class BatchedStateSpace:
                 done = torch.cuda.Event()
                 done.record(s_)
                 cur.wait_event(done)
+        return ll, status
+
+    def _loglik_fused(self, theta_full, Y, ll, status, out_n_iter, events):
+        """One call of the generated library's ``gecon_model_loglik`` (include/gecon_b200.h, gecon_pipeline_args): the whole chunk
+        loop runs in C on the current stream -- compact Jacobian, solver, Blanchard-Kahn count, filter -- with no torch kernel
+        in between.  ``events`` (bench.py's per-kernel timing hook) turns on the pipeline's own CUDA-event timing."""
+        m = self.model
+        dev = theta_full.device
+        theta_full = theta_full.contiguous()
+        fv = np.ascontiguousarray(self.filter_vars, dtype=np.int32)
+        obs = np.ascontiguousarray(self.obs_idx_filter, dtype=np.int32)
+        lead = np.ascontiguousarray(m.permuted_lead_var_idx, dtype=np.int32)
+        args = L.PipelineArgs(
+            struct_size=C.sizeof(L.PipelineArgs), n_err=len(self.measurement_error), p=self.p, n_filter=self.n_filter,
+            n_lead=(int(lead.size) if self.check_bk else 0), filter_vars=fv.ctypes.data, obs_idx=obs.ctypes.data,
+            lead_idx=(lead.ctypes.data if self.check_bk and lead.size else None), theta=theta_full.data_ptr(),
+            theta_stride=theta_full.shape[1], N=theta_full.shape[0], Y=Y.data_ptr(), Tobs=Y.shape[0], max_iter=self.max_iter, tol=self.tol,
+            solver_tol=self.solver_tol, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
+            mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), mask_intercept=int(self.mask_intercept), gate_mask=self.gate_mask,
+            check_bk=int(self.check_bk and lead.size > 0), scan_semantics=int(self.solver == "scan_cycle_reduction"),
+            timing=int(events is not None), chunk=self.chunk, ll=ll.data_ptr(), status=status.data_ptr(),
+            n_iter=(out_n_iter.data_ptr() if out_n_iter is not None else None),
+        )  # fmt: skip
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        before = L.load_library().gecon_launch_count()
+        rc = m._loglik(C.byref(args), C.c_void_p(stream))
+        if rc != 0:
+            L.check(rc, f"gecon_model_loglik({m.name})")
+        if events is not None:
+            ms = (C.c_float * 4)()
+            L.load_library().gecon_pipeline_stage_ms(ms)
+            events.append(("__fused_ms__", dict(zip(("jacobian", "cr_solve", "bk_count", "kalman_ll"), (float(v) for v in ms))), None))
+        self.fused_launches = int(L.load_library().gecon_launch_count() - before)
         return ll, status
 
     # ------------------------------------------------------------------------------------------------ gradient

@@ -48,7 +48,9 @@ class TemperedSMC:
     step_scale: float = 0.02
     seed: int = 0
     exchange: str = "rows"
+    profile: bool = False  # CUDA events around the exchange (all-gather + row fetch) of every stage -> self.exchange_ms
     stats: list = field(default_factory=list)
+    exchange_ms: list = field(default_factory=list)
 
     def initialise(self, theta_local: torch.Tensor):
         """theta_local: this rank's shard of the initial (prior) population, [N_local, d] on the device."""
@@ -91,6 +93,9 @@ class TemperedSMC:
         self.status = torch.where(accept, self._st_prop, self.status)
         # ---- reweighting and the stage's collective: (log-weight, log-likelihood, status) of every particle, 24 bytes each.
         # (phi' - phi) * ll with ll = -inf is -inf, except at phi' = phi where it is NaN: the resampler maps NaN to -inf
+        if self.profile:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
         self._pack[:, 0] = (phi_next - self.phi) * self.ll
         self._pack[:, 1] = self.ll
         self._pack[:, 2] = self.status.to(torch.float64)  # (int32 bit field: exact in a double)
@@ -106,6 +111,10 @@ class TemperedSMC:
         self.ll = gath[mine, 1].contiguous()
         self.status = gath[mine, 2].to(torch.int32)
         self.theta = gath[mine, 3:].contiguous() if self.exchange == "allgather" else parallel.fetch_rows(self.theta, anc)
+        if self.profile:
+            ev[1].record()
+            ev[1].synchronize()
+            self.exchange_ms.append(ev[0].elapsed_time(ev[1]))
         self.phi = float(phi_next)
         fin = torch.isfinite(self.ll)
         st = SMCStageStats(phi=self.phi, ess=ess, accept_rate=float(accept.double().mean()),

@@ -62,6 +62,17 @@ extern "C" {
  * Follows _cycle_reduction_core: T = 0 and GECON_ST_CR_NOT_CONVERGED unless ||A0||_1 < tol and ||A2||_1 < tol
  * within max_iter iterations.  If C is NULL the system is backward looking: T = -B^-1 A, R = -B^-1 D.
  * ------------------------------------------------------------------------------------------------------------- */
+/* Compact Jacobian: the structural non-zeros of A, B, C, D only (a per-model generated kernel writes them, see the end of this
+ * file), so that the dense matrices never exist in HBM: medium NK 112 doubles per draw instead of 1,824.  When a solver entry
+ * point is given one, its A, B, C, D pointers are ignored. */
+typedef struct gecon_compact_jac {
+    const double* vals;   /* [N][stride] device: entry e of draw i at vals[i * stride + e] */
+    int64_t stride;       /* doubles between consecutive draws (>= nnz) */
+    const int32_t* table; /* [nnz] device: row << 16 | col of entry e (rows / columns in solver order) */
+    int32_t off[5];       /* entries of A are [off[0], off[1]), of B [off[1], off[2]), of C [off[2], off[3]), of D [off[3], off[4]) */
+    int32_t reserved;
+} gecon_compact_jac;
+
 typedef struct gecon_cr_args {
     size_t struct_size;  /* sizeof(gecon_cr_args) */
     const double* A;     /* [N][n][n] */
@@ -118,6 +129,7 @@ typedef struct gecon_cr_args {
                                not tested), T = -A1hat^-1 A is ALWAYS computed (no zeroing), n_iter = the steps actually taken
                                (the `n_steps` output of scan_cycle_reduction); GECON_ST_CR_NOT_CONVERGED then only says that
                                max_iter passed without ||A0||_1 < tol */
+    const gecon_compact_jac* compact; /* HOST pointer to the descriptor, or NULL.  Device entry point only */
 } gecon_cr_args;
 
 int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream);
@@ -147,6 +159,7 @@ typedef struct gecon_bk_args {
     int32_t skip_mask;       /* with accumulate != 0: draws with status & skip_mask are left untouched (e.g.
                                 GECON_ST_BK_CERTIFIED | GECON_ST_JAC_NONFINITE) */
     int32_t reserved0;
+    const gecon_compact_jac* compact; /* HOST pointer to the descriptor, or NULL (then A, B, C are read).  Device entry point only */
 } gecon_bk_args;
 
 int gecon_bk_count_batched(const gecon_bk_args* args, void* stream);
@@ -218,6 +231,9 @@ typedef struct gecon_kalman_args {
                              [N][k][k] (qfull_stride = k k) or shared [k][k] (0); when given, qdiag is ignored (may be NULL)
                              and the state dimension runs on the CTA-per-draw kernel */
     int64_t qfull_stride;
+    int32_t h_count;      /* 0: hdiag holds p entries per draw.  > 0: only the first h_count entries are read, the others are 0
+                             (lets hdiag point INTO a wider parameter vector: error variances of the first h_count observables) */
+    int32_t reserved3;
     int32_t mask_intercept; /* 0 (upstream StandardFilter as restated there): the intercept d is NOT masked at missing
                                entries, v_i = 0 - d_i there.  1: missing entries have v_i = 0 (d masked like Z and H), the
                                convention of a filter that drops missing rows.  tests/golden/make_kalman_goldens.py records which
@@ -363,8 +379,70 @@ int gecon_real_eig_batched(const double* M, int64_t N, int32_t m, int32_t balanc
                            void* stream);
 int gecon_real_eig_host(const double* M, int64_t N, int32_t m, int32_t balance, double* re, double* im, int32_t* status);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused theta -> log-likelihood (`gecon_model_<hash>_loglik`; the per-draw path of SURVEY 3.3,
+ * gEconpy/model/statespace.py:725-820, 1139-1215): per chunk of draws, on the caller's stream, the generated model kernel
+ * writes the COMPACT Jacobian, the solver kernels consume it, the filter reads the shock / measurement-error scales in
+ * place from the parameter vector.  No dense A, B, C, D, no memsets, no copy kernels; workspace from the stream-ordered
+ * allocator.  Plain state spaces only: selector observation matrix, diagonal shock covariance, no state augmentation, no
+ * observation equations, no steady-state intercept (the Python pipeline handles those).
+ * Every generated model library exports
+ *     int gecon_model_loglik(gecon_pipeline_args* args, void* stream);
+ * which fills in `jacobian`, `nz_table`, `nz_off`, `nnz`, `n`, `k`, `n_theta`, `col_ranges` (and `lead_idx` / `n_lead` when
+ * they are NULL / 0 and check_bk != 0) from its own tables and calls gecon_loglik_pipeline.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef int (*gecon_jacobian_compact_fn)(const double* theta, int64_t theta_stride, int64_t N, double* vals, double* xss,
+                                         int32_t* status, void* stream);
+
+typedef struct gecon_pipeline_args {
+    size_t struct_size;
+    gecon_jacobian_compact_fn jacobian; /* the model's gecon_model_jacobian_compact */
+    const int32_t* nz_table;  /* HOST [nnz]: row << 16 | col of the structural non-zeros, grouped A, B, C, D */
+    const int32_t* nz_off;    /* HOST [5] */
+    int32_t nnz;
+    int32_t n;                /* model variables */
+    int32_t k;                /* shocks */
+    int32_t n_theta;          /* free parameters: the leading columns of a parameter row */
+    int32_t n_err;            /* measurement-error sigmas: they follow the k shock sigmas and belong to the FIRST n_err observables
+                                 (gEconpy/model/statespace.py:800-808) */
+    int32_t p;                /* observables */
+    int32_t n_filter;         /* variables handed to the filter (lagged + observed), <= n */
+    int32_t n_lead;
+    const int32_t* filter_vars; /* HOST [n_filter]: their positions in solver order */
+    const int32_t* obs_idx;     /* HOST [p]: positions of the observables WITHIN filter_vars */
+    const int32_t* lead_idx;    /* HOST [n_lead]: structural lead variables (solver order) */
+    int32_t col_ranges[4];    /* lag_lo, lag_hi, lead_lo, lead_hi (gecon_cr_args) */
+    const double* theta;      /* DEVICE [N][theta_stride]: free parameters | sigma_<shock> (k) | error_sigma (n_err) | ... */
+    int64_t theta_stride;
+    int64_t N;
+    const double* Y;          /* DEVICE [Tobs][p] */
+    int32_t Tobs;
+    int32_t max_iter;
+    double tol;               /* cycle reduction */
+    double solver_tol;        /* residual gate (statespace.py:1210-1215) */
+    double jitter;
+    double missing_fill;
+    int32_t mvn_const_mode;
+    int32_t mask_intercept;
+    int32_t gate_mask;
+    int32_t check_bk;
+    int32_t scan_semantics;
+    int32_t timing;           /* != 0: CUDA events around every kernel; gecon_pipeline_stage_ms then returns the per-stage totals of
+                                 the calling thread's last call (jacobian, cr_solve, bk_count, kalman_ll).  Synchronises the stream */
+    int64_t chunk;            /* draws per launch (<= 0: 65,536) */
+    double* ll;               /* DEVICE [N] out */
+    int32_t* status;          /* DEVICE [N] out */
+    int32_t* n_iter;          /* DEVICE [N] out or NULL */
+} gecon_pipeline_args;
+
+int gecon_loglik_pipeline(const gecon_pipeline_args* args, void* stream);
+int gecon_pipeline_stage_ms(float* ms4);
+
 /* library / device information */
 int gecon_abi_version(void);
+/* measured fp64 peaks of the current device in TFLOP/s: register-resident DFMA chains and mma.sync.m8n8k4.f64 chains (the
+ * denominators of the roofline fractions; a few milliseconds, synchronises the device) */
+int gecon_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 int gecon_device_count(void);
 const char* gecon_get_last_error(void);
 /* resident CTAs per SM and dynamic shared memory (bytes) of a kernel for state dimension n:
@@ -379,6 +457,11 @@ int64_t gecon_launch_count(void);
  *   int gecon_model_info(int32_t* n, int32_t* k, int32_t* n_theta);
  *   int gecon_model_jacobian_batched(const double* theta, int64_t N, double* A, double* B, double* C, double* D,
  *                                    double* xss, int32_t* status, void* stream);
+ *   int gecon_model_jacobian_compact(const double* theta, int64_t theta_stride, int64_t N, double* vals, double* xss,
+ *                                    int32_t* status, void* stream);          (structural non-zeros only)
+ *   int gecon_model_structure(int32_t* nnz, const int32_t** table, const int32_t** off, int32_t* col_ranges,
+ *                             int32_t* n_lead, const int32_t** lead_idx);
+ *   int gecon_model_loglik(gecon_pipeline_args* args, void* stream);          (the fused entry point above)
  * theta is [N][n_theta]; A,B,C,D come out in the reference's permuted solver order (perturbation.py:130-158).
  * Replaces the compiled pytensor function f(*ss, *params) -> [A,B,C,D] (model.py:1647-1664, build.py:681-695).
  * ------------------------------------------------------------------------------------------------------------- */

@@ -183,3 +183,74 @@ def test_full_size_population_is_permutation_chunk_and_duplicate_invariant(compi
             assert st[i] == 0 and abs(llh[i] - ref["ll"]) <= 1e-7
         else:
             assert np.isneginf(llh[i])
+
+
+def test_wide_prior_population_failure_classes_at_scale(compiled):
+    """65,536 draws from a prior wide enough that EVERY failure class of the path is populated (>= 15 % each:
+    NaN steady state, cycle reduction out of iterations, Blanchard-Kahn violated, residual gate) through the production call
+    (``loglik_device``, fused entry point), then -- on a 576-draw subsample stratified over the classes -- status words bit-exact
+    and |ll - oracle| <= 1e-7 against the CPU restatement.  The population is bench.py's ``nk_wide`` workload."""
+    import sys
+
+    import torch
+
+    from helpers import SIGMA_ERR as S_ERR, SIGMA_SHOCK as S_SHOCK
+    from oracle import solvers as osol
+
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    import bench
+
+    from geconpy_b200 import _lib as L
+    from geconpy_b200.model.compiled import BatchedStateSpace
+
+    wl = bench.WORKLOADS["nk_wide"]
+    cm, mod = compiled(wl["model"]), model(wl["model"])
+    N, Tobs, max_iter = 65536, 200, wl["max_iter"]
+    ss = BatchedStateSpace(cm).configure(observed_states=wl["observed"], measurement_error=wl["meas"], tol=1e-8, max_iter=max_iter)
+    assert ss.fused
+    theta = bench.make_draws(mod.spec, N, None, seed=0, box=wl["box"])
+    Y = simulate_obs(mod, Tobs, observed=wl["observed"], seed=3, sigma_err=S_ERR)
+    full = np.hstack([theta, np.full((N, mod.k), S_SHOCK), np.full((N, len(wl["meas"])), S_ERR)])
+    ll_d, st_d = ss.loglik_device(torch.as_tensor(full, device="cuda"), torch.as_tensor(Y, device="cuda"))
+    ll, st = ll_d.cpu().numpy(), st_d.cpu().numpy()
+    cls = {"nan_ss": (st & L.ST_JAC_NONFINITE) != 0, "cr_fail": (st & L.ST_CR_NOT_CONVERGED) != 0,
+           "bk": (st & (L.ST_BK | L.ST_BK_INCONCLUSIVE)) != 0, "resid": (st & L.ST_RESID) != 0, "ok": st == 0}
+    frac = {k_: float(v.mean()) for k_, v in cls.items()}
+    assert all(frac[k_] >= 0.15 for k_ in ("nan_ss", "cr_fail", "bk", "resid")) and frac["ok"] >= 0.25, frac
+    assert np.isfinite(ll[cls["ok"]]).all() and np.isneginf(ll[~cls["ok"]]).all()
+    assert ((st & L.ST_SKIPPED) != 0).sum() == (~cls["ok"]).sum()
+    # ---- stratified subsample: 128 draws of each class (and of the draws that fail ONLY Blanchard-Kahn) + 128 good ones; the
+    # classes overlap (a draw can fail in two ways), so the union is smaller than 6 x 128
+    rng = np.random.default_rng(0)
+    strata = dict(cls, bk_only=cls["bk"] & ~cls["cr_fail"] & ~cls["resid"])
+    pick = np.unique(np.concatenate([rng.choice(np.flatnonzero(m_), size=min(128, int(m_.sum())), replace=False) for m_ in strata.values()]))
+    assert pick.size >= 512
+    lead = mod.permuted_lead_var_idx
+    herr = np.full(len(wl["meas"]), S_ERR)
+    n_inconclusive = 0
+    for i in pick:
+        with np.errstate(all="ignore"):
+            A, B, C, D = mod.jacobians(theta[i], mode="statespace")
+        want = 0
+        if not all(np.isfinite(M).all() for M in (A, B, C, D)):
+            want = L.ST_JAC_NONFINITE  # nothing downstream is evaluated on either side
+            got = st[i] & ~(L.ST_SKIPPED | L.ST_CR_NAN | L.ST_CR_NOT_CONVERGED | L.ST_SINGULAR | L.ST_RESID | L.ST_BK | L.ST_BK_INCONCLUSIVE)
+            assert got == want and np.isneginf(ll[i]), (i, hex(st[i]))
+            continue
+        T, conv, _it = osol.cycle_reduction_core(A, B, C, max_iter=max_iter, tol=1e-8)
+        resid = osol.policy_residual(A, B, C, T)
+        bk_ok = osol.bk_condition_pt(A, B, C, D, lead)[0]
+        want |= 0 if conv else L.ST_CR_NOT_CONVERGED
+        want |= 0 if resid < 1e-8 else L.ST_RESID
+        want |= 0 if bk_ok else L.ST_BK
+        got = st[i] & ~(L.ST_SKIPPED | L.ST_BK_CERTIFIED)
+        if got & L.ST_BK_INCONCLUSIVE:  # an eigenvalue within 1e-6 of the unit circle: reported as such, never guessed
+            n_inconclusive += 1
+            got = (got & ~L.ST_BK_INCONCLUSIVE) | (0 if bk_ok else L.ST_BK)
+        assert got == want, (i, hex(st[i]), hex(want))
+        if want == 0:
+            ref = oss.loglik(mod, theta[i], Y, wl["observed"], np.full(mod.k, S_SHOCK), herr, tol=1e-8, max_iter=max_iter)
+            assert ref["ok"] and abs(ll[i] - ref["ll"]) <= 1e-7, (i, ll[i], ref["ll"])
+        else:
+            assert np.isneginf(ll[i])
+    assert n_inconclusive <= 2
