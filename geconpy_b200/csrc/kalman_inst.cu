@@ -65,6 +65,8 @@ static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* inf
         // one CTA of 16 warps per SM (same 16 warps per SM as 4 CTAs of 4, but one staged copy of Y and one set-up per SM):
         // measured 45.6 -> 43.9 ms on the medium NK model; 20 warps (96 registers, spills) 50.5 ms, 12 warps 46.6 ms.
         // Falls back to 4-warp CTAs when 16 private tile sets + Y do not fit in shared memory.
+        static const int wpc_try = std::getenv("GECON_KW16_WPC") ? std::atoi(std::getenv("GECON_KW16_WPC")) : 16;  // experiment hook
+        if (wpc_try == 20 && KwSmem<NP, PT, 20>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 20>(a, st, info);
         if (KwSmem<NP, PT, 16>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 16>(a, st, info);
     }
     // (NP = 24: one CTA of 8 warps instead of two of 4 measured the same, 99.8 vs 99.5 ms on the large NK model: not built)

@@ -8,11 +8,14 @@
 // five CTA barriers per step leave the SM idle most of the time.  Here a warp owns a draw, so the only synchronisation
 // is __syncwarp, and 16 draws per SM advance independently.  Per step:
 //   1  every lane redundantly: F = Z P Z' + H + jitter I, its L D L' factorisation, the innovation and its quadratic
-//      form (p x p, registers);  lane i: row i of P Z', of K = P Z' F^-1, of M = K G / 2 - P Z', filtered mean a+_i
-//   2  P+ = P + [K | M | a+] [M | K | e_n]'  as ONE DMMA product with k = 2p + 1 on the accumulators that still hold P
-//      from the previous step (the expanded Joseph form P + K M' + M K'; the extra column drops a+ into the spare
-//      column n of P+, so the next product also propagates the mean);  the jitter on the diagonal of P+ is carried
-//      by the constant term of phase 4 (R Q R' + jitter T T')
+//      form (p x p, registers);  lane i: row i of P Z', of K = P Z' F^-1, of N = -(P Z' + jitter K), filtered mean a+_i
+//   2  P+ = P + [K | a+] [N | e_n]'  as ONE DMMA product with k = p + 1 on the accumulators that still hold P from the
+//      previous step.  This IS the Joseph form: with G = Z P Z' + H = F - jitter I and K = P Z' F^-1,
+//      K G = P Z' - jitter K and K (P Z')' = P Z' F^-1 (P Z')' is symmetric, so
+//      (I - K Z) P (I - K Z)' + K H K' = P - K (P Z')' - (P Z') K' + K G K' = P - K (P Z' + jitter K)' = P + K N'
+//      (rank p instead of the rank 2p of the expanded form P + K M' + M K', M = K G / 2 - P Z', used until round 2).
+//      The extra column drops a+ into the spare column n of P+, so the next product also propagates the mean; the
+//      jitter on the diagonal of P+ is carried by the constant term of phase 4 (R Q R' + jitter T T')
 //   3  W = T [P+ | a+]      (DMMA; T fragments live in registers for the whole draw)
 //   4  P = R Q R' + W T'    (DMMA; R Q R' in registers for NP <= 16)
 // P is symmetric, so phases 2 and 4 only compute and store the tiles on or above the block diagonal (3 of 4 tiles at NP = 16,
@@ -27,8 +30,8 @@ namespace gecon {
 
 template <int PT>
 struct KmCfg {
-    static constexpr int KS2 = (2 * PT + 1 + 3) / 4;            // k-steps of the rank-(2p+1) update
-    static constexpr int KW = 4 * KS2;                          // rows of the (transposed) panels [K|M|a+]', [M|K|e_n]'
+    static constexpr int KS2 = (PT + 1 + 3) / 4;                // k-steps of the rank-(p+1) update
+    static constexpr int KW = 4 * KS2;                          // rows of the (transposed) panels [K|a+]', [N|e_n]'
 };
 
 template <int NP, int PT, int WPC_ = 4>
@@ -38,8 +41,7 @@ struct KwSmem {
     static constexpr int KM2 = 2 * KmCfg<PT>::KW * Cfg<NP>::LD;    // KM and MK panels, stored transposed: [k][LD]
     static constexpr int ALIAS = KM2 > TILE ? KM2 : TILE;          // the Lyapunov scratch tile shares their storage
     static constexpr bool C0_REGS = (NP <= 8);   // R Q R' + jitter T T' in registers, else in a shared-memory tile
-    static constexpr bool GM_REGS = (PT <= 4);                      // G = Z P Z' + H in registers, else in shared memory
-    static constexpr int PER_WARP = 2 * TILE + ALIAS + (C0_REGS ? 0 : TILE) + NP + (GM_REGS ? 0 : PMAX * PMAX);  // doubles (even)
+    static constexpr int PER_WARP = 2 * TILE + ALIAS + (C0_REGS ? 0 : TILE) + NP;  // doubles (even)
     static size_t bytes(int Tobs) {
         const size_t ny = ((size_t)Tobs * PT + 1) & ~(size_t)1;
         return sizeof(double) * (ny + (size_t)WPC * PER_WARP) + sizeof(int) * ((size_t)Tobs + 4) + 16;
@@ -167,12 +169,10 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
     double* P = wb0;
     double* W = P + TILE;
     double* Aw = W + TILE;          // Lyapunov scratch; afterwards the same storage holds the two panels
-    double* KM = Aw;                // [KW][LD]  rows: K' | M' | a+'   (transposed: lane i writes column i, conflict-free)
-    double* MK = KM + KW * LD;      // [KW][LD]  rows: M' | K' | e_n'
+    double* KM = Aw;                // [KW][LD]  rows: K' | a+'    (transposed: lane i writes column i, conflict-free)
+    double* MK = KM + KW * LD;      // [KW][LD]  rows: N' | e_n'
     double* C0t = Aw + S::ALIAS;    // R Q R' (only when it does not live in registers)
     double* s_q = C0t + (C0_REGS ? 0 : TILE);
-    double* s_G = s_q + NP;         // [PT][PT] when it does not live in registers
-    constexpr bool GM_REGS = S::GM_REGS;
     int* s_wb = reinterpret_cast<int*>(sm + ny + (size_t)WPC * S::PER_WARP);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_wb + Tobs) + 7) & ~(uintptr_t)7);
 
@@ -199,6 +199,12 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
             s_wb[t] = bits;
         }
         __syncthreads();
+        // missing entries -> 0 in the staged copy (their mask bit is what the filter looks at): the step loop reads y without a select
+        for (uint32_t i = tid; i < ybytes / 8; i += WPC * 32) {
+            const uint32_t t = i / PT, a = i - t * PT;
+            if (!((s_wb[t] >> a) & 1)) s_Y[i] = 0.0;
+        }
+        __syncthreads();
     }
     int obs_r[PT];
 #pragma unroll
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
     const double ll_const = (p.mvn_const_mode == 0) ? PT * LOG2PI : LOG2PI;
     const int lyap_cap = p.lyap_max_iter > 0 ? p.lyap_max_iter : 64;
     const double jitter = p.jitter;
+    const bool keep_d = (p.mask_intercept == 0);  // the intercept is NOT masked at missing entries (pymc_extras: d + Z_masked a)
     const int nks = (n + 3) >> 2;
     const int il = lane < NP ? lane : 0;  // row handled by this lane in phase 1 (clamped: lanes >= n compute on row 0 and discard)
     const bool rowlane = lane < n;
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
         for (int i = lane; i < 2 * KW * LD; i += 32) KM[i] = 0.0;
         if (lane < NP) W[lane * LD + n] = 0.0;
         __syncwarp();
-        if (lane == 0) MK[2 * PT * LD + n] = 1.0;
+        if (lane == 0) MK[PT * LD + n] = 1.0;
         __syncwarp();
 
         double ll_acc = 0.0, quad_acc = 0.0, detprod = 1.0;
@@ -339,27 +346,20 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
             const double* y = s_Y + (size_t)t * PT;
             const int wb = s_wb[t];
             // ---- phase 1: P Z' row, innovation, F = G + jitter I (lower triangle), all from the shared-memory copy of P
-            double pz[PT], v[PT], f[PT][PT], gm[GM_REGS ? PT : 1][GM_REGS ? PT : 1];
+            double pz[PT], v[PT], f[PT][PT];
 #pragma unroll
             for (int a = 0; a < PT; ++a) {
                 const bool ob = (wb >> a) & 1;
                 const double s = P[sym_off<NP>(obs_r[a], il)];
                 pz[a] = ob ? s : 0.0;
                 const double za = W[obs_r[a] * LD + n];
-                v[a] = (ob ? y[a] : 0.0) - (((ob || !p.mask_intercept) ? dv0[a] : 0.0) + (ob ? za : 0.0));
+                v[a] = (y[a] - ((ob || keep_d) ? dv0[a] : 0.0)) - (ob ? za : 0.0);  // y is 0 where missing
 #pragma unroll
                 for (int b = 0; b <= a; ++b) {
                     double x = P[sym_off<NP>(obs_r[a], obs_r[b])];
                     x = (ob && ((wb >> b) & 1)) ? x : 0.0;
-                    if (a == b) x += ob ? hv[a] : 0.0;
-                    if constexpr (GM_REGS) {
-                        gm[a][b] = x;
-                        gm[b][a] = x;
-                    } else if (lane == 0) {
-                        s_G[a * PT + b] = x;
-                        s_G[b * PT + a] = x;
-                    }
-                    f[a][b] = (a == b) ? x + jitter : x;
+                    if (a == b) x += (ob ? hv[a] : 0.0) + jitter;
+                    f[a][b] = x;
                 }
             }
             // L D L' of F (no square roots), log det F = log prod d
@@ -384,7 +384,6 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
                 }
             }
             notpd = notpd || bad;
-            if constexpr (!GM_REGS) __syncwarp();
             // innovation: v' F^-1 v
             {
                 double x[PT];
@@ -415,7 +414,7 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
                     }
                 }
             }
-            // ---- phase 2: row of K = P Z' F^-1, filtered mean, M = K G / 2 - P Z'
+            // ---- phase 2: row of K = P Z' F^-1, filtered mean, N = -(P Z' + jitter K)
             {
                 double x[PT];
 #pragma unroll
@@ -438,20 +437,14 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
                     double* mk = MK + lane;
 #pragma unroll
                     for (int a = 0; a < PT; ++a) {
-                        double kg = 0.0;
-#pragma unroll
-                        for (int b = 0; b < PT; ++b) kg = fma(x[b], GM_REGS ? gm[b][a] : s_G[b * PT + a], kg);
-                        const double m = fma(0.5, kg, -pz[a]);
                         km[a * LD] = x[a];
-                        km[(PT + a) * LD] = m;
-                        mk[a * LD] = m;
-                        mk[(PT + a) * LD] = x[a];
+                        mk[a * LD] = -fma(jitter, x[a], pz[a]);
                     }
-                    km[2 * PT * LD] = af;
+                    km[PT * LD] = af;
                 }
             }
             __syncwarp();
-            // ---- phase 3: P+ = P + [K | M | a+] [M | K | e_n]' (+ jitter on the diagonal), accumulators -> P tile
+            // ---- phase 3: P+ = P + [K | a+] [N | e_n]' (the jitter on the diagonal: see c0), accumulators -> P tile
 #pragma unroll
             for (int ks = 0; ks < KS2; ++ks) {
                 double a[NS], b[NS];

@@ -81,9 +81,9 @@ def check_bk_condition_pt(A, B, C, D, lead_var_idx):
     return ok, int(lead.size), nu
 
 
-def _bk_matrix(A, B, C, lead):
-    """``M = (-Gamma0_sel + 1e-8 I)^-1 Gamma1_sel`` of the Sims pencil (perturbation.py:480-505, gensys.py:568-614), batched:
-    assembled with ``pytensorf.block`` and solved with the batched pivoted solve (on the device for torch CUDA inputs)."""
+def _bk_pencil(A, B, C, lead):
+    """``(G, Gamma1_sel)`` with ``G = -Gamma0_sel + 1e-8 I`` of the Sims pencil (perturbation.py:480-505, gensys.py:568-614), batched and
+    assembled with ``pytensorf.block`` (on the device for torch CUDA inputs).  The reference's matrix is ``M = G^-1 Gamma1_sel``."""
     from ..pytensorf.block import block
 
     lead = np.asarray(lead, dtype=np.int64)
@@ -103,14 +103,61 @@ def _bk_matrix(A, B, C, lead):
         g0 = np.ascontiguousarray(g0[..., keep, :][..., :, keep])
         g1 = np.ascontiguousarray(g1[..., keep, :][..., :, keep])
         G = -g0 + _FLOAT_ZERO_TOL * np.eye(keep.size)
+    return G, g1
+
+
+def _bk_matrix(A, B, C, lead):
+    """``M = (-Gamma0_sel + 1e-8 I)^-1 Gamma1_sel`` by the batched pivoted solve."""
+    G, g1 = _bk_pencil(A, B, C, lead)
     M, _st = batched.solve(G, g1)
     return M
 
 
 def compute_bk_eigenvalues_pt(A, B, C, _D, lead_var_idx):
-    """``(eigvals_real, eigvals_imag)`` of the regularised pencil matrix, sorted by modulus (perturbation.py:448-505): what
-    ``check_bk_condition_pt`` counts.  Numeric arrays (numpy / torch CUDA), optionally with a leading draw axis."""
-    re, im, _st = batched.real_eig(_bk_matrix(A, B, C, lead_var_idx))
+    """``(eigvals_real, eigvals_imag)`` of the regularised pencil matrix ``M = G^-1 Gamma1``, sorted by modulus
+    (perturbation.py:448-505): what ``check_bk_condition_pt`` counts.  Numeric arrays (numpy / torch CUDA), optionally with a
+    leading draw axis.
+
+    ``M`` itself has entries of order 1e8 (the regularised infinite eigenvalues), so any backward-stable eigen-solver applied to
+    it -- ``numpy.linalg.eig`` included -- returns the eigenvalues near the unit circle only to ``eps * 1e8 * cond`` ~ 1e-4.  The
+    eigenvalue kernel is therefore run on the Cayley transform ``N = (Gamma1 - G)^-1 (Gamma1 + G) = (M - I)^-1 (M + I)``, whose
+    entries are O(1) unless an eigenvalue sits at +1: ``mu = (lambda + 1) / (lambda - 1)`` maps back by the same formula,
+    ``lambda = (mu + 1) / (mu - 1)``.  The finite eigenvalues then agree with the QZ eigenvalues of the pencil to ~1e-10; the
+    regularised infinite ones (mu within 1e-8 of 1) come back as 1e7...inf instead of exactly ~1e8 -- far outside the unit circle
+    either way.  A draw whose ``Gamma1 - G`` is singular (an eigenvalue exactly 1) falls back to the kernel on ``M``."""
+    G, g1 = _bk_pencil(A, B, C, lead_var_idx)
+    squeeze = G.ndim == 2
+    if squeeze:
+        G, g1 = G[None], g1[None]
+    Ncay, st_solve = batched.solve(g1 - G, g1 + G)
+    mu_re, mu_im, st_eig = batched.real_eig(Ncay, sort=False)
+    is_torch = hasattr(mu_re, "device") and not isinstance(mu_re, np.ndarray)
+    if is_torch:
+        import torch as xp
+    else:
+        xp = np
+    # lambda = (mu + 1) / (mu - 1) = ((a + 1)(a - 1) + b^2 - 2 b i) / ((a - 1)^2 + b^2),  mu = a + b i
+    den = (mu_re - 1.0) ** 2 + mu_im**2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        re = ((mu_re + 1.0) * (mu_re - 1.0) + mu_im**2) / den
+        im = -2.0 * mu_im / den
+    inf = float("inf")
+    zero_den = den == 0
+    re = xp.where(zero_den, xp.full_like(re, inf), re)
+    im = xp.where(zero_den, xp.zeros_like(im), im)
+    bad = (st_solve != 0) | (st_eig != 0)
+    if bool(bad.any()):  # an eigenvalue at +1 (or a failed QR sweep): the direct route for those draws
+        Mb, _ = batched.solve(G[bad], g1[bad])
+        rb, ib, _ = batched.real_eig(Mb, sort=False)
+        re[bad], im[bad] = rb, ib
+    if is_torch:
+        idx = xp.argsort(xp.hypot(re, im), dim=1, stable=True)
+        re, im = xp.gather(re, 1, idx), xp.gather(im, 1, idx)
+    else:
+        idx = np.argsort(np.hypot(re, im), axis=1, kind="stable")
+        re, im = np.take_along_axis(re, idx, 1), np.take_along_axis(im, idx, 1)
+    if squeeze:
+        return re[0], im[0]
     return re, im
 
 

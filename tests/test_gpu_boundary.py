@@ -90,17 +90,17 @@ def test_bk_eigenvalues_and_table(B, name):
         mod_got = np.hypot(re[i], im[i])
         assert int((mod_got > 1).sum()) == int((np.abs(ref) > 1).sum()) == int(nu[i])
         # finite eigenvalues against the QZ eigenvalues of the PENCIL (G1, G0_reg), which never forms the 1e8-sized entries of
-        # M = G0_reg^-1 G1: any backward-stable eigen-solver applied to M itself (dgeev included) is only good to
-        # eps * ||M|| * cond ~ 1e-4 there; the regularised infinite eigenvalues (~1e8) are excluded
+        # M = G0_reg^-1 G1: a backward-stable eigen-solver applied to M itself (dgeev included: ``lapack`` below) is only good to
+        # eps * ||M|| * cond ~ 1e-4 there.  compute_bk_eigenvalues_pt runs the eigenvalue kernel on the Cayley transform of the
+        # pencil instead, so it must be at least as close to QZ as dgeev-on-M is, and close in absolute terms.  The regularised
+        # infinite eigenvalues (~1e8) are excluded from the comparison (they are counted above).
         import scipy.linalg
 
         qz = scipy.linalg.eigvals(G1, G0_reg)
         got_fin = (re[i] + 1j * im[i])[mod_got < 1e3]
         assert got_fin.size == (np.abs(qz) < 1e3).sum() == (np.abs(ref) < 1e3).sum()
         ours, lapack = _match_spectra(got_fin, qz[np.abs(qz) < 1e3], 0), _match_spectra(ref[np.abs(ref) < 1e3], qz[np.abs(qz) < 1e3], 0)
-        # (dgeev also permutes rows / columns to isolate eigenvalues while balancing, which this kernel does not: on these matrices
-        # -- norm 1e8, many exactly-zero eigenvalues -- that is worth up to two digits)
-        assert ours <= max(1e-6, 100.0 * lapack) and ours <= 5e-3, (name, i, ours, lapack)
+        assert ours <= 1e-6 and ours <= max(1e-9, lapack), (name, i, ours, lapack)
     df = P.check_bk_condition(A[0], Bm[0], C[0], D[0], verbose=False)
     n_lead_numeric = int((np.abs(C[0]).sum(axis=0) > 1e-8).sum())  # the numpy variant's rule (perturbation.py:441)
     assert list(df.columns) == ["Modulus", "Real", "Imaginary"] and len(df) == mod.n + n_lead_numeric
