@@ -254,6 +254,9 @@ class KalmanGradArgs(C.Structure):
         ("Z_bar", C.c_void_p),
         ("mask_intercept", C.c_int32),
         ("reserved2", C.c_int32),
+        ("qfull", C.c_void_p),
+        ("qfull_stride", C.c_int64),
+        ("qfull_bar", C.c_void_p),
     ]
 
 

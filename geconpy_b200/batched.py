@@ -341,12 +341,17 @@ def kalman_loglik(
 
 
 def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None, jitter=1e-8, missing_fill=-9999.0,
-                       mvn_const="per_obs", status_in=None, gate_mask=0, sigma_inputs=False, lyap_max_iter=0, mask_intercept=False):
+                       mvn_const="per_obs", status_in=None, gate_mask=0, sigma_inputs=False, lyap_max_iter=0, mask_intercept=False,
+                       Q=None):
     """Log-likelihood AND its gradient (``gecon_kalman_grad_*``): returns a dict with ``ll`` [N],
     ``status`` [N], ``T`` [N,n,n], ``R`` [N,n,k], ``q`` [N,k], ``h`` [N,p], ``d`` [N,p] -- the derivatives of ll with
     respect to the arguments of the same name (``q``/``h`` w.r.t. the standard deviations when ``sigma_inputs``) -- and,
     for a dense design matrix (shared ``(p, n)`` or one per draw ``(N, p, n)``), ``Z`` [N,p,n].
+    ``Q`` ([k, k] or [N, k, k]): full shock covariance instead of ``qdiag`` (then pass ``qdiag=None``); the result carries
+    ``Q`` [N,k,k] (symmetrised dll/dQ) instead of ``q``.
     What pytensor differentiates behind ``build_statespace_graph`` (gEconpy/model/statespace.py:812-820,1151-1157)."""
+    if (Q is None) == (qdiag is None):
+        raise ValueError("give exactly one of qdiag (shock variances / standard deviations) and Q (full shock covariance)")
     if (Z is None) == (obs_idx is None):
         raise ValueError("give exactly one of Z (dense design matrix) and obs_idx (selector)")
     m = _marshal_for(T, R)
@@ -358,6 +363,7 @@ def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None,
     Ya, pY = m.inp(Y)
     Tobs, p = (Ya.shape[0], 1) if Ya.ndim == 1 else Ya.shape
     q, pq = m.inp(qdiag)
+    Qa, pQ = m.inp(Q)
     h, ph = m.inp(hdiag)
     dd, pd_ = m.inp(d)
     Za, pZ = m.inp(Z)
@@ -368,24 +374,26 @@ def kalman_loglik_grad(T, R, qdiag, Y, Z=None, obs_idx=None, hdiag=None, d=None,
     Zb, pZb = m.out((N, p, n)) if Za is not None else (None, None)
     Tb, pTb = m.out((N, n, n))
     Rb, pRb = m.out((N, n, k))
-    qb, pqb = m.out((N, k))
+    qb, pqb = m.out((N, k)) if Qa is None else (None, None)
+    Qb, pQb = m.out((N, k, k)) if Qa is not None else (None, None)
     hb, phb = m.out((N, p))
     db, pdb = m.out((N, p))
     args = L.KalmanGradArgs(
-        struct_size=C.sizeof(L.KalmanGradArgs), T=pT, R=pR, qdiag=pq, q_stride=(k if q.ndim == 2 else 0), hdiag=ph,
+        struct_size=C.sizeof(L.KalmanGradArgs), T=pT, R=pR, qdiag=pq, q_stride=(k if (q is not None and q.ndim == 2) else 0), hdiag=ph,
         h_stride=(p if (h is not None and h.ndim == 2) else 0), Z=pZ, obs_idx=pO, d=pd_,
         d_stride=(p if (dd is not None and dd.ndim == 2) else 0), Y=pY, N=N, n=n, k=k, p=p, Tobs=Tobs, jitter=float(jitter),
         missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1), lyap_max_iter=int(lyap_max_iter),
         status_in=pSin, gate_mask=int(gate_mask), sigma_inputs=int(bool(sigma_inputs)), ll=pll, status=pS, T_bar=pTb, R_bar=pRb,
         q_bar=pqb, h_bar=phb, d_bar=pdb, z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0), Z_bar=pZb,
-        mask_intercept=int(bool(mask_intercept)),
+        mask_intercept=int(bool(mask_intercept)), qfull=pQ, qfull_stride=(k * k if (Qa is not None and Qa.ndim == 3) else 0), qfull_bar=pQb,
     )  # fmt: skip
     lib = L.load_library()
     if m.device:
         L.check(lib.gecon_kalman_grad_batched(C.byref(args), m.stream()), "gecon_kalman_grad_batched")
     else:
         L.check(lib.gecon_kalman_grad_host(C.byref(args)), "gecon_kalman_grad_host")
-    out = dict(ll=ll, status=st, T=Tb, R=Rb, q=qb, h=hb, d=db)
+    out = dict(ll=ll, status=st, T=Tb, R=Rb, h=hb, d=db)
+    out.update(dict(q=qb) if Qa is None else dict(Q=Qb))
     if Zb is not None:
         out["Z"] = Zb
     if squeeze:

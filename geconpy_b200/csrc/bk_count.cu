@@ -11,9 +11,15 @@
 // with sign(N) from the determinant-scaled Newton iteration S <- (mu S + (mu S)^-1) / 2.  Only Gauss-Jordan inverses
 // and elementwise updates are needed, i.e. the same in-CTA primitives as the cycle-reduction kernel.  The iteration
 // works on N' (trace and sign commute with transposition), which is what one solve with (Gamma1 + G)' produces.
-// A draw whose trace does not settle on an integer of the right parity (an eigenvalue on or next to the unit circle)
-// is flagged GECON_ST_BK_INCONCLUSIVE instead of being guessed.
+// N' is balanced first (Parlett-Reinsch scaling, eig.cuh).  The sign iteration is only trusted when it is well conditioned: a trace that does not settle on an integer (an eigenvalue on
+// or next to the unit circle), or a sign matrix with entries above 1e6 (nearly parallel stable / unstable invariant subspaces:
+// the Newton iteration's error grows like eps ||S||^2, and wide priors produce pencils with ||S|| ~ 1e9 ... 1e100), sends the
+// draw to the FALLBACK: warp 0 of the CTA runs the Hessenberg + Francis QR eigenvalue routine (eig.cuh) on N' and counts
+// Re(mu) > 0 directly -- the backward-stable route, on a matrix with O(1) entries, which agrees with QZ on the pencil where
+// dgeev on M (entries 1e8) is itself only good to 1e-4.  Only a draw on which that fails too (singular Gamma1 + G, QR sweep
+// not converging) is flagged GECON_ST_BK_INCONCLUSIVE instead of being guessed.
 #include "common.cuh"
+#include "eig.cuh"
 #include "linalg.cuh"
 
 namespace gecon {
@@ -57,34 +63,44 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk
             gC = p.C + (size_t)draw * n * n;
         }
         // W = (Gamma1 + G)',  X = (Gamma1 - G)'   (element [r][c] of the transpose = element (c, r))
-        for (int i = threadIdx.x; i < C::TILE; i += NT) {
-            const int r = i / LD, c = i - r * LD;
-            double wv = 0.0, xv = 0.0;
-            if (r < m && c < m) {
-                const int R = s_sel[c], Cc = s_sel[r];  // (row, col) in the 2n x 2n pencil
-                double g0, g1;
-                if (R < n) {
-                    g0 = (Cc < n) ? gB[R * n + Cc] : gC[R * n + (Cc - n)];
-                    g1 = (Cc < n) ? gA[R * n + Cc] : 0.0;
-                } else {
-                    g0 = (Cc == R - n) ? -1.0 : 0.0;
-                    g1 = (Cc == R) ? 1.0 : 0.0;
+        auto assemble = [&]() {
+            for (int i = threadIdx.x; i < C::TILE; i += NT) {
+                const int r = i / LD, c = i - r * LD;
+                double wv = 0.0, xv = 0.0;
+                if (r < m && c < m) {
+                    const int R = s_sel[c], Cc = s_sel[r];  // (row, col) in the 2n x 2n pencil
+                    double g0, g1;
+                    if (R < n) {
+                        g0 = (Cc < n) ? gB[R * n + Cc] : gC[R * n + (Cc - n)];
+                        g1 = (Cc < n) ? gA[R * n + Cc] : 0.0;
+                    } else {
+                        g0 = (Cc == R - n) ? -1.0 : 0.0;
+                        g1 = (Cc == R) ? 1.0 : 0.0;
+                    }
+                    const double g = -g0 + ((r == c) ? 1e-8 : 0.0);
+                    wv = g1 + g;
+                    xv = g1 - g;
                 }
-                const double g = -g0 + ((r == c) ? 1e-8 : 0.0);
-                wv = g1 + g;
-                xv = g1 - g;
+                W[i] = wv;
+                X[i] = xv;
             }
-            W[i] = wv;
-            X[i] = xv;
-        }
+        };
+        assemble();
         __syncthreads();
         const int mt = (m + 7) >> 3;
         bool ok = gj_solve_blocked<NP>(W, W, X, X, 0, mt, nullptr, nullptr, 0, 0, m, true, s_piv, s_flag, s_inv);
+        // Balance N' (diagonal similarity by powers of two: spectrum and trace of the sign unchanged).  Wide priors produce pencils
+        // whose rows differ by 30 orders of magnitude; unbalanced, the sign matrix of such an N has entries of 1e9 ... 1e100 and
+        // the Newton iteration is useless (numpy emulation on the nk_wide population: reliable on 64 % of the finite draws without
+        // balancing, 100 % with it).
+        if (ok && threadIdx.x < 32) warp_balance_scale(X, LD, m, (int)threadIdx.x);
+        __syncthreads();
         tile_copy<NP>(S, X);
         __syncthreads();
 
         bool settled = false;
         int it = 0;
+        double smax_last = 0.0;
         while (ok && it < cap) {
             ++it;
             tile_copy<NP>(W, S);
@@ -112,6 +128,7 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk
             }
             dmax = block_max<NP>(dmax, s_red);
             smax = block_max<NP>(smax, s_red);
+            smax_last = smax;
             if (dmax != dmax || smax != smax) {
                 ok = false;
                 break;
@@ -124,12 +141,50 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk
         __syncthreads();
         double tr = ((int)threadIdx.x < m) ? S[threadIdx.x * LD + threadIdx.x] : 0.0;
         tr = block_sum<NP>(tr, s_red);
+        const double cnt = 0.5 * (m + tr);
+        const double rc = rint(cnt);
+        int nu = -1;
+        if (ok && settled && fabs(cnt - rc) < 0.05 && rc >= 0.0 && rc <= (double)m && smax_last <= 1e6) {
+            nu = (int)rc;
+        } else {
+            // ---- fallback: eigenvalues of N' by the QR routine (warp 0), count Re(mu) > 0
+            assemble();
+            __syncthreads();
+            const bool ok2 = gj_solve_blocked<NP>(W, W, X, X, 0, mt, nullptr, nullptr, 0, 0, m, true, s_piv, s_flag, s_inv);
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const int lane = threadIdx.x;
+                int res = -1;
+                bool finite = ok2;
+                if (ok2) {
+                    for (int i = lane; i < m * m; i += 32) finite = finite && (fabs(X[(i / m) * LD + (i % m)]) <= 1.7e308);
+                }
+                finite = __all_sync(0xffffffffu, finite);
+                if (finite) {
+                    double* ort = W;  // the solve has destroyed W: scratch
+                    double* wr = W + NP;
+                    double* wi = W + 2 * NP;
+                    if (warp_real_eig(X, LD, m, 1, ort, wr, wi, lane)) {
+                        __syncwarp();
+                        int c = 0;
+                        bool fin = true;
+                        for (int i = lane; i < m; i += 32) {
+                            c += (wr[i] > 0.0) ? 1 : 0;
+                            fin = fin && (fabs(wr[i]) <= 1.7e308) && (fabs(wi[i]) <= 1.7e308);
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+                        if (__all_sync(0xffffffffu, fin)) res = c;
+                    }
+                }
+                if (lane == 0) s_flag[0] = res;
+            }
+            __syncthreads();
+            nu = s_flag[0];
+        }
         if (threadIdx.x == 0) {
-            int st = 0, nu = -1;
-            const double cnt = 0.5 * (m + tr);
-            const double rc = rint(cnt);
-            if (ok && settled && fabs(cnt - rc) < 0.05 && rc >= 0.0 && rc <= (double)m) {
-                nu = (int)rc;
+            int st = 0;
+            if (nu >= 0) {
                 if (nu != nl) st |= GECON_ST_BK;
             } else {
                 st |= GECON_ST_BK | GECON_ST_BK_INCONCLUSIVE;

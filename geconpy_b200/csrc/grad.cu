@@ -40,7 +40,7 @@ static int check_kg(const gecon_kalman_grad_args* a) {
         set_last_error("gecon_kalman_grad_args: bad struct_size");
         return GECON_E_BADARG;
     }
-    if (!a->T || !a->R || !a->qdiag || !a->Y || !a->ll || !a->status || !a->T_bar || !a->R_bar || !a->q_bar || a->N < 0 || a->n < 1 || a->k < 1 ||
+    if (!a->T || !a->R || (!a->qfull && (!a->qdiag || !a->q_bar)) || (a->qfull && !a->qfull_bar) || !a->Y || !a->ll || !a->status || !a->T_bar || !a->R_bar || a->N < 0 || a->n < 1 || a->k < 1 ||
         a->p < 1 || a->Tobs < 0 || (!a->Z && !a->obs_idx)) {
         set_last_error("gecon_kalman_grad_args: null pointer or bad dimension");
         return GECON_E_BADARG;

@@ -151,6 +151,9 @@ struct KalmanGradArgs {
     double* h_bar;    // [N][p]
     double* d_bar;    // [N][p]
     double* Z_bar;    // [N][p][n] or NULL: dll/dZ (dense design matrices only)
+    const double* qfull;  // [N][k][k] (qfull_stride = k k) or [k][k] (0), or NULL: full shock covariance (then qdiag / q_bar are unused)
+    long long qfull_stride;
+    double* qfull_bar;    // [N][k][k]: dll/dQ
     double* traj;     // workspace [n_cta][Tobs][n n + n]
     double* c0bar_ws;  // workspace [n_cta][2][n n]: adjoint of R Q R', and R Q R' itself
 };
@@ -158,29 +161,47 @@ struct KalmanGradArgs {
 // doubles of shared memory needed by kalman_grad_draw
 GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
     const int ld = ldim(n);
-    return (size_t)8 * n * ld + (size_t)5 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
-           k + nt + 8;
+    return (size_t)8 * n * ld + (size_t)6 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
+           k + (size_t)k * k + nt + 8;
 }
 
 // One draw.  sm: shared memory (kalman_grad_smem_doubles), cta: index of this CTA's workspace slot.
+//
+// Forward step (what is differentiated; same function of the parameters as the Joseph form of oracle/statespace.py):
+//   PZ = P Zm',  v = ym - dm - Zm a,  F = Zm PZ + Hm + j I,  K = PZ F^-1,  e = F^-1 v,  af = a + K v,
+//   N = PZ + j K,  Pf = P - K N' + j I     [= (I - K Zm) P (I - K Zm)' + K Hm K' + j I: K PZ' is symmetric and K (F - j I) = PZ - j K]
+//   a' = T af,  P' = T Pf T' + C0
+// so the update and its adjoint are O(n^2 p); the only n^3 products are T Pf, (T Pf) T' forward and, in reverse,
+//   T_bar += (P'_bar + P'_bar') (T Pf) + a'_bar af',   Pf_bar = T' (P'_bar T),   C0_bar += P'_bar,   af_bar = T' a'_bar
+//   N_bar = -Pf_bar' K,  K_bar = -Pf_bar N + j N_bar + af_bar v',  v_bar = -e + K' af_bar,  F_bar = -(F^-1 - e e') / 2
+//   G = K_bar F^-1,  PZ_bar = N_bar + G + Zm' F_bar',  F_bar' = sym(F_bar - K' G),  h_bar += w diag(F_bar'),
+//   P_bar = Pf_bar + PZ_bar Zm,  a_bar = af_bar - Zm' v_bar,  d_bar -= dmask v_bar,
+//   Zm_bar = F_bar' PZ' + PZ_bar' P - v_bar a'
+// (13 n^3 products per step with the expanded Joseph form and its adjoint until round 2; 6 now).
+// F is symmetrised before it is inverted and F_bar' is symmetrised before it is used: both are part of the graph.  Without them
+// the rank-p update is the same function of the parameters but NOT a stable recursion -- an antisymmetric perturbation of P is
+// neither damped by the update (the Joseph form damps it by L . L') nor kept out of F, and the reverse sweep amplifies
+// rounding-level antisymmetry of P_bar by the same mechanism (measured on the medium NK model with error variances 1e-6:
+// gradient wrong in the first digit after 50 steps; with the two symmetrisations it agrees with the Joseph-form adjoint to 1e-12).
 GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, double* sm) {
     const int n = g.n, k = g.k, p = g.p, Tobs = g.Tobs, ld = ldim(n);
     const int tile = n * ld;
     double* Tm = sm;
     double* P = Tm + tile;
     double* Pf = P + tile;
-    double* L = Pf + tile;
-    double* Pb = L + tile;   // adjoint of the predicted covariance
-    double* Pfb = Pb + tile;  // adjoint of the filtered covariance
+    double* Pb = Pf + tile;   // adjoint of the predicted covariance
+    double* Pfb = Pb + tile;  // adjoint of the filtered covariance (and the A_k of the two doublings)
     double* W1 = Pfb + tile;
     double* W2 = W1 + tile;
+    double* Tb = W2 + tile;   // accumulated adjoint of T
     const int ps = p;             // row stride of the n x p panels and of the p x p matrices
-    double* PZ = W2 + tile;       // [n][p]
+    double* PZ = Tb + tile;       // [n][p]
     double* K = PZ + n * ps;
-    double* Kb = K + n * ps;
+    double* Nn = K + n * ps;      // PZ + jitter K
+    double* Kb = Nn + n * ps;
     double* PZb = Kb + n * ps;
-    double* PK = PZb + n * ps;
-    double* Zs = PK + n * ps;     // [p][n]
+    double* G1 = PZb + n * ps;    // K_bar F^-1
+    double* Zs = G1 + n * ps;     // [p][n]
     double* Zb = Zs + p * n;      // [p][n] adjoint of the design matrix
     double* a = Zb + p * n;
     double* af = a + n;
@@ -201,7 +222,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     double* sc = db + p;  // [0] logdet, [1] ok flag, [2] ll, [3] all-missing flag
     double* Rs = sc + 4;  // [n][k]
     double* qs = Rs + n * (k > 0 ? k : 1);
-    double* s_red = qs + k;
+    double* Qs = qs + k;  // [k][k] full shock covariance (when g.qfull)
+    double* s_red = Qs + k * k;
 
     const double LOG2PI = 1.8378770664093453;
     const double ll_const = (g.mvn_const_mode == 0) ? p * LOG2PI : LOG2PI;
@@ -212,7 +234,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     if (status & g.gate_mask) {
         GFOR(i, n * n) gTb[i] = 0.0;
         GFOR(i, n * k) gRb[i] = 0.0;
-        GFOR(i, k) g.q_bar[(size_t)draw * k + i] = 0.0;
+        if (g.qfull) GFOR(i, k * k) g.qfull_bar[(size_t)draw * k * k + i] = 0.0;
+        else GFOR(i, k) g.q_bar[(size_t)draw * k + i] = 0.0;
         GFOR(i, p) {
             if (g.h_bar) g.h_bar[(size_t)draw * p + i] = 0.0;
             if (g.d_bar) g.d_bar[(size_t)draw * p + i] = 0.0;
@@ -234,13 +257,17 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     GFOR(idx, n * n) {
         const int i = idx / n, j = idx - i * n;
         Tm[i * ld + j] = gT[idx];
-        gTb[idx] = 0.0;
+        Tb[i * ld + j] = 0.0;
         gC0b[idx] = 0.0;
     }
     GFOR(idx, n * k) Rs[idx] = gR[idx];
-    GFOR(c, k) {
-        const double qv = g.qdiag[(size_t)draw * g.q_stride + c];
-        qs[c] = g.sigma_inputs ? qv * qv : qv;
+    if (g.qfull) {
+        GFOR(idx, k * k) Qs[idx] = g.qfull[(size_t)draw * (size_t)g.qfull_stride + idx];
+    } else {
+        GFOR(c, k) {
+            const double qv = g.qdiag[(size_t)draw * g.q_stride + c];
+            qs[c] = g.sigma_inputs ? qv * qv : qv;
+        }
     }
     GFOR(i, p) {
         const double h = g.hdiag ? g.hdiag[(size_t)draw * g.h_stride + i] : 0.0;
@@ -264,10 +291,18 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         const int i = idx / n, j = idx - i * n;
         const int lo = i < j ? i : j, hi = i < j ? j : i;
         double s = 0.0;
-        for (int c = 0; c < k; ++c) s = fma(Rs[lo * k + c] * qs[c], Rs[hi * k + c], s);
+        if (g.qfull) {  // R Q R' exactly as written (every entry of Q is an independent input of the derivative)
+            for (int c = 0; c < k; ++c) {
+                double rq = 0.0;
+                for (int c2 = 0; c2 < k; ++c2) rq = fma(Qs[c * k + c2], Rs[j * k + c2], rq);
+                s = fma(Rs[i * k + c], rq, s);
+            }
+        } else {
+            for (int c = 0; c < k; ++c) s = fma(Rs[lo * k + c] * qs[c], Rs[hi * k + c], s);
+        }
         C0[i * n + j] = s;
         P[i * ld + j] = s;
-        L[i * ld + j] = Tm[i * ld + j];  // A_0 = T
+        Pfb[i * ld + j] = Tm[i * ld + j];  // A_0 = T
     }
     GSYNC();
     // ---- P0 by Smith doubling: P <- P + A P A', A <- A^2
@@ -275,15 +310,15 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         const int cap = g.lyap_max_iter > 0 ? g.lyap_max_iter : 64;
         bool done = false;
         for (int it = 0; it < cap && !done; ++it) {
-            mm<false, false>(W1, ld, L, ld, P, ld, n, n, n, 1.0, 0.0);
+            mm<false, false>(W1, ld, Pfb, ld, P, ld, n, n, n, 1.0, 0.0);
             GSYNC();
-            mm<false, true>(W2, ld, W1, ld, L, ld, n, n, n, 1.0, 0.0);
-            mm<false, false>(Pf, ld, L, ld, L, ld, n, n, n, 1.0, 0.0);
+            mm<false, true>(W2, ld, W1, ld, Pfb, ld, n, n, n, 1.0, 0.0);
+            mm<false, false>(Pf, ld, Pfb, ld, Pfb, ld, n, n, n, 1.0, 0.0);
             GSYNC();
             GFOR(idx, n * n) {
                 const int i = idx / n, j = idx - i * n;
                 P[i * ld + j] += W2[i * ld + j];
-                L[i * ld + j] = Pf[i * ld + j];
+                Pfb[i * ld + j] = Pf[i * ld + j];
             }
             GSYNC();
             const double dmax = absmax(W2, ld, n, n, s_red), pmax = absmax(P, ld, n, n, s_red);
@@ -298,7 +333,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     }
     GSYNC();
 
-    // One update step on the predicted (a, P): fills w, ym, v, PZ, F^-1 (in F), K, e, af, L, W1 = L P, Pf.
+    // One update step on the predicted (a, P): fills w, ym, v, PZ, F^-1 (in F), K, e, af, Nn, Pf.
     auto update = [&](int t, bool accumulate_ll) {
         GFOR(i, p) {
             const double yv = g.Y[(size_t)t * p + i];
@@ -350,6 +385,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             double s = 0.0;
             for (int b = 0; b < p; ++b) s = fma(PZ[i * ps + b], F[b * ps + c], s);
             K[i * ps + c] = s;
+            Nn[i * ps + c] = fma(jit, s, PZ[i * ps + c]);
         }
         GFOR(c, p) {
             double s = 0.0;
@@ -364,25 +400,15 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GFOR(idx, n * n) {
             const int i = idx / n, j = idx - i * n;
-            double s = (i == j) ? 1.0 : 0.0;
-            for (int c = 0; c < p; ++c) s = fma(-K[i * ps + c] * w[c], Zs[c * n + j], s);
-            L[i * ld + j] = s;
+            double s = P[i * ld + j] + ((i == j) ? jit : 0.0);
+            for (int c = 0; c < p; ++c) s = fma(-K[i * ps + c], Nn[j * ps + c], s);
+            Pf[i * ld + j] = s;
         }
         if (accumulate_ll && G_TID == 0 && sc[3] == 0.0) {
             double quad = 0.0;
             for (int c = 0; c < p; ++c) quad = fma(v[c], e[c], quad);
             sc[2] += -0.5 * (ll_const + sc[0] + quad);
         }
-        GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return L[i * ld + k_]; }, [&](int k_, int j) { return P[k_ * ld + j]; },
-              [&](int i, int j, double v_) { W1[i * ld + j] = v_; });
-        GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return W1[i * ld + k_]; }, [&](int k_, int j) { return L[j * ld + k_]; },
-              [&](int i, int j, double v_) {
-                  double s = v_ + ((i == j) ? jit : 0.0);
-                  for (int c = 0; c < p; ++c) s = fma(K[i * ps + c] * (w[c] * hv[c]), K[j * ps + c], s);
-                  Pf[i * ld + j] = s;
-              });
         GSYNC();
     };
 
@@ -418,78 +444,66 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         GFOR(i, n) a[i] = tr[n * n + i];
         GSYNC();
         update(t, false);
-        // predict:  P' = T Pf T' + C0,  a' = T af
+        // predict in reverse:  P' = T Pf T' + C0,  a' = T af
         gemm4(n, n, n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
               [&](int i, int j, double v_) { W2[i * ld + j] = v_; });
         GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return Pb[i * ld + k_] + Pb[k_ * ld + i]; }, [&](int k_, int j) { return W2[k_ * ld + j]; },
               [&](int i, int j, double v_) {
-                  gTb[i * n + j] += v_ + ab[i] * af[j];
+                  Tb[i * ld + j] += v_ + ab[i] * af[j];
                   gC0b[i * n + j] += Pb[i * ld + j];
               });
-        GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return Pb[i * ld + k_]; }, [&](int k_, int j) { return Tm[k_ * ld + j]; },
-              [&](int i, int j, double v_) { W2[i * ld + j] = v_; });
+              [&](int i, int j, double v_) { W1[i * ld + j] = v_; });
         GFOR(i, n) {
             double s = 0.0;
             for (int j = 0; j < n; ++j) s = fma(Tm[j * ld + i], ab[j], s);
             afb[i] = s;
         }
         GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return Tm[k_ * ld + i]; }, [&](int k_, int j) { return W2[k_ * ld + j]; },
+        gemm4(n, n, n, [&](int i, int k_) { return Tm[k_ * ld + i]; }, [&](int k_, int j) { return W1[k_ * ld + j]; },
               [&](int i, int j, double v_) { Pfb[i * ld + j] = v_; });
         // log-likelihood term
         GFOR(idx, p * p) {
             const int c = idx / p, b = idx - c * p;
             Fb[c * ps + b] = (sc[3] == 0.0) ? -0.5 * (F[c * ps + b] - e[c] * e[b]) : 0.0;
         }
-        GFOR(c, p) vb[c] = (sc[3] == 0.0) ? -e[c] : 0.0;
-        GSYNC();
-        // update:  Pf = L P L' + K Hm K' + j I,  L = I - K Zm,  af = a + K v   (W1 = L P, P symmetric)
-        gemm4(n, n, n, [&](int i, int k_) { return Pfb[i * ld + k_] + Pfb[k_ * ld + i]; }, [&](int k_, int j) { return W1[k_ * ld + j]; },
-              [&](int i, int j, double v_) { W2[i * ld + j] = v_; });  // L_bar -> W2
-        gemm4(n, n, n, [&](int i, int k_) { return Pfb[i * ld + k_]; }, [&](int k_, int j) { return L[k_ * ld + j]; },
-              [&](int i, int j, double v_) { Pf[i * ld + j] = v_; });  // Pf tile now holds Pfb L
-        gemm4(n, p, n, [&](int i, int k_) { return Pfb[i * ld + k_]; }, [&](int k_, int c) { return K[k_ * ps + c]; },
-              [&](int i, int c, double v_) { PK[i * ps + c] = v_; });  // PK = Pfb K
-        GSYNC();
-        GFOR(idx, n * p) {  // K_bar
-            const int i = idx / p, c = idx - i * p;
-            double s = afb[i] * v[c];
-            double s1 = 0.0, s2 = 0.0;
-            for (int kk = 0; kk < n; ++kk) {
-                s1 = fma(Pfb[i * ld + kk] + Pfb[kk * ld + i], K[kk * ps + c], s1);
-                s2 = fma(W2[i * ld + kk], Zs[c * n + kk], s2);
-            }
-            Kb[i * ps + c] = s + s1 * (w[c] * hv[c]) - s2 * w[c];
-        }
         GFOR(c, p) {
-            double s = 0.0;
-            for (int i = 0; i < n; ++i) s = fma(K[i * ps + c], PK[i * ps + c], s);
-            hb[c] += w[c] * s;
-            double u = vb[c];
+            double u = (sc[3] == 0.0) ? -e[c] : 0.0;
             for (int i = 0; i < n; ++i) u = fma(K[i * ps + c], afb[i], u);
             vb[c] = u;
         }
         GSYNC();
-        GFOR(idx, n * p) {  // PZ_bar = K_bar F^-1
+        // update in reverse (all O(n^2 p))
+        GFOR(idx, n * p) {
+            const int i = idx / p, c = idx - i * p;
+            double s1 = 0.0, s2 = 0.0;
+            for (int j = 0; j < n; ++j) {
+                s1 = fma(Pfb[i * ld + j], Nn[j * ps + c], s1);
+                s2 = fma(Pfb[j * ld + i], K[j * ps + c], s2);
+            }
+            PZb[i * ps + c] = -s2;                                  // N_bar
+            Kb[i * ps + c] = fma(afb[i], v[c], -fma(jit, s2, s1));  // -Pf_bar N + j N_bar + af_bar v'
+        }
+        GSYNC();
+        GFOR(idx, n * p) {  // G = K_bar F^-1
             const int i = idx / p, c = idx - i * p;
             double s = 0.0;
             for (int b = 0; b < p; ++b) s = fma(Kb[i * ps + b], F[b * ps + c], s);
-            PZb[i * ps + c] = s;
+            G1[i * ps + c] = s;
         }
         GSYNC();
-        GFOR(idx, p * p) {  // F_bar -= K' PZ_bar
+        GFOR(idx, p * p) {  // F_bar -= K' G
             const int c = idx / p, b = idx - c * p;
             double s = 0.0;
-            for (int i = 0; i < n; ++i) s = fma(K[i * ps + c], PZb[i * ps + b], s);
+            for (int i = 0; i < n; ++i) s = fma(K[i * ps + c], G1[i * ps + b], s);
             Fb[c * ps + b] -= s;
         }
         GSYNC();
-        GFOR(idx, n * p) {  // PZ_bar += Zm' F_bar
+        GFOR(idx, n * p) {  // PZ_bar = N_bar + G + Zm' F_bar
             const int i = idx / p, b = idx - i * p;
-            double s = PZb[i * ps + b];
-            for (int c = 0; c < p; ++c) s = fma(w[c] * Zs[c * n + i], Fb[c * ps + b], s);
+            double s = PZb[i * ps + b] + G1[i * ps + b];
+            for (int c = 0; c < p; ++c) s = fma(w[c] * Zs[c * n + i], 0.5 * (Fb[c * ps + b] + Fb[b * ps + c]), s);
             PZb[i * ps + b] = s;
         }
         GFOR(c, p) {
@@ -497,18 +511,18 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             db[c] -= (g.mask_intercept ? w[c] : 1.0) * vb[c];
         }
         GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return L[k_ * ld + i]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
-              [&](int i, int j, double v_) {  // P_bar = L' (Pfb L) + PZ_bar Zm
-                  double s = v_;
-                  for (int c = 0; c < p; ++c) s = fma(PZb[i * ps + c] * w[c], Zs[c * n + j], s);
-                  Pb[i * ld + j] = s;
-              });
-        if (g.Z_bar) {  // Zm = diag(w) Z enters L = I - K Zm, v = ym - d - Zm a, PZ = P Zm', G = Zm PZ
+        GFOR(idx, n * n) {  // P_bar = Pf_bar + PZ_bar Zm
+            const int i = idx / n, j = idx - i * n;
+            double s = Pfb[i * ld + j];
+            for (int c = 0; c < p; ++c) s = fma(PZb[i * ps + c] * w[c], Zs[c * n + j], s);
+            Pb[i * ld + j] = s;
+        }
+        if (g.Z_bar) {  // Zm = diag(w) Z enters v = ym - d - Zm a, PZ = P Zm', F = Zm PZ + ...
             GFOR(idx, p * n) {
                 const int c = idx / n, j = idx - c * n;
                 double s = -vb[c] * a[j];
-                for (int i = 0; i < n; ++i) s += fma(PZb[i * ps + c], P[i * ld + j], -K[i * ps + c] * W2[i * ld + j]);
-                for (int b = 0; b < p; ++b) s = fma(Fb[c * ps + b], PZ[j * ps + b], s);
+                for (int i = 0; i < n; ++i) s = fma(PZb[i * ps + c], P[i * ld + j], s);
+                for (int b = 0; b < p; ++b) s = fma(0.5 * (Fb[c * ps + b] + Fb[b * ps + c]), PZ[j * ps + b], s);
                 Zb[idx] += w[c] * s;
             }
         }
@@ -519,39 +533,67 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GSYNC();
     }
-    // ---- P0 = dlyap(T, C0): S = T' S T + P0_bar by doubling (S in Pb, A in L);  P still holds P0
-    GFOR(idx, n * ld) L[idx] = Tm[idx];
+    // ---- P0 = dlyap(T, C0): S = T' S T + P0_bar by doubling (S in Pb, A in Pfb);  P still holds P0
+    GFOR(idx, n * ld) Pfb[idx] = Tm[idx];
     GSYNC();
     {
         const int cap = g.lyap_max_iter > 0 ? g.lyap_max_iter : 64;
         for (int it = 0; it < cap; ++it) {
-            mm<false, false>(W1, ld, Pb, ld, L, ld, n, n, n, 1.0, 0.0);
+            mm<false, false>(W1, ld, Pb, ld, Pfb, ld, n, n, n, 1.0, 0.0);
             GSYNC();
-            mm<true, false>(W2, ld, L, ld, W1, ld, n, n, n, 1.0, 0.0);
-            mm<false, false>(Pf, ld, L, ld, L, ld, n, n, n, 1.0, 0.0);
+            mm<true, false>(W2, ld, Pfb, ld, W1, ld, n, n, n, 1.0, 0.0);
+            mm<false, false>(Pf, ld, Pfb, ld, Pfb, ld, n, n, n, 1.0, 0.0);
             GSYNC();
             GFOR(idx, n * n) {
                 const int i = idx / n, j = idx - i * n;
                 Pb[i * ld + j] += W2[i * ld + j];
-                L[i * ld + j] = Pf[i * ld + j];
+                Pfb[i * ld + j] = Pf[i * ld + j];
             }
             GSYNC();
             const double dmax = absmax(W2, ld, n, n, s_red), smax = absmax(Pb, ld, n, n, s_red);
             if (!(dmax > 1e-17 * smax)) break;
         }
     }
-    // C0_bar += S;  T_bar += (S + S') T P0
+    // C0_bar += S;  T_bar = accumulated + (S + S') T P0
     mm<false, false>(W1, ld, Tm, ld, P, ld, n, n, n, 1.0, 0.0);
     GFOR(idx, n * n) gC0b[idx] += Pb[(idx / n) * ld + (idx % n)];
     GSYNC();
     GFOR(idx, n * n) {
         const int i = idx / n, j = idx - i * n;
-        double s = 0.0;
+        double s = Tb[i * ld + j];
         for (int kk = 0; kk < n; ++kk) s = fma(Pb[i * ld + kk] + Pb[kk * ld + i], W1[kk * ld + j], s);
-        gTb[idx] += s;
+        gTb[idx] = s;
         W2[i * ld + j] = gC0b[idx] + gC0b[j * n + i];  // C0_bar + C0_bar'
     }
     GSYNC();
+    if (g.qfull) {
+        // C0 = R Q R':  R_bar = C0_bar R Q' + C0_bar' R Q,  Q_bar = R' C0_bar R      (W1 <- C0_bar R, Pf <- C0_bar' R)
+        GFOR(idx, n * k) {
+            const int i = idx / k, c = idx - i * k;
+            double s1 = 0.0, s2 = 0.0;
+            for (int j = 0; j < n; ++j) {
+                s1 = fma(gC0b[i * n + j], Rs[j * k + c], s1);
+                s2 = fma(gC0b[j * n + i], Rs[j * k + c], s2);
+            }
+            W1[i * ld + c] = s1;
+            Pf[i * ld + c] = s2;
+        }
+        GSYNC();
+        GFOR(idx, n * k) {
+            const int i = idx / k, c = idx - i * k;
+            double s = 0.0;
+            for (int c2 = 0; c2 < k; ++c2) s = fma(W1[i * ld + c2], Qs[c * k + c2], fma(Pf[i * ld + c2], Qs[c2 * k + c], s));
+            gRb[idx] = s;
+        }
+        GFOR(idx, k * k) {
+            const int a_ = idx / k, b_ = idx - a_ * k;
+            // symmetrised: Q is a covariance, and how dll/dQ splits between Q_ab and Q_ba depends on how the filter is extended to
+            // non-symmetric covariances (the Joseph form and the rank-p form extend it differently); only the symmetric part is defined
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s = fma(Rs[i * k + a_], W1[i * ld + b_], fma(Rs[i * k + b_], W1[i * ld + a_], s));
+            g.qfull_bar[(size_t)draw * k * k + idx] = 0.5 * s;
+        }
+    } else {
     // R_bar = (C0_bar + C0_bar') R Q;  q_bar_c = sum_ij R_ic C0_bar_ij R_jc = (1/2) sum_i R_ic ((C0_bar + C0_bar') R)_ic
     GFOR(idx, n * k) {
         const int i = idx / k, c = idx - i * k;
@@ -567,6 +609,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         s *= 0.5;
         if (g.sigma_inputs) s *= 2.0 * g.qdiag[(size_t)draw * g.q_stride + c];
         g.q_bar[(size_t)draw * k + c] = s;
+    }
     }
     GFOR(c, p) {
         if (g.h_bar) {

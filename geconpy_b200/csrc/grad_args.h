@@ -13,6 +13,7 @@ inline KalmanGradArgs to_internal(const gecon_kalman_grad_args& a) {
     g.jitter = a.jitter, g.missing_fill = a.missing_fill, g.mvn_const_mode = a.mvn_const_mode, g.lyap_max_iter = a.lyap_max_iter;
     g.status_in = a.status_in, g.gate_mask = a.gate_mask, g.sigma_inputs = a.sigma_inputs;
     g.mask_intercept = a.mask_intercept;
+    g.qfull = a.qfull, g.qfull_stride = a.qfull_stride, g.qfull_bar = a.qfull_bar;
     g.ll = a.ll, g.status = a.status, g.T_bar = a.T_bar, g.R_bar = a.R_bar, g.q_bar = a.q_bar, g.h_bar = a.h_bar, g.d_bar = a.d_bar, g.Z_bar = a.Z_bar;
     g.traj = nullptr, g.c0bar_ws = nullptr;
     return g;

@@ -79,12 +79,15 @@ GECON_KF_DECL(8) GECON_KF_DECL(16) GECON_KF_DECL(24) GECON_KF_DECL(32) GECON_KF_
 int launch_kw_8(const gecon_kalman_args& a, cudaStream_t st, int* info);
 int launch_kw_16(const gecon_kalman_args& a, cudaStream_t st, int* info);
 int launch_kw_24(const gecon_kalman_args& a, cudaStream_t st, int* info);
+int launch_kw_32(const gecon_kalman_args& a, cudaStream_t st, int* info);
 
 // padded dimension of the warp-per-draw kernel (needs a spare column for the mean), or 0 when the CTA kernel must run
 static int warp_kernel_np(const gecon_kalman_args& a) {
     if (!a.obs_idx || a.Z || a.qfull) return 0;  // dense design matrices and full shock covariances stay on the CTA kernel
     const int np = round_up8((a.n + 1) > a.k ? (a.n + 1) : a.k);
-    return np <= 24 ? np : 0;
+    // NP = 32: four private 9 KB tiles per warp (149 KB for a 4-warp CTA); very long samples leave no room for them next to Y
+    if (np == 32 && (size_t)a.Tobs * a.p * 8 + (size_t)a.Tobs * 4 > 70 * 1024) return 0;
+    return np <= 32 ? np : 0;
 }
 
 static int launch_kf(int np, const gecon_kalman_args& a, cudaStream_t st, int* info) {
@@ -92,6 +95,7 @@ static int launch_kf(int np, const gecon_kalman_args& a, cudaStream_t st, int* i
         case 8: return launch_kw_8(a, st, info);
         case 16: return launch_kw_16(a, st, info);
         case 24: return launch_kw_24(a, st, info);
+        case 32: return launch_kw_32(a, st, info);
     }
     switch (np) {
         case 8: return launch_kf_8(a, st, info);

@@ -33,7 +33,7 @@ static int launch_one(const gecon_kalman_args& a, cudaStream_t st, int* info) {
     return 0;
 }
 
-// one warp per draw (kalman_warp.cuh): selector Z, n + 1 <= NP <= 24
+// one warp per draw (kalman_warp.cuh): selector Z, n + 1 <= NP <= 32
 template <int NP, int PT, int MINB, int WPC_ = 4>
 static int launch_one_warp_b(const gecon_kalman_args& a, cudaStream_t st, int* info) {
     using S = KwSmem<NP, PT, WPC_>;
@@ -69,6 +69,13 @@ static int launch_one_warp(const gecon_kalman_args& a, cudaStream_t st, int* inf
         if (wpc_try == 20 && KwSmem<NP, PT, 20>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 20>(a, st, info);
         if (KwSmem<NP, PT, 16>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 16>(a, st, info);
     }
+    if constexpr (NP == 32) {
+        // filter dimensions 24..31 (the 45-variable composite of BASELINE config 4b runs at u = 26): T fragments, P and W accumulators
+        // fill the register file (255 registers), four 9 KB tiles per warp: one CTA of 5 warps per SM when Y leaves room, else 4.
+        // Still 4-5x the CTA-per-draw kernel, which spends its time in five CTA barriers per step.
+        if (KwSmem<NP, PT, 5>::bytes(a.Tobs) <= 227 * 1024) return launch_one_warp_b<NP, PT, 1, 5>(a, st, info);
+        return launch_one_warp_b<NP, PT, 1, 4>(a, st, info);
+    }
     // (NP = 24: one CTA of 8 warps instead of two of 4 measured the same, 99.8 vs 99.5 ms on the large NK model: not built)
     // NP = 8 needs 94 registers: five 4-warp CTAs per SM fit (2.57 -> 2.47 ms on the RBC workload)
     return launch_one_warp_b<NP, PT, (NP <= 8 ? 5 : NP <= 16 ? 4 : 2)>(a, st, info);
@@ -93,7 +100,7 @@ int GECON_CAT(launch_kf_, GECON_KF_NP)(const gecon_kalman_args& a, cudaStream_t 
     return GECON_E_UNSUPPORTED_SIZE;
 }
 
-#if GECON_KF_NP <= 24
+#if GECON_KF_NP <= 32
 int GECON_CAT(launch_kw_, GECON_KF_NP)(const gecon_kalman_args& a, cudaStream_t st, int* info) {
     constexpr int NP = GECON_KF_NP;
     switch (a.p) {

@@ -1,4 +1,4 @@
-// Kalman-filter log-likelihood, ONE WARP PER DRAW (small state dimensions: padded NP <= 24, selector Z).
+// Kalman-filter log-likelihood, ONE WARP PER DRAW (padded NP <= 32, i.e. filter dimension <= 31; selector Z).
 //
 // Same semantics as kalman_ll_kernel (kalman.cuh; pymc_extras StandardFilter as called from
 // gEconpy/model/statespace.py:1151-1157, restated in oracle/statespace.py): update -> jitter -> predict, Joseph-form

@@ -585,8 +585,6 @@ class BatchedStateSpace:
             raise RuntimeError("call configure(...) first")
         if not (torch is not None and isinstance(theta_full, torch.Tensor) and theta_full.is_cuda):
             raise TypeError("loglik_and_grad_device needs CUDA tensors; use loglik_and_grad() for host arrays")
-        if self.full_covariance:
-            raise NotImplementedError("the gradient path takes diagonal shock covariances (sigma_<shock>) only")
         m = self.model
         lib = L.load_library()
         dev = theta_full.device
@@ -605,7 +603,7 @@ class BatchedStateSpace:
             na, n, k, p = self.n_aug, m.n, m.k, self.p
             g = self._grad_ws = dict(
                 nc=nc, device=dev, Tfull=torch.empty((nc, n, n), **f64), Rfull=torch.empty((nc, n, k), **f64),
-                Tb_f=torch.empty((nc, na, na), **f64), Rb_f=torch.empty((nc, na, k), **f64), qb=torch.empty((nc, k), **f64),
+                Tb_f=torch.empty((nc, na, na), **f64), Rb_f=torch.empty((nc, na, k), **f64), qb=torch.empty((nc, self._n_cov), **f64),
                 hb=torch.empty((nc, p), **f64), db=torch.empty((nc, p), **f64), Tb=torch.zeros((nc, n, n), **f64),
                 Rb=torch.zeros((nc, n, k), **f64), Ab=torch.empty((nc, n, n), **f64), Bb=torch.empty((nc, n, n), **f64),
                 Cb=torch.empty((nc, n, n), **f64), Db=torch.empty((nc, n, k), **f64), thb=torch.empty((nc, m.n_theta), **f64),
@@ -629,9 +627,12 @@ class BatchedStateSpace:
             cnt = min(nc, N - lo)
             th = theta_full[lo : lo + cnt]
             ws["theta"][:cnt].copy_(th[:, : m.n_theta])
-            ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
+            if self.full_covariance:
+                ws["Q"][:cnt].copy_(th[:, m.n_theta : m.n_theta + self._n_cov].reshape(cnt, m.k, m.k))
+            else:
+                ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
             if n_err:
-                ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + m.k :])
+                ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + self._n_cov :])
             st = ws["status"][:cnt]
             e = mark("jacobian")
             m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
@@ -670,8 +671,11 @@ class BatchedStateSpace:
             ws["T"][:cnt, :nf, :nf] = g["Tfull"][:cnt].index_select(1, U).index_select(2, U)
             ws["R"][:cnt, :nf] = g["Rfull"][:cnt].index_select(1, U)
             kg = L.KalmanGradArgs(
-                struct_size=C.sizeof(L.KalmanGradArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(), qdiag=ws["sig"].data_ptr(),
-                q_stride=m.k, hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
+                struct_size=C.sizeof(L.KalmanGradArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
+                qdiag=(None if self.full_covariance else ws["sig"].data_ptr()), q_stride=m.k,
+                qfull=(ws["Q"].data_ptr() if self.full_covariance else None), qfull_stride=m.k * m.k,
+                qfull_bar=(g["qb"].data_ptr() if self.full_covariance else None),
+                hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
                 Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None),
                 obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
                 d=(ws["d"].data_ptr() if "d" in ws else None), d_stride=(self.p if "d" in ws else 0),
@@ -681,7 +685,8 @@ class BatchedStateSpace:
                 missing_fill=self.missing_fill_value, mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0,
                 status_in=st.data_ptr(), gate_mask=self.gate_mask, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(),
                 status=status[lo : lo + cnt].data_ptr(), T_bar=g["Tb_f"].data_ptr(), R_bar=g["Rb_f"].data_ptr(),
-                q_bar=g["qb"].data_ptr(), h_bar=g["hb"].data_ptr(), d_bar=g["db"].data_ptr(), mask_intercept=int(self.mask_intercept),
+                q_bar=(None if self.full_covariance else g["qb"].data_ptr()), h_bar=g["hb"].data_ptr(), d_bar=g["db"].data_ptr(),
+                mask_intercept=int(self.mask_intercept),
             )  # fmt: skip
             e = mark("kalman_grad")
             L.check(lib.gecon_kalman_grad_batched(C.byref(kg), C.c_void_p(stream)), "gecon_kalman_grad_batched")
@@ -722,9 +727,9 @@ class BatchedStateSpace:
             e and e.record()
             out = grad[lo : lo + cnt]
             out[:, : m.n_theta] = g["thb"][:cnt]
-            out[:, m.n_theta : m.n_theta + m.k] = g["qb"][:cnt]
+            out[:, m.n_theta : m.n_theta + self._n_cov] = g["qb"][:cnt]  # d/d sigma_<shock>, or the symmetrised d/d state_cov[i,j]
             if n_err:
-                out[:, m.n_theta + m.k :] = g["hb"][:cnt].index_select(1, g["err_pos"])
+                out[:, m.n_theta + self._n_cov :] = g["hb"][:cnt].index_select(1, g["err_pos"])
             bad = (status[lo : lo + cnt] != 0) | (g["st2"][:cnt] != 0)
             out.masked_fill_(bad[:, None], 0.0)
         if self.constant_params:
@@ -751,6 +756,13 @@ class BatchedStateSpace:
         Y_d = torch.as_tensor(np.ascontiguousarray(Y, dtype=np.float64).reshape(-1, self.p)).to(dev)
         ll, st = self.loglik_device(th_d, Y_d)
         return ll.cpu().numpy(), st.cpu().numpy()
+
+    def sample_autocorrelation_matrices(self, theta_full, n_lags: int = 10, observed: bool = False, lag_step: int = 1):
+        """``DSGEStateSpace.sample_autocorrelation_matrices`` (statespace.py:1217-1303) for a population of parameter draws:
+        see ``geconpy_b200.model.posterior.sample_autocorrelation_matrices``."""
+        from .posterior import sample_autocorrelation_matrices
+
+        return sample_autocorrelation_matrices(self, theta_full, n_lags=n_lags, observed=observed, lag_step=lag_step)
 
     def solve(self, theta, device="cuda:0"):
         """theta[N, n_theta] -> dict(T, R, status, n_iter, resid, n_unstable) with T, R un-permuted to variable order

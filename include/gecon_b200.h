@@ -293,6 +293,7 @@ int gecon_propagate_host(const gecon_propagate_args* args);
  * pytensor differentiates behind PyMCStateSpace.build_statespace_graph (gEconpy/model/statespace.py:812-820,1151-1157).
  * With sigma_inputs != 0, q_bar / h_bar are derivatives with respect to the standard deviations.
  * Sizes: n <= 48, k <= n, p <= 8.  Gated draws (status_in & gate_mask) get ll = -inf and zero gradients.
+ * Shock covariance: diagonal (qdiag -> q_bar) or full (qfull -> qfull_bar; full_shock_covariance=True, statespace.py:245-249).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct gecon_kalman_grad_args {
     size_t struct_size;
@@ -330,6 +331,11 @@ typedef struct gecon_kalman_grad_args {
     double* Z_bar;    /* [N][p][n] out or NULL: dll/dZ (dense design matrices; the adjoint of observation equations) */
     int32_t mask_intercept; /* as in gecon_kalman_args */
     int32_t reserved2;
+    const double* qfull;    /* full shock covariance Q, as in gecon_kalman_args ([N][k][k] with qfull_stride = k k, or shared [k][k]
+                               with 0); when given, qdiag / q_bar are ignored (may be NULL) and the derivative goes to qfull_bar */
+    int64_t qfull_stride;
+    double* qfull_bar;      /* [N][k][k] out: dll/dQ, symmetrised ((G + G') / 2, G = R' C0_bar R): Q is a covariance, only the
+                               symmetric part of its derivative is defined */
 } gecon_kalman_grad_args;
 
 int gecon_kalman_grad_batched(const gecon_kalman_grad_args* args, void* stream);

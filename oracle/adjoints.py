@@ -76,8 +76,9 @@ def dlyap_adjoint(T, P0, P0_bar, max_iter=64):
 
 
 def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, missing_fill=oss.MISSING_FILL, mvn_const="per_obs",
-                           mask_intercept=False):
-    """ll and its gradient with respect to T (n,n), R (n,k), q (k, shock VARIANCES), h (p, error VARIANCES), d (p).
+                           mask_intercept=False, Q=None):
+    """ll and its gradient with respect to T (n,n), R (n,k), q (k, shock VARIANCES; or Q (k,k), the full shock covariance, when
+    ``Q`` is given), h (p, error VARIANCES), d (p).
 
     Forward pass as ``oracle.statespace.kalman_loglik`` (a0 = 0, P0 = dlyap(T, R diag(q) R'), d NOT masked), storing the
     predicted moments; then the reverse sweep.  Matrices are treated as unconstrained in the sweep (the forward map
@@ -85,7 +86,8 @@ def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, 
     Y = np.asarray(Y, dtype=np.float64)
     n, k, p, Tobs = T.shape[0], R.shape[1], Z.shape[0], Y.shape[0]
     d = np.zeros(p) if d is None else np.asarray(d, dtype=np.float64)
-    C0 = R @ np.diag(q) @ R.T
+    Qm = np.diag(q) if Q is None else np.asarray(Q, dtype=np.float64)  # Q: full shock covariance (statespace.py:245-249); then q is unused
+    C0 = R @ Qm @ R.T
     P0 = oss.dlyap(T, C0)
     I_n, I_p = np.eye(n), np.eye(p)
     log2pi = np.log(2.0 * np.pi)
@@ -163,9 +165,9 @@ def kalman_loglik_adjoints(Y, T, R, q, Z, h, d=None, jitter=oss.JITTER_DEFAULT, 
     S, T_lyap = dlyap_adjoint(T, P0, P_bar)
     C0_bar += S
     T_bar += T_lyap
-    R_bar = C0_bar @ R @ np.diag(q) + C0_bar.T @ R @ np.diag(q)
-    q_bar = np.einsum("ic,ij,jc->c", R, C0_bar, R)
-    return dict(ll=ll, T=T_bar, R=R_bar, q=q_bar, h=h_bar, d=d_bar, Z=Z_bar)
+    R_bar = C0_bar @ R @ Qm.T + C0_bar.T @ R @ Qm
+    Q_bar = R.T @ C0_bar @ R  # every entry of Q treated as an independent input
+    return dict(ll=ll, T=T_bar, R=R_bar, q=np.diag(Q_bar).copy(), Q=Q_bar, h=h_bar, d=d_bar, Z=Z_bar)
 
 
 def loglik_grad(model, theta, Y, observed, sigma_shock, sigma_err=None, tol=1e-13, max_iter=1000, jitter=oss.JITTER_DEFAULT, fd_eps=1e-6):

@@ -150,6 +150,76 @@ def test_kalman_grad_source_matches_oracle(hostcheck, n, k, p, Tobs, missing, se
             assert np.abs(Zb[i] - g["Z"]).max() <= 1e-10 * max(1.0, np.abs(g["Z"]).max())
 
 
+def test_kalman_grad_source_with_a_full_shock_covariance(hostcheck):
+    """full_shock_covariance=True (statespace.py:245-249): Q is a k x k input, C0 = R Q R'; dll/dQ_ab for every entry, against the
+    oracle's adjoint, itself against central differences of the oracle's filter."""
+    rng = np.random.default_rng(5)
+    N, n, k, p, Tobs = 2, 6, 3, 2, 30
+    T, R, _q, h, Z, Y, d = _random_filter(rng, N, n, k, p, Tobs, False)
+    Lq = rng.standard_normal((N, k, k))
+    Q = np.einsum("nij,nkj->nik", Lq, Lq) + 0.3 * np.eye(k)
+    serr = np.sqrt(h)
+    ll, st = np.zeros(N), np.zeros(N, np.int32)
+    Tb, Rb, Qb, hb, db = np.zeros((N, n, n)), np.zeros((N, n, k)), np.zeros((N, k, k)), np.zeros((N, p)), np.zeros((N, p))
+    Zb = np.zeros((N, p, n))
+    a = L.KalmanGradArgs(
+        struct_size=C.sizeof(L.KalmanGradArgs), T=T.ctypes.data, R=R.ctypes.data, qdiag=None, q_stride=0, hdiag=serr.ctypes.data, h_stride=p,
+        Z=Z.ctypes.data, obs_idx=None, d=d.ctypes.data, d_stride=p, Y=Y.ctypes.data, N=N, n=n, k=k, p=p, Tobs=Tobs, jitter=1e-8,
+        missing_fill=-9999.0, mvn_const_mode=0, lyap_max_iter=0, status_in=None, gate_mask=0, sigma_inputs=1, ll=ll.ctypes.data,
+        status=st.ctypes.data, T_bar=Tb.ctypes.data, R_bar=Rb.ctypes.data, q_bar=None, h_bar=hb.ctypes.data, d_bar=db.ctypes.data, z_stride=0,
+        Z_bar=Zb.ctypes.data, qfull=Q.ctypes.data, qfull_stride=k * k, qfull_bar=Qb.ctypes.data,
+    )  # fmt: skip
+    assert hostcheck.gecon_kalman_grad_hostcheck(C.byref(a)) == 0
+    for i in range(N):
+        g = oad.kalman_loglik_adjoints(Y, T[i], R[i], None, Z, h[i], d[i], Q=Q[i])
+        assert st[i] == 0 and abs(ll[i] - g["ll"]) <= 1e-9
+        # (Q is a covariance: only the symmetric part of dll/dQ is defined -- how it splits between Q_ab and Q_ba depends on how a
+        # filter is extended to non-symmetric covariances -- so the kernel returns it symmetrised)
+        q_ref = 0.5 * (g["Q"] + g["Q"].T)
+        assert np.abs(Qb[i] - Qb[i].T).max() <= 1e-13 * np.abs(Qb[i]).max()
+        for got, ref in ((Tb[i], g["T"]), (Rb[i], g["R"]), (Qb[i], q_ref), (hb[i], 2 * serr[i] * g["h"]), (db[i], g["d"]), (Zb[i], g["Z"])):
+            assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+    g = oad.kalman_loglik_adjoints(Y, T[0], R[0], None, Z, h[0], d[0], Q=Q[0])
+    num = _fd(Q[0], lambda q_: oss.kalman_loglik(Y, T[0], R[0], q_, Z, np.diag(h[0]), d=d[0]))
+    assert np.abs(0.5 * (num + num.T) - 0.5 * (g["Q"] + g["Q"].T)).max() <= 2e-7 * max(1.0, np.abs(num).max())  # (symmetric parts: see above)
+
+
+@pytest.mark.parametrize("name,Tobs", [("full_nk", 50), ("nk_complete_more_shocks", 30)])
+def test_kalman_grad_source_on_model_matrices_with_tiny_error_variances(hostcheck, name, Tobs):
+    """The regime the estimation runs in -- T, R of a solved model, selector Z, error variances 1e-6 next to state variances 1e-4 --
+    is where an un-symmetrised rank-p covariance update loses the gradient completely (its antisymmetric mode is not damped); random
+    well-conditioned filters do not show it.  Same source as the GPU kernel, against the oracle's Joseph-form adjoint."""
+    mod = model(name)
+    observed = mod.spec["observed_default"]
+    th = draws(mod, 2, seed=31, width=0.02, valid=True)
+    Y = simulate_obs(mod, Tobs, seed=3, sigma_err=SIGMA_ERR)
+    N, n, k, p = len(th), mod.n, mod.k, len(observed)
+    T, R = np.zeros((N, n, n)), np.zeros((N, n, k))
+    for i in range(N):
+        A, B, Cm, D = mod.jacobians(th[i], mode="statespace")
+        Ti = osol.cycle_reduction_core(A, B, Cm, max_iter=1000, tol=1e-13)[0]
+        T[i], R[i] = mod.unpermute_policy(Ti, osol.selection_matrix(B, Cm, D, Ti))
+    obs = np.array([mod.var_names.index(v) for v in observed], dtype=np.int32)
+    Z = np.zeros((p, n))
+    Z[np.arange(p), obs] = 1.0
+    sig, serr, d = np.full((N, k), SIGMA_SHOCK), np.full((N, p), SIGMA_ERR), np.zeros((N, p))
+    ll, st = np.zeros(N), np.zeros(N, np.int32)
+    Tb, Rb, qb, hb, db = np.zeros((N, n, n)), np.zeros((N, n, k)), np.zeros((N, k)), np.zeros((N, p)), np.zeros((N, p))
+    a = L.KalmanGradArgs(
+        struct_size=C.sizeof(L.KalmanGradArgs), T=T.ctypes.data, R=R.ctypes.data, qdiag=sig.ctypes.data, q_stride=k, hdiag=serr.ctypes.data,
+        h_stride=p, Z=None, obs_idx=obs.ctypes.data, d=d.ctypes.data, d_stride=p, Y=Y.ctypes.data, N=N, n=n, k=k, p=p, Tobs=Tobs, jitter=1e-8,
+        missing_fill=-9999.0, mvn_const_mode=0, lyap_max_iter=0, status_in=None, gate_mask=0, sigma_inputs=1, ll=ll.ctypes.data,
+        status=st.ctypes.data, T_bar=Tb.ctypes.data, R_bar=Rb.ctypes.data, q_bar=qb.ctypes.data, h_bar=hb.ctypes.data, d_bar=db.ctypes.data,
+        z_stride=0, Z_bar=None,
+    )  # fmt: skip
+    assert hostcheck.gecon_kalman_grad_hostcheck(C.byref(a)) == 0
+    for i in range(N):
+        g = oad.kalman_loglik_adjoints(Y, T[i], R[i], sig[i] ** 2, Z, serr[i] ** 2, d[i])
+        assert st[i] == 0 and abs(ll[i] - g["ll"]) <= 1e-9
+        for got, ref in ((Tb[i], g["T"]), (Rb[i], g["R"]), (qb[i], 2 * sig[i] * g["q"]), (hb[i], 2 * serr[i] * g["h"]), (db[i], g["d"])):
+            assert np.abs(got - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("name", ["rbc", "rbc_extended", "full_nk", "nk_complete_more_shocks"])
 @pytest.mark.parametrize("with_R", [False, True])
 def test_policy_adjoint_source_matches_the_kronecker_restatement(hostcheck, name, with_R):

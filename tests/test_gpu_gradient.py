@@ -228,3 +228,48 @@ def test_pipeline_gradient_through_observation_equations():
         fm[:, j] -= h
         num = (ss.loglik(fp, Y)[0] - ss.loglik(fm, Y)[0]) / (2 * h)
         assert np.abs(num - grad[:, j]).max() <= 2e-4 * max(1.0, np.abs(num).max()), (j, num, grad[:, j])
+
+
+def test_pipeline_gradient_with_a_full_shock_covariance():
+    """full_shock_covariance=True (statespace.py:245-249): the parameter vector carries state_cov[i, j], the
+    gradient its symmetrised derivative.  Checked against central differences of the GPU log-likelihood along SYMMETRIC directions
+    of Q (E_ab + E_ba: the only directions a covariance can move in), and the diagonal-covariance path as a special case."""
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    mod = model("full_nk")
+    observed = mod.spec["observed_default"]
+    cm = CompiledModel("full_nk")
+    kw = dict(observed_states=observed, measurement_error=observed, tol=1e-13, max_iter=1000)
+    ss = BatchedStateSpace(cm).configure(full_shock_covariance=True, **kw)
+    ss_d = BatchedStateSpace(cm).configure(**kw)
+    N, k, nt = 3, mod.k, mod.theta_vector().size
+    th = draws(mod, N, seed=12, width=0.02, valid=True)
+    Y = simulate_obs(mod, 40, seed=3, sigma_err=SIGMA_ERR)
+    rng = np.random.default_rng(2)
+    Lq = SIGMA_SHOCK * (np.eye(k) + 0.3 * rng.standard_normal((N, k, k)))
+    Q = np.einsum("nij,nkj->nik", Lq, Lq)
+    err = np.full((N, len(observed)), SIGMA_ERR)
+    full = np.hstack([th, Q.reshape(N, -1), err])
+    ll, grad, st = ss.loglik_and_grad(full, Y)
+    assert (st == 0).all() and grad.shape == (N, nt + k * k + len(observed))
+    gQ = grad[:, nt : nt + k * k].reshape(N, k, k)
+    assert np.abs(gQ - gQ.transpose(0, 2, 1)).max() <= 1e-12 * np.abs(gQ).max()
+    for a, b in ((0, 0), (1, 1), (0, 1), (2, 3), (1, 3)):
+        E = np.zeros((k, k))
+        E[a, b] = E[b, a] = 1.0
+        h = 1e-6 * Q[:, a, a].mean()
+        fp, fm = full.copy(), full.copy()
+        fp[:, nt : nt + k * k] += h * E.ravel()
+        fm[:, nt : nt + k * k] -= h * E.ravel()
+        num = (ss.loglik(fp, Y)[0] - ss.loglik(fm, Y)[0]) / (2 * h)
+        want = (gQ * E[None]).sum(axis=(1, 2))
+        assert np.abs(num - want).max() <= 1e-4 * np.abs(want).max(), (a, b, num, want)
+    # a diagonal Q through the full-covariance path == the sigma path: same ll, d/d sigma = 2 sigma d/d Q_cc, same theta gradient
+    sig = np.full((N, k), SIGMA_SHOCK) * (1.0 + 0.1 * np.arange(N))[:, None]
+    Qd = np.stack([np.diag(s_**2) for s_ in sig])
+    ll_f, g_f, _ = ss.loglik_and_grad(np.hstack([th, Qd.reshape(N, -1), err]), Y)
+    ll_s, g_s, _ = ss_d.loglik_and_grad(np.hstack([th, sig, err]), Y)
+    assert np.abs(ll_f - ll_s).max() <= 1e-7
+    assert _close(g_f[:, :nt], g_s[:, :nt], rtol=1e-8)
+    dQ = g_f[:, nt : nt + k * k].reshape(N, k, k)
+    assert _close(2 * sig * np.diagonal(dQ, axis1=1, axis2=2), g_s[:, nt : nt + k], rtol=1e-8)

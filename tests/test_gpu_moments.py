@@ -100,3 +100,77 @@ def test_propagate_sizes(rng):
             for t in range(L):
                 x = T[i] @ x + R[i] @ E[i, t]
                 np.testing.assert_allclose(out[i, t], x, rtol=1e-11, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------- posterior-batched ACF, prior-predictive data
+def _configured(name, observed, meas):
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    return BatchedStateSpace(CompiledModel(name)).configure(observed_states=observed, measurement_error=meas, tol=1e-13, max_iter=1000)
+
+
+@pytest.mark.parametrize("name,observed,lag_step", [("rbc", ["Y", "C"], 1), ("rbc", ["Y", "C"], 4), ("full_nk", ["Y", "pi", "r_G"], 1)])
+def test_sample_autocorrelation_matrices_matches_the_reference_formula(name, observed, lag_step):
+    """statespace.py:1266-1298 restated with scipy on the oracle's T, R: Sigma = dlyap(T, R Q R'), T_step = T^lag_step,
+    acov_k = T_step^k Sigma (Z . Z' and + H at lag 0 when observed), normalised by the lag-0 standard deviations."""
+    import scipy.linalg as sla
+
+    from helpers import SIGMA_ERR, SIGMA_SHOCK, draws
+    from oracle import solvers as osol
+
+    from geconpy_b200.model.posterior import sample_autocorrelation_matrices
+
+    mod = model(name)
+    ss = _configured(name, observed, observed)
+    N, n_lags = 5, 6
+    th = draws(mod, N, seed=11, width=0.02, valid=True)
+    sig = np.full((N, mod.k), SIGMA_SHOCK) * (1.0 + 0.2 * np.arange(N))[:, None]
+    err = np.full((N, len(observed)), SIGMA_ERR)
+    full = np.hstack([th, sig, err])
+    got_all, st = sample_autocorrelation_matrices(ss, full, n_lags=n_lags, lag_step=lag_step, return_status=True)
+    got_obs = sample_autocorrelation_matrices(ss, full, n_lags=n_lags, lag_step=lag_step, observed=True)
+    assert (st == 0).all() and got_all.shape == (N, n_lags + 1, mod.n, mod.n) and got_obs.shape == (N, n_lags + 1, len(observed), len(observed))
+    Z = np.zeros((len(observed), mod.n))
+    Z[np.arange(len(observed)), [mod.var_names.index(v) for v in observed]] = 1.0
+    for i in range(N):
+        A, B, C, D = mod.jacobians(th[i], mode="statespace")
+        T = osol.cycle_reduction_core(A, B, C, max_iter=1000, tol=1e-13)[0]
+        T, R = mod.unpermute_policy(T, osol.selection_matrix(B, C, D, T))
+        Sigma = sla.solve_discrete_lyapunov(T, R @ np.diag(sig[i] ** 2) @ R.T, method="direct")
+        Ts = np.linalg.matrix_power(T, lag_step)
+        acov = np.stack([np.linalg.matrix_power(Ts, k_) @ Sigma for k_ in range(n_lags + 1)])
+        std = np.sqrt(np.diag(acov[0]))
+        with np.errstate(all="ignore"):
+            ref_all = acov / np.outer(std, std)[None]
+        ok = np.isfinite(ref_all)  # variables with zero variance (0 / 0) are NaN on both sides
+        assert np.array_equal(np.isfinite(got_all[i]), ok) and np.abs(got_all[i][ok] - ref_all[ok]).max() <= 1e-8
+        aco = Z @ acov @ Z.T
+        aco[0] = Z @ Sigma @ Z.T + np.diag(err[i] ** 2)
+        so = np.sqrt(np.diag(aco[0]))
+        assert np.abs(got_obs[i] - aco / np.outer(so, so)[None]).max() <= 1e-8
+    assert np.allclose(np.diagonal(got_obs[:, 0], axis1=-2, axis2=-1), 1.0)
+
+
+def test_data_from_prior_is_reproducible_and_consistent_with_the_likelihood():
+    """statespace.py:1324-1429: prior draws, one unconditional trajectory each, one of them the truth.  Same seed -> same data; the
+    requested share of every column is missing; the truth's own likelihood of its data is finite and beats a clearly wrong draw."""
+    from geconpy_b200.model.posterior import data_from_prior
+
+    ss = _configured("rbc", ["Y", "C"], ["Y", "C"])
+    truth, data, prior = data_from_prior(ss, n_timesteps=120, n_samples=64, pct_missing=0.1, random_seed=7)
+    truth2, data2, prior2 = data_from_prior(ss, n_timesteps=120, n_samples=64, pct_missing=0.1, random_seed=7)
+    D, D2 = np.asarray(data), np.asarray(data2)
+    assert D.shape == (120, 2) and np.array_equal(np.isnan(D), np.isnan(D2)) and np.array_equal(np.nan_to_num(D), np.nan_to_num(D2))
+    assert truth == truth2 and list(getattr(data, "columns", ["Y", "C"])) == ["Y", "C"]
+    assert (np.isnan(D).sum(axis=0) == 12).all()
+    ok = prior["status"] == 0
+    assert ok[prior["param_idx"]] and ok.sum() >= 32 and prior["observed"].shape == (64, 120, 2)
+    assert np.isfinite(prior["observed"][ok]).all() and np.isnan(prior["observed"][~ok]).all()
+    m = ss.model
+    th_true = np.array([truth[p_] for p_ in m.param_names])
+    full = np.hstack([prior["theta"], np.full((64, m.k), 0.01), np.full((64, 2), 1e-3)])
+    ll, st = ss.loglik(full, D)
+    i = prior["param_idx"]
+    assert np.array_equal(prior["theta"][i], th_true) and st[i] == 0 and np.isfinite(ll[i])
+    finite = np.isfinite(ll)
+    assert ll[i] >= np.median(ll[finite])  # the data-generating draw explains its own data better than a typical prior draw
