@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 MODEL_LIBDIR = LIBDIR / "models"
 CORE_LIB = LIBDIR / "libgecon_b200.so"
-CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu", "grad.cu", "eig.cu", "pipeline.cu"]
+CORE_SOURCES = ["capi.cu", "cr_solve.cu", "kalman.cu", "bk_count.cu", "propagate.cu", "grad.cu", "eig.cu", "pipeline.cu", "policy_adjoint.cu"]
 # the Kalman kernel is instantiated for (NP, p) in 8 x 8 combinations: one object per padded dimension NP, built in parallel
 KALMAN_INST = "kalman_inst.cu"
 KALMAN_NPS = [8, 16, 24, 32, 40, 48, 56, 64]

@@ -7,6 +7,8 @@
 
 namespace gecon {
 
+int policy_adjoint_dmma_launch(const gecon_grad::PolicyAdjointArgs& g, cudaStream_t st);  // policy_adjoint.cu
+
 __global__ void kalman_grad_kernel(const gecon_grad::KalmanGradArgs g) {
     extern __shared__ __align__(16) double sm_grad[];
     for (long long draw = blockIdx.x; draw < g.N; draw += gridDim.x) {
@@ -105,6 +107,10 @@ extern "C" int gecon_policy_adjoint_batched(const gecon_policy_adjoint_args* a, 
     if (rc) return rc;
     if (a->N == 0) return 0;
     const gecon_grad::PolicyAdjointArgs g = gecon_grad::to_internal(*a);
+    // tensor-path kernel (policy_adjoint.cu); GECON_PA_DFMA=1 keeps the host-checkable DFMA version below (same arithmetic, one source
+    // with the CPU check build)
+    static const bool use_dfma = getenv("GECON_PA_DFMA") && atoi(getenv("GECON_PA_DFMA")) != 0;
+    if (!use_dfma) return policy_adjoint_dmma_launch(g, (cudaStream_t)stream);
     const int nt = grad_threads(a->n);
     const size_t smem = sizeof(double) * gecon_grad::policy_adjoint_smem_doubles(a->n, nt);
     int grid = 0;

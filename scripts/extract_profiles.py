@@ -4,7 +4,7 @@ and the hot source lines.  Usage: python scripts/extract_profiles.py [tag]"""
 import csv, json, shutil, sys
 from pathlib import Path
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 root = Path(__file__).resolve().parent.parent
 src, dst = root / "gpurun_out" / f"profiles_{tag}", root / "profiles"
 WANT = [
@@ -21,10 +21,12 @@ for f in src.glob(f"{tag}_bench_*.json"):
     lines = [l for l in f.read_text().splitlines() if l.startswith("{")]
     if lines:
         (dst / f.name).write_text(lines[-1] + "\n")
-for f in list(src.glob(f"{tag}_launches_nk.csv")) + list(src.glob(f"{tag}_*_lines.txt")) + list(src.glob(f"{tag}_gradient_timing.json")):
+for f in (list(src.glob(f"{tag}_launches_nk.csv")) + list(src.glob(f"{tag}_*_lines.txt")) + list(src.glob(f"{tag}_gradient_timing.json"))
+          + list(src.glob(f"{tag}_*_opmix.txt")) + list(src.glob(f"{tag}_*_key_metrics.txt"))):
     shutil.copy(f, dst / f.name)
 raw, traffic = {}, {"source": "ncu --set full --clock-control none, bench.py --draws 65536 (one chunk = one launch), medium NK"}
-for k in ("cr_solve", "kalman"):
+STAGE = {"cr_solve": "cr_solve", "kalman": "kalman_ll", "cr_warp": "cr_solve", "kalman_ll_warp": "kalman_ll"}  # capture name -> bench.py stage
+for k in STAGE:
     f = src / f"{tag}_{k}_raw.csv"
     if not f.exists():
         continue
@@ -45,7 +47,7 @@ for k in ("cr_solve", "kalman"):
     draws = 65536
     if "dram__bytes_read.sum" in m:
         traffic[name.split("(")[0].replace("void ", "").replace("gecon::", "")] = {
-            "dram_bytes_per_draw": (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / draws}
+            "stage": STAGE[k], "dram_bytes_per_draw": (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / draws}
 (dst / f"{tag}_ncu_raw_metrics.json").write_text(json.dumps(raw, indent=1))
 (dst / f"{tag}_ncu_traffic.json").write_text(json.dumps(traffic, indent=1))
 print(json.dumps({k: {kk: vv for kk, vv in m.items() if "stalled" not in kk} for k, m in raw.items()}, indent=1))

@@ -320,5 +320,6 @@ def test_full_shock_covariance_pipeline():
         else:
             assert np.isneginf(ll[i])
     assert n_ok >= N // 2
-    with pytest.raises(NotImplementedError):
-        ss.loglik_and_grad(np.hstack([th, Q.reshape(N, -1), err]), Y)
+    # the gradient path takes the full covariance too (round 2; checked in tests/test_gpu_gradient.py): same ll, finite gradient
+    ll_g, grad, st_g = ss.loglik_and_grad(np.hstack([th, Q.reshape(N, -1), err]), Y)
+    assert np.array_equal(st_g, st) and np.abs(ll_g[st == 0] - ll[st == 0]).max() <= TOL_LL and np.isfinite(grad).all()
