@@ -89,11 +89,12 @@ extern "C" int gecon_kalman_grad_batched(const gecon_kalman_grad_args* a, void* 
     int grid = 0;
     rc = persistent_grid(kalman_grad_kernel, nt, smem, a->N, &grid, nullptr);
     if (rc) return rc;
-    const size_t per_cta = (size_t)a->Tobs * ((size_t)a->n * a->n + a->n) + 2 * (size_t)a->n * a->n;
+    const size_t traj_cta = (size_t)a->Tobs * gecon_grad::kalman_grad_traj_stride(a->n, a->p);
+    const size_t per_cta = traj_cta + 2 * (size_t)a->n * a->n;
     double* ws = nullptr;
     GECON_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * per_cta * grid, st));
     g.traj = ws;
-    g.c0bar_ws = ws + (size_t)grid * a->Tobs * ((size_t)a->n * a->n + a->n);
+    g.c0bar_ws = ws + (size_t)grid * traj_cta;
     kalman_grad_kernel<<<grid, nt, smem, st>>>(g);
     g_launch_count++;
     const cudaError_t le = cudaGetLastError();

@@ -50,11 +50,12 @@ GHH int ldim(int n) { return n | 1; }  // odd leading dimension: column walks hi
 //   epi(i, j, sum_k a(i, k) * b(k, j)),   i < m, j < n, k < kk,
 // so one a-load and four b-loads feed four FMA (1.25 shared loads per FMA instead of 2) and the index decode is paid once
 // per four outputs.  a, b, epi are inlined lambdas; column indices past n are clamped (their results are dropped).
+// tab (optional): work item -> (i << 16) | j0, precomputed once so that the sweeps do no integer division.
 template <class FA, class FB, class FE>
-GHD void gemm4(int m, int n, int kk, FA a, FB b, FE epi) {
+GHD void gemm4(int m, int n, int kk, FA a, FB b, FE epi, const int* tab = nullptr) {
     const int nb = (n + 3) >> 2;
     GFOR(w, m * nb) {
-        const int i = w / nb, j0 = (w - i * nb) << 2;
+        const int i = tab ? (tab[w] >> 16) : w / nb, j0 = tab ? (tab[w] & 0xffff) : (w - (w / nb) * nb) << 2;
         const int j1 = (j0 + 1 < n) ? j0 + 1 : n - 1, j2 = (j0 + 2 < n) ? j0 + 2 : n - 1, j3 = (j0 + 3 < n) ? j0 + 3 : n - 1;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll 2
@@ -158,11 +159,14 @@ struct KalmanGradArgs {
     double* c0bar_ws;  // workspace [n_cta][2][n n]: adjoint of R Q R', and R Q R' itself
 };
 
+// doubles per step of the trajectory buffer: predicted P (n n) and a (n), then F^-1 (p p), v (p) and K (n p) of the update
+GHH size_t kalman_grad_traj_stride(int n, int p) { return (size_t)n * n + n + (size_t)p * p + p + (size_t)n * p; }
+
 // doubles of shared memory needed by kalman_grad_draw
 GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
     const int ld = ldim(n);
-    return (size_t)8 * n * ld + (size_t)6 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
-           k + (size_t)k * k + nt + 8;
+    return (size_t)8 * n * ld + (size_t)5 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
+           k + (size_t)k * k + nt + 8 + ((size_t)n * n + (size_t)n * p + (size_t)n * ((n + 3) / 4) + 1) / 2;
 }
 
 // One draw.  sm: shared memory (kalman_grad_smem_doubles), cta: index of this CTA's workspace slot.
@@ -197,8 +201,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     const int ps = p;             // row stride of the n x p panels and of the p x p matrices
     double* PZ = Tb + tile;       // [n][p]
     double* K = PZ + n * ps;
-    double* Nn = K + n * ps;      // PZ + jitter K
-    double* Kb = Nn + n * ps;
+    double* Kb = K + n * ps;
     double* PZb = Kb + n * ps;
     double* G1 = PZb + n * ps;    // K_bar F^-1
     double* Zs = G1 + n * ps;     // [p][n]
@@ -224,6 +227,9 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     double* qs = Rs + n * (k > 0 ? k : 1);
     double* Qs = qs + k;  // [k][k] full shock covariance (when g.qfull)
     double* s_red = Qs + k * k;
+    int* dec = reinterpret_cast<int*>(s_red + G_NT + 8);  // [n n] element index -> (i << 16) | j: no integer division inside the sweeps
+    int* decp = dec + n * n;                              // [n p] panel index -> (i << 16) | c
+    int* decg = decp + n * p;                             // [n ceil(n / 4)] work item of an n x n gemm4 -> (i << 16) | j0
 
     const double LOG2PI = 1.8378770664093453;
     const double ll_const = (g.mvn_const_mode == 0) ? p * LOG2PI : LOG2PI;
@@ -247,7 +253,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         return;
     }
-    double* traj = g.traj + (size_t)cta * Tobs * (size_t)(n * n + n);
+    const size_t TS = kalman_grad_traj_stride(n, p);
+    double* traj = g.traj + (size_t)cta * Tobs * TS;
     double* gC0b = g.c0bar_ws + (size_t)cta * 2 * n * n;
     double* C0 = gC0b + n * n;  // R Q R' (read once per forward step): global, L2-resident, to keep the shared-memory footprint down
     const double* gT = g.T + (size_t)draw * n * n;
@@ -285,6 +292,9 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         a[i] = 0.0;
         ab[i] = 0.0;
     }
+    GFOR(idx, n * n) dec[idx] = ((idx / n) << 16) | (idx % n);
+    GFOR(idx, n * p) decp[idx] = ((idx / p) << 16) | (idx % p);
+    GFOR(idx, n * ((n + 3) >> 2)) decg[idx] = ((idx / ((n + 3) >> 2)) << 16) | ((idx % ((n + 3) >> 2)) << 2);
     GSYNC();
     // C0 = R Q R'
     GFOR(idx, n * n) {
@@ -333,21 +343,41 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     }
     GSYNC();
 
-    // One update step on the predicted (a, P): fills w, ym, v, PZ, F^-1 (in F), K, e, af, Nn, Pf.
-    auto update = [&](int t, bool accumulate_ll) {
+    // P Zm' (n x p) and the missing-value masks of step t
+    auto masks = [&](int t) {
         GFOR(i, p) {
             const double yv = g.Y[(size_t)t * p + i];
             const bool miss = (yv != yv) || (yv == g.missing_fill);
             w[i] = miss ? 0.0 : 1.0;
             ym[i] = miss ? 0.0 : yv;
         }
-        GSYNC();
+    };
+    auto pz_panel = [&]() {
         GFOR(idx, n * p) {
-            const int i = idx / p, c = idx - i * p;
+            const int i = decp[idx] >> 16, c = decp[idx] & 0xffff;
             double s = 0.0;
             for (int j = 0; j < n; ++j) s = fma(P[i * ld + j], Zs[c * n + j], s);
             PZ[i * ps + c] = w[c] * s;
         }
+    };
+    // Pf = P - K (PZ + j K)' + j I   (N = PZ + j K is never stored)
+    auto filtered_cov = [&]() {
+        GFOR(idx, n * n) {
+            const int i = dec[idx] >> 16, j = dec[idx] & 0xffff;
+            double s = P[i * ld + j] + ((i == j) ? jit : 0.0);
+            for (int c = 0; c < p; ++c) s = fma(-K[i * ps + c], fma(jit, K[j * ps + c], PZ[j * ps + c]), s);
+            Pf[i * ld + j] = s;
+        }
+    };
+
+    // ---- forward sweep: store the predicted moments and the update's F^-1, v, K; filter; predict
+    for (int t = 0; t < Tobs; ++t) {
+        double* tr = traj + (size_t)t * TS;
+        GFOR(idx, n * n) tr[idx] = P[(dec[idx] >> 16) * ld + (dec[idx] & 0xffff)];
+        GFOR(i, n) tr[n * n + i] = a[i];
+        masks(t);
+        GSYNC();
+        pz_panel();
         GFOR(c, p) {
             double s = 0.0;
             for (int j = 0; j < n; ++j) s = fma(Zs[c * n + j], a[j], s);
@@ -371,7 +401,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
                     F[c * ps + b] = F[b * ps + c] = s;
                 }
             double logdet = 0.0;
-            const bool ok = spd_inverse_small(F, p, ps, accumulate_ll ? &logdet : nullptr);
+            const bool ok = spd_inverse_small(F, p, ps, &logdet);
             if (!ok) sc[1] = 0.0;
             sc[0] = logdet;
             double allmiss = 1.0;
@@ -380,46 +410,38 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             sc[3] = allmiss;
         }
         GSYNC();
+        double* trF = tr + n * n + n;
+        double* trv = trF + p * p;
+        double* trK = trv + p;
         GFOR(idx, n * p) {
-            const int i = idx / p, c = idx - i * p;
+            const int i = decp[idx] >> 16, c = decp[idx] & 0xffff;
             double s = 0.0;
             for (int b = 0; b < p; ++b) s = fma(PZ[i * ps + b], F[b * ps + c], s);
             K[i * ps + c] = s;
-            Nn[i * ps + c] = fma(jit, s, PZ[i * ps + c]);
+            trK[idx] = s;
         }
         GFOR(c, p) {
             double s = 0.0;
             for (int b = 0; b < p; ++b) s = fma(F[c * ps + b], v[b], s);
             e[c] = s;
+            trv[c] = v[c];
         }
+        GFOR(idx, p * p) trF[idx] = F[idx];
         GSYNC();
         GFOR(i, n) {
             double s = a[i];
             for (int c = 0; c < p; ++c) s = fma(K[i * ps + c], v[c], s);
             af[i] = s;
         }
-        GFOR(idx, n * n) {
-            const int i = idx / n, j = idx - i * n;
-            double s = P[i * ld + j] + ((i == j) ? jit : 0.0);
-            for (int c = 0; c < p; ++c) s = fma(-K[i * ps + c], Nn[j * ps + c], s);
-            Pf[i * ld + j] = s;
-        }
-        if (accumulate_ll && G_TID == 0 && sc[3] == 0.0) {
+        filtered_cov();
+        if (G_TID == 0 && sc[3] == 0.0) {
             double quad = 0.0;
             for (int c = 0; c < p; ++c) quad = fma(v[c], e[c], quad);
             sc[2] += -0.5 * (ll_const + sc[0] + quad);
         }
         GSYNC();
-    };
-
-    // ---- forward sweep: store the predicted moments, filter, predict
-    for (int t = 0; t < Tobs; ++t) {
-        double* tr = traj + (size_t)t * (n * n + n);
-        GFOR(idx, n * n) tr[idx] = P[(idx / n) * ld + (idx % n)];
-        GFOR(i, n) tr[n * n + i] = a[i];
-        update(t, true);
         gemm4(n, n, n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
-              [&](int i, int j, double v_) { W2[i * ld + j] = v_; });
+              [&](int i, int j, double v_) { W2[i * ld + j] = v_; }, decg);
         GFOR(i, n) {
             double s = 0.0;
             for (int j = 0; j < n; ++j) s = fma(Tm[i * ld + j], af[j], s);
@@ -427,7 +449,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return W2[i * ld + k_]; }, [&](int k_, int j) { return Tm[j * ld + k_]; },
-              [&](int i, int j, double v_) { P[i * ld + j] = v_ + C0[i * n + j]; });
+              [&](int i, int j, double v_) { P[i * ld + j] = v_ + C0[i * n + j]; }, decg);
         GFOR(i, n) a[i] = an[i];
         GSYNC();
     }
@@ -439,22 +461,49 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     GFOR(idx, n * ld) Pb[idx] = 0.0;
     GSYNC();
     for (int t = Tobs - 1; t >= 0; --t) {
-        const double* tr = traj + (size_t)t * (n * n + n);
-        GFOR(idx, n * n) P[(idx / n) * ld + (idx % n)] = tr[idx];
+        const double* tr = traj + (size_t)t * TS;
+        const double* trF = tr + n * n + n;
+        const double* trv = trF + p * p;
+        const double* trK = trv + p;
+        // replay of the update: P, a, F^-1, v, K come back from the trajectory; PZ, e, af, Pf are recomputed (O(n^2 p))
+        GFOR(idx, n * n) P[(dec[idx] >> 16) * ld + (dec[idx] & 0xffff)] = tr[idx];
         GFOR(i, n) a[i] = tr[n * n + i];
+        GFOR(idx, p * p) F[idx] = trF[idx];
+        GFOR(c, p) v[c] = trv[c];
+        GFOR(idx, n * p) K[idx] = trK[idx];
+        masks(t);
         GSYNC();
-        update(t, false);
+        pz_panel();
+        GFOR(c, p) {
+            double s = 0.0;
+            for (int b = 0; b < p; ++b) s = fma(F[c * ps + b], v[b], s);
+            e[c] = s;
+        }
+        GFOR(i, n) {
+            double s = a[i];
+            for (int c = 0; c < p; ++c) s = fma(K[i * ps + c], v[c], s);
+            af[i] = s;
+        }
+        if (G_TID == 0) {
+            double allmiss = 1.0;
+            for (int c = 0; c < p; ++c)
+                if (w[c] != 0.0) allmiss = 0.0;
+            sc[3] = allmiss;
+        }
+        GSYNC();
+        filtered_cov();
+        GSYNC();
         // predict in reverse:  P' = T Pf T' + C0,  a' = T af
         gemm4(n, n, n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
-              [&](int i, int j, double v_) { W2[i * ld + j] = v_; });
+              [&](int i, int j, double v_) { W2[i * ld + j] = v_; }, decg);
         GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return Pb[i * ld + k_] + Pb[k_ * ld + i]; }, [&](int k_, int j) { return W2[k_ * ld + j]; },
               [&](int i, int j, double v_) {
                   Tb[i * ld + j] += v_ + ab[i] * af[j];
                   gC0b[i * n + j] += Pb[i * ld + j];
-              });
+              }, decg);
         gemm4(n, n, n, [&](int i, int k_) { return Pb[i * ld + k_]; }, [&](int k_, int j) { return Tm[k_ * ld + j]; },
-              [&](int i, int j, double v_) { W1[i * ld + j] = v_; });
+              [&](int i, int j, double v_) { W1[i * ld + j] = v_; }, decg);
         GFOR(i, n) {
             double s = 0.0;
             for (int j = 0; j < n; ++j) s = fma(Tm[j * ld + i], ab[j], s);
@@ -462,7 +511,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GSYNC();
         gemm4(n, n, n, [&](int i, int k_) { return Tm[k_ * ld + i]; }, [&](int k_, int j) { return W1[k_ * ld + j]; },
-              [&](int i, int j, double v_) { Pfb[i * ld + j] = v_; });
+              [&](int i, int j, double v_) { Pfb[i * ld + j] = v_; }, decg);
         // log-likelihood term
         GFOR(idx, p * p) {
             const int c = idx / p, b = idx - c * p;
@@ -476,18 +525,19 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         GSYNC();
         // update in reverse (all O(n^2 p))
         GFOR(idx, n * p) {
-            const int i = idx / p, c = idx - i * p;
+            const int i = decp[idx] >> 16, c = decp[idx] & 0xffff;
             double s1 = 0.0, s2 = 0.0;
             for (int j = 0; j < n; ++j) {
-                s1 = fma(Pfb[i * ld + j], Nn[j * ps + c], s1);
-                s2 = fma(Pfb[j * ld + i], K[j * ps + c], s2);
+                const double kj = K[j * ps + c];
+                s1 = fma(Pfb[i * ld + j], fma(jit, kj, PZ[j * ps + c]), s1);
+                s2 = fma(Pfb[j * ld + i], kj, s2);
             }
             PZb[i * ps + c] = -s2;                                  // N_bar
             Kb[i * ps + c] = fma(afb[i], v[c], -fma(jit, s2, s1));  // -Pf_bar N + j N_bar + af_bar v'
         }
         GSYNC();
         GFOR(idx, n * p) {  // G = K_bar F^-1
-            const int i = idx / p, c = idx - i * p;
+            const int i = decp[idx] >> 16, c = decp[idx] & 0xffff;
             double s = 0.0;
             for (int b = 0; b < p; ++b) s = fma(Kb[i * ps + b], F[b * ps + c], s);
             G1[i * ps + c] = s;
@@ -501,7 +551,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GSYNC();
         GFOR(idx, n * p) {  // PZ_bar = N_bar + G + Zm' F_bar
-            const int i = idx / p, b = idx - i * p;
+            const int i = decp[idx] >> 16, b = decp[idx] & 0xffff;
             double s = PZb[i * ps + b] + G1[i * ps + b];
             for (int c = 0; c < p; ++c) s = fma(w[c] * Zs[c * n + i], 0.5 * (Fb[c * ps + b] + Fb[b * ps + c]), s);
             PZb[i * ps + b] = s;
@@ -512,7 +562,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         }
         GSYNC();
         GFOR(idx, n * n) {  // P_bar = Pf_bar + PZ_bar Zm
-            const int i = idx / n, j = idx - i * n;
+            const int i = dec[idx] >> 16, j = dec[idx] & 0xffff;
             double s = Pfb[i * ld + j];
             for (int c = 0; c < p; ++c) s = fma(PZb[i * ps + c] * w[c], Zs[c * n + j], s);
             Pb[i * ld + j] = s;

@@ -13,7 +13,7 @@
 extern "C" int gecon_kalman_grad_hostcheck(const gecon_kalman_grad_args* a) {
     gecon_grad::KalmanGradArgs g = gecon_grad::to_internal(*a);
     std::vector<double> sm(gecon_grad::kalman_grad_smem_doubles(g.n, g.k, g.p, 1));
-    std::vector<double> traj((size_t)g.Tobs * (g.n * g.n + g.n) + 1), c0b(2 * (size_t)g.n * g.n);
+    std::vector<double> traj((size_t)g.Tobs * gecon_grad::kalman_grad_traj_stride(g.n, g.p) + 1), c0b(2 * (size_t)g.n * g.n);
     g.traj = traj.data();
     g.c0bar_ws = c0b.data();
     for (long long i = 0; i < g.N; ++i) gecon_grad::kalman_grad_draw(g, i, 0, sm.data());
