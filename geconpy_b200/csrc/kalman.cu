@@ -2,6 +2,7 @@
 // (kalman.cuh) is instantiated in kalman_inst.cu, compiled once per padded dimension NP (build.py) so that the
 // 7 x 8 (NP, p) instantiations build in parallel.
 #include "kalman.cuh"
+#include "kalman_thread.cuh"
 
 namespace gecon {
 
@@ -90,7 +91,26 @@ static int warp_kernel_np(const gecon_kalman_args& a) {
     return np <= 32 ? np : 0;
 }
 
+// one thread per draw (kalman_thread.cuh): selector Z, diagonal Q, filter dimension <= 4, p <= 2 (GECON_KF_THREAD=0 disables it)
+static int launch_kf_thread(const gecon_kalman_args& a, cudaStream_t st, int* info, bool* taken) {
+    static const bool enabled = !(getenv("GECON_KF_THREAD") && atoi(getenv("GECON_KF_THREAD")) == 0);
+    *taken = enabled && a.obs_idx && !a.Z && !a.qfull && a.qdiag && a.n >= 1 && a.n <= 4 && a.p >= 1 && a.p <= 2 && a.p <= a.n;
+    if (!*taken) return 0;
+#define GECON_KT_CASE(U_, P_) \
+    if (a.n == U_ && a.p == P_) return launch_kalman_thread<U_, P_>(a, st, info);
+    GECON_KT_CASE(1, 1) GECON_KT_CASE(2, 1) GECON_KT_CASE(3, 1) GECON_KT_CASE(4, 1)
+    GECON_KT_CASE(2, 2) GECON_KT_CASE(3, 2) GECON_KT_CASE(4, 2)
+#undef GECON_KT_CASE
+    *taken = false;
+    return 0;
+}
+
 static int launch_kf(int np, const gecon_kalman_args& a, cudaStream_t st, int* info) {
+    {
+        bool taken = false;
+        const int rc = launch_kf_thread(a, st, info, &taken);
+        if (taken) return rc;
+    }
     switch (warp_kernel_np(a)) {
         case 8: return launch_kw_8(a, st, info);
         case 16: return launch_kw_16(a, st, info);

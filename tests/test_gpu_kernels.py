@@ -277,7 +277,7 @@ def test_kalman_missing_data_no_measurement_error_and_intercept(B):
             assert abs(ll2[i] - ref2) <= TOL_LL, (i, ll2[i], ref2)
 
 
-@pytest.mark.parametrize("n,p", [(10, 3), (30, 4)])  # one warp per draw / one CTA per draw
+@pytest.mark.parametrize("n,p", [(3, 2), (10, 3), (40, 4)])  # one thread per draw / one warp per draw / one CTA per draw
 @pytest.mark.parametrize("mask_intercept", [False, True])
 def test_kalman_intercept_meets_missing_data(B, rng, n, p, mask_intercept):
     """a non-zero observation intercept together with missing entries, in both conventions
@@ -320,11 +320,13 @@ def _random_statespace(rng, N, n, k, rho=0.9):
     return T, R
 
 
-@pytest.mark.parametrize("n,k,p", [(1, 1, 1), (3, 2, 1), (5, 3, 2), (7, 2, 4), (12, 4, 3), (15, 6, 5), (15, 16, 8), (20, 7, 7), (23, 9, 6), (23, 3, 8),
+@pytest.mark.parametrize("n,k,p", [(1, 1, 1), (3, 2, 1), (2, 1, 1), (2, 3, 2), (3, 1, 2), (4, 2, 1), (4, 5, 2),  # one thread per draw (n <= 4, p <= 2)
+                                    (5, 3, 2), (7, 2, 4), (12, 4, 3), (15, 6, 5), (15, 16, 8), (20, 7, 7), (23, 9, 6), (23, 3, 8),
                                     (9, 2, 1), (9, 4, 5), (10, 4, 3), (10, 3, 8), (11, 5, 2), (11, 2, 7),  # fringe variant of the warp kernel
                                     (24, 5, 2), (40, 8, 8), (60, 10, 7), (63, 4, 3)])
 def test_kalman_synthetic_sizes(B, rng, n, k, p):
-    """Both filter kernels over their whole size range (one warp per draw up to n = 23, one CTA per draw above), every
+    """The three filter kernels over their whole size range (one thread per draw up to n = 4 and p = 2, one warp per draw up to n = 31,
+    one CTA per draw above), every
     number of observables, with measurement error, missing data, an intercept and per-step output."""
     N, Tobs = 4, 45
     T, R = _random_statespace(rng, N, n, k)
