@@ -124,6 +124,28 @@ def build_model(name: str, source: str, force: bool = False) -> Path:
     return lib
 
 
+def build_grad_spec(n: int, k: int, p: int, force: bool = False) -> Path:
+    """The Kalman adjoint kernel compiled for ONE (filter dimension, shocks, observables) triple (csrc/grad_spec.cu): same source as
+    the generic kernel, dimensions as compile-time constants.  Cached by dimensions + source digest next to the model libraries."""
+    deps = [CSRC / f for f in ("grad_spec.cu", "grad.cuh", "grad_args.h", "common.cuh")] + [PKG.parent / "include" / "gecon_b200.h"]
+    dig = _digest(deps, NVCC_FLAGS)[:16]
+    MODEL_LIBDIR.mkdir(parents=True, exist_ok=True)
+    lib = MODEL_LIBDIR / f"libgecon_grad_n{n}_k{k}_p{p}_{dig}.so"
+    if lib.exists() and not force:
+        return lib
+    build_core()
+    tmp_lib = lib.with_name(lib.name + f".{os.getpid()}.tmp")
+    try:
+        link = ["-L", str(LIBDIR), "-lgecon_b200", "-Xlinker", "-rpath=$ORIGIN/.."]
+        _run([find_nvcc(), *NVCC_FLAGS, "-shared", f"-DGECON_GRAD_CN={n}", f"-DGECON_GRAD_CK={k}", f"-DGECON_GRAD_CP={p}", "-o", str(tmp_lib),
+              str(CSRC / "grad_spec.cu"), *link, "-lcudart"])
+        os.replace(tmp_lib, lib)
+    finally:
+        if tmp_lib.exists():
+            tmp_lib.unlink()
+    return lib
+
+
 if __name__ == "__main__":
     import sys
 

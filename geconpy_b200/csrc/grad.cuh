@@ -188,7 +188,12 @@ GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
 // rounding-level antisymmetry of P_bar by the same mechanism (measured on the medium NK model with error variances 1e-6:
 // gradient wrong in the first digit after 50 steps; with the two symmetrisations it agrees with the Joseph-form adjoint to 1e-12).
 GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, double* sm) {
+#ifdef GECON_GRAD_CN  // per-configuration build (grad_spec.cu): the dimensions are compile-time, every loop below unrolls
+    constexpr int n = GECON_GRAD_CN, k = GECON_GRAD_CK, p = GECON_GRAD_CP, ld = GECON_GRAD_CN | 1;
+    const int Tobs = g.Tobs;
+#else
     const int n = g.n, k = g.k, p = g.p, Tobs = g.Tobs, ld = ldim(n);
+#endif
     const int tile = n * ld;
     double* Tm = sm;
     double* P = Tm + tile;

@@ -461,79 +461,81 @@ class BatchedStateSpace:
             events.append((name, e0, e1))
             return e1
 
-        for ci, lo in enumerate(range(0, N, nc)):
-            cnt = min(nc, N - lo)
-            th = theta_full[lo : lo + cnt]
-            slot = ci % len(streams)
-            ws = self._workspace(dev, nc, slot)
-            torch.cuda.set_stream(streams[slot])
-            stream = streams[slot].cuda_stream
-            # split the parameter vector (strided device copies; no arithmetic)
-            ws["theta"][:cnt].copy_(th[:, : m.n_theta])
-            if self.full_covariance:
-                ws["Q"][:cnt].copy_(th[:, m.n_theta : m.n_theta + self._n_cov].reshape(cnt, m.k, m.k))
-            else:
-                ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
-            if n_err:
-                ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + self._n_cov :])
-            st = ws["status"][:cnt]
-            e = mark("jacobian")
-            m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
-            e and e.record()
-            if self.ss_obs_intercept:  # d = log x_ss / x_ss of the listed observed states (x aggregation period for "sum")
-                xs = ws["xss"][:cnt].index_select(1, ws["d_var"])
-                ws["d"][:cnt].index_copy_(1, ws["d_pos"], torch.where(ws["d_loglin"], xs.log(), xs) * ws["d_scale"])
-            if self._obs_lib is not None:
-                rc = self._obs_lib.gecon_obs_batched(ws["theta"].data_ptr(), cnt, ws["Z"].data_ptr(), self.p * self.n_aug,
-                                                     ws["d"].data_ptr(), self.p, C.c_void_p(stream))  # fmt: skip
-                m.launches += 1
-                if rc != 0:
-                    raise L.GeconLibraryError(f"gecon_obs_batched failed with CUDA error {rc}")
-            cr = L.CrArgs(
-                struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(),
-                C=(None if self.solver == "backward_direct" else ws["C"].data_ptr()), scan_semantics=int(self.solver == "scan_cycle_reduction"),
-                D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
-                resid_tol=self.solver_tol, unperm=ws["subset"].data_ptr(), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
-                status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
-                n_out=self.n_filter, n_lead=(int(ws["lead"].numel()) if self.check_bk else 0),
-                lead_idx=(ws["lead"].data_ptr() if self.check_bk else None), n_unstable=ws["n_unstable"].data_ptr(),
-                t_stride=self.n_aug * self.n_aug, r_stride=self.n_aug * m.k, t_ld=self.n_aug,
-                lag_lo=m.col_ranges[0], lag_hi=m.col_ranges[1], lead_lo=m.col_ranges[2], lead_hi=m.col_ranges[3],
-            )  # fmt: skip
-            e = mark("cr_solve")
-            L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
-            e and e.record()
-            if self.check_bk:
-                bk = L.BkArgs(
-                    struct_size=C.sizeof(L.BkArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(), N=cnt,
-                    n=m.n, n_lead=int(ws["lead"].numel()), lead_idx=ws["lead"].data_ptr(), accumulate=1, max_iter=0,
-                    n_unstable=ws["n_unstable"].data_ptr(), status=st.data_ptr(),
-                    skip_mask=L.ST_BK_CERTIFIED | L.ST_JAC_NONFINITE,
-                )  # fmt: skip
-                e = mark("bk_count")
-                L.check(lib.gecon_bk_count_batched(C.byref(bk), C.c_void_p(stream)), "gecon_bk_count_batched")
+        try:  # the current torch stream is restored even if a launch raises
+            for ci, lo in enumerate(range(0, N, nc)):
+                cnt = min(nc, N - lo)
+                th = theta_full[lo : lo + cnt]
+                slot = ci % len(streams)
+                ws = self._workspace(dev, nc, slot)
+                torch.cuda.set_stream(streams[slot])
+                stream = streams[slot].cuda_stream
+                # split the parameter vector (strided device copies; no arithmetic)
+                ws["theta"][:cnt].copy_(th[:, : m.n_theta])
+                if self.full_covariance:
+                    ws["Q"][:cnt].copy_(th[:, m.n_theta : m.n_theta + self._n_cov].reshape(cnt, m.k, m.k))
+                else:
+                    ws["sig"][:cnt].copy_(th[:, m.n_theta : m.n_theta + m.k])
+                if n_err:
+                    ws["herr"][:cnt].index_copy_(1, ws["err_pos"], th[:, m.n_theta + self._n_cov :])
+                st = ws["status"][:cnt]
+                e = mark("jacobian")
+                m.jacobian_device(ws["theta"][:cnt], ws["A"], ws["B"], ws["C"], ws["D"], ws.get("xss"), st, stream)
                 e and e.record()
-            kf = L.KalmanArgs(
-                struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
-                qdiag=(None if self.full_covariance else ws["sig"].data_ptr()), q_stride=m.k,
-                qfull=(ws["Q"].data_ptr() if self.full_covariance else None), qfull_stride=m.k * m.k,
-                hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
-                Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None),
-                z_stride=(self.p * self.n_aug if self._obs_lib is not None else 0),
-                obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
-                d=(ws["d"].data_ptr() if "d" in ws else None), d_stride=(self.p if "d" in ws else 0),
-                Y=Y.data_ptr(), P0=None, N=cnt, n=self.n_aug, k=m.k, p=self.p,
-                Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
-                mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
-                gate_mask=self.gate_mask, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),
-                ll_t=None, mask_intercept=int(self.mask_intercept),
-            )  # fmt: skip
-            e = mark("kalman_ll")
-            L.check(lib.gecon_kalman_ll_batched(C.byref(kf), C.c_void_p(stream)), "gecon_kalman_ll_batched")
-            e and e.record()
-            if out_n_iter is not None:
-                out_n_iter[lo : lo + cnt].copy_(ws["n_iter"][:cnt])
-        torch.cuda.set_stream(cur)
+                if self.ss_obs_intercept:  # d = log x_ss / x_ss of the listed observed states (x aggregation period for "sum")
+                    xs = ws["xss"][:cnt].index_select(1, ws["d_var"])
+                    ws["d"][:cnt].index_copy_(1, ws["d_pos"], torch.where(ws["d_loglin"], xs.log(), xs) * ws["d_scale"])
+                if self._obs_lib is not None:
+                    rc = self._obs_lib.gecon_obs_batched(ws["theta"].data_ptr(), cnt, ws["Z"].data_ptr(), self.p * self.n_aug,
+                                                         ws["d"].data_ptr(), self.p, C.c_void_p(stream))  # fmt: skip
+                    m.launches += 1
+                    if rc != 0:
+                        raise L.GeconLibraryError(f"gecon_obs_batched failed with CUDA error {rc}")
+                cr = L.CrArgs(
+                    struct_size=C.sizeof(L.CrArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(),
+                    C=(None if self.solver == "backward_direct" else ws["C"].data_ptr()), scan_semantics=int(self.solver == "scan_cycle_reduction"),
+                    D=ws["D"].data_ptr(), N=cnt, n=m.n, k=m.k, max_iter=self.max_iter, accumulate=1, tol=self.tol,
+                    resid_tol=self.solver_tol, unperm=ws["subset"].data_ptr(), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
+                    status=st.data_ptr(), n_iter=ws["n_iter"].data_ptr(), resid=ws["resid"].data_ptr(), norms=None,
+                    n_out=self.n_filter, n_lead=(int(ws["lead"].numel()) if self.check_bk else 0),
+                    lead_idx=(ws["lead"].data_ptr() if self.check_bk else None), n_unstable=ws["n_unstable"].data_ptr(),
+                    t_stride=self.n_aug * self.n_aug, r_stride=self.n_aug * m.k, t_ld=self.n_aug,
+                    lag_lo=m.col_ranges[0], lag_hi=m.col_ranges[1], lead_lo=m.col_ranges[2], lead_hi=m.col_ranges[3],
+                )  # fmt: skip
+                e = mark("cr_solve")
+                L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
+                e and e.record()
+                if self.check_bk:
+                    bk = L.BkArgs(
+                        struct_size=C.sizeof(L.BkArgs), A=ws["A"].data_ptr(), B=ws["B"].data_ptr(), C=ws["C"].data_ptr(), N=cnt,
+                        n=m.n, n_lead=int(ws["lead"].numel()), lead_idx=ws["lead"].data_ptr(), accumulate=1, max_iter=0,
+                        n_unstable=ws["n_unstable"].data_ptr(), status=st.data_ptr(),
+                        skip_mask=L.ST_BK_CERTIFIED | L.ST_JAC_NONFINITE,
+                    )  # fmt: skip
+                    e = mark("bk_count")
+                    L.check(lib.gecon_bk_count_batched(C.byref(bk), C.c_void_p(stream)), "gecon_bk_count_batched")
+                    e and e.record()
+                kf = L.KalmanArgs(
+                    struct_size=C.sizeof(L.KalmanArgs), T=ws["T"].data_ptr(), R=ws["R"].data_ptr(),
+                    qdiag=(None if self.full_covariance else ws["sig"].data_ptr()), q_stride=m.k,
+                    qfull=(ws["Q"].data_ptr() if self.full_covariance else None), qfull_stride=m.k * m.k,
+                    hdiag=ws["herr"].data_ptr() if n_err else None, h_stride=self.p,
+                    Z=(ws["Z"].data_ptr() if self.dense_Z is not None else None),
+                    z_stride=(self.p * self.n_aug if self._obs_lib is not None else 0),
+                    obs_idx=(ws["obs"].data_ptr() if self.dense_Z is None else None),
+                    d=(ws["d"].data_ptr() if "d" in ws else None), d_stride=(self.p if "d" in ws else 0),
+                    Y=Y.data_ptr(), P0=None, N=cnt, n=self.n_aug, k=m.k, p=self.p,
+                    Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
+                    mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
+                    gate_mask=self.gate_mask, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),
+                    ll_t=None, mask_intercept=int(self.mask_intercept),
+                )  # fmt: skip
+                e = mark("kalman_ll")
+                L.check(lib.gecon_kalman_ll_batched(C.byref(kf), C.c_void_p(stream)), "gecon_kalman_ll_batched")
+                e and e.record()
+                if out_n_iter is not None:
+                    out_n_iter[lo : lo + cnt].copy_(ws["n_iter"][:cnt])
+        finally:
+            torch.cuda.set_stream(cur)
         if n_streams > 1:
             for s_ in streams:
                 done = torch.cuda.Event()
@@ -575,6 +577,26 @@ class BatchedStateSpace:
         return ll, status
 
     # ------------------------------------------------------------------------------------------------ gradient
+    def _grad_spec_lib(self):
+        """The Kalman adjoint kernel built for this configuration's (filter dimension, shocks, observables) -- ``build.build_grad_spec``,
+        cached on disk like the generated model kernels -- or None when ``GECON_GRAD_SPEC=0`` (then the generic kernel of the core
+        library runs: same source, run-time dimensions)."""
+        import os
+
+        if os.environ.get("GECON_GRAD_SPEC", "1") == "0":
+            return None
+        key = (self.n_aug, self.model.k, self.p)
+        cache = self.__dict__.setdefault("_grad_spec_cache", {})
+        if key not in cache:
+            from .. import build
+
+            L.load_library()
+            lib = C.CDLL(str(build.build_grad_spec(*key)))
+            lib.gecon_kalman_grad_spec.restype = C.c_int
+            lib.gecon_kalman_grad_spec.argtypes = [C.POINTER(L.KalmanGradArgs), C.c_void_p]
+            cache[key] = lib
+        return cache[key]
+
     def loglik_and_grad_device(self, theta_full, Y, events=None):
         """theta_full [N, n_param] (CUDA) -> (ll [N], grad [N, n_param], status [N]): the log-likelihood and its gradient
         with respect to every entry of the parameter vector (free parameters, sigma_<shock>, error_sigma_<state>) --
@@ -689,7 +711,12 @@ class BatchedStateSpace:
                 mask_intercept=int(self.mask_intercept),
             )  # fmt: skip
             e = mark("kalman_grad")
-            L.check(lib.gecon_kalman_grad_batched(C.byref(kg), C.c_void_p(stream)), "gecon_kalman_grad_batched")
+            spec = self._grad_spec_lib()
+            if spec is not None:  # the same kernel source compiled for this configuration's (n, k, p): csrc/grad_spec.cu
+                L.check(spec.gecon_kalman_grad_spec(C.byref(kg), C.c_void_p(stream)), "gecon_kalman_grad_spec")
+                m.launches += 1
+            else:
+                L.check(lib.gecon_kalman_grad_batched(C.byref(kg), C.c_void_p(stream)), "gecon_kalman_grad_batched")
             e and e.record()
             # scatter the filter-block adjoints back into solver order (the augmentation rows are constants)
             Tb, Rb = g["Tb"][:cnt], g["Rb"][:cnt]
