@@ -225,3 +225,41 @@ def test_strided_solver_outputs_are_validated():
     assert lib.gecon_cr_solve_host(C.byref(a)) == -1  # strided outputs are a device-entry-point feature
     kf = _lib.KalmanArgs(struct_size=C.sizeof(_lib.KalmanArgs), T=1, R=1, qdiag=1, Y=1, ll=1, status=1, Z=1, N=1, n=4, k=1, p=2, Tobs=1, z_stride=5)
     assert lib.gecon_kalman_ll_batched(C.byref(kf), None) == -1 and b"z_stride" in lib.gecon_get_last_error()
+
+
+def test_grad_spec_source_compiles_for_any_dimensions_and_exports_its_entry_points(tmp_path):
+    """csrc/grad_spec.cu (the per-configuration build of the Kalman adjoint kernel) cross-compiles for sm_100a with arbitrary
+    compile-time (n, k, p), links against the core library and exports both entry points; its dimension check is a loud error."""
+    import ctypes as C
+
+    from geconpy_b200 import _lib as L
+    from geconpy_b200.build import build_grad_spec
+
+    lib = C.CDLL(str(build_grad_spec(5, 2, 2)))
+    nkp = (C.c_int32 * 3)()
+    assert lib.gecon_kalman_grad_spec_dims(nkp) == 0 and list(nkp) == [5, 2, 2]
+    lib.gecon_kalman_grad_spec.argtypes = [C.POINTER(L.KalmanGradArgs), C.c_void_p]
+    a = L.KalmanGradArgs(struct_size=C.sizeof(L.KalmanGradArgs), n=6, k=2, p=2)
+    assert lib.gecon_kalman_grad_spec(C.byref(a), None) == -1  # GECON_E_BADARG
+    assert b"built for (n, k, p) = (5, 2, 2)" in L.load_library().gecon_get_last_error()
+    a = L.KalmanGradArgs(struct_size=C.sizeof(L.KalmanGradArgs) - 8, n=5, k=2, p=2)
+    assert lib.gecon_kalman_grad_spec(C.byref(a), None) == -1  # GECON_E_BADARG
+
+
+def test_posterior_helpers_validate_their_arguments_before_touching_the_device():
+    from types import SimpleNamespace
+
+    from geconpy_b200.model import posterior
+
+    ss = SimpleNamespace(configured=False)
+    with pytest.raises(RuntimeError, match="configure"):
+        posterior.sample_autocorrelation_matrices(ss, np.zeros((1, 3)))
+    with pytest.raises(RuntimeError, match="configure"):
+        posterior.data_from_prior(ss)
+    ss = SimpleNamespace(configured=True)
+    with pytest.raises(ValueError, match="n_lags"):
+        posterior.sample_autocorrelation_matrices(ss, np.zeros((1, 3)), n_lags=-1)
+    with pytest.raises(ValueError, match="lag_step"):
+        posterior.sample_autocorrelation_matrices(ss, np.zeros((1, 3)), lag_step=0)
+    with pytest.raises(ValueError, match="pct_missing"):
+        posterior.data_from_prior(ss, pct_missing=1.0)
