@@ -738,8 +738,8 @@ def main():
                           "roofline": {k_: ro["roofline"][k_] for k_ in ("kernel", "achieved", "peak", "frac", "kernel_ms_per_step", "per_kernel",
                                                                          "mean_cr_iterations_all")},
                           "draw_outcomes": ro["draw_outcomes"]}
-            if nm == "nk_wide":
-                others[nm]["parity_spot_check"] = parity_spot_check(wo, 96)
+            # parity at each workload's own size: draws of THIS run against the CPU restatement (|ll - oracle| <= 1e-7, same gating)
+            others[nm]["parity_spot_check"] = parity_spot_check(wo, {"rbc": 32, "large": 16, "large45": 12, "nk_wide": 96}[nm])
             del wo
             torch.cuda.empty_cache()
         extras["workloads"] = others
