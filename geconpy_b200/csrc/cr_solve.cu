@@ -26,12 +26,20 @@ __device__ __forceinline__ void acc_sub(Acc<NP>& a, const Acc<NP>& b) {
 // strip) lives in an L2-resident global workspace, one tile per CTA, allocated stream-ordered by the launcher.
 template <int NP>
 constexpr bool cr_a1h_global() {
-    return NP > 56;
+    return NP > 56 || NP == 48;
+}
+// NP = 48 (round 2): seven 20 KB tiles allow ONE six-warp CTA per SM; with A1hat and A2 (read as an A operand by two products, as a
+// right-hand-side source by the first block step and by one norm per iteration; written once) in the per-CTA global workspace, five
+// tiles = 100 KB and two CTAs share an SM, each hiding the other's barriers.
+template <int NP>
+constexpr bool cr_a2_global() {
+    return NP == 48;
 }
 
 template <int NP>
 struct CrSmem {
-    static constexpr int TILES = cr_a1h_global<NP>() ? 6 : 7;
+    static constexpr int TILES = 7 - (cr_a1h_global<NP>() ? 1 : 0) - (cr_a2_global<NP>() ? 1 : 0);
+    static constexpr int WS_TILES = (cr_a1h_global<NP>() ? 1 : 0) + (cr_a2_global<NP>() ? 1 : 0);
     static constexpr size_t bytes = sizeof(double) * (TILES * Cfg<NP>::TILE + 8 * NP) + sizeof(int) * (4 * NP + 8);
 };
 
@@ -39,7 +47,7 @@ struct CrSmem {
 template <int NP>
 constexpr int cr_min_ctas() {
     // (NP = 16: 8 / 10 / 12 CTAs per SM measured 4.60 / 4.53 / 4.67 ms on the RBC workload)
-    return NP <= 8 ? 16 : NP <= 16 ? 10 : NP <= 24 ? 5 : NP <= 32 ? 3 : NP <= 40 ? 2 : 1;
+    return NP <= 8 ? 16 : NP <= 16 ? 10 : NP <= 24 ? 5 : NP <= 32 ? 3 : NP <= 48 ? 2 : 1;
 }
 
 template <int NP>
@@ -50,9 +58,11 @@ __global__ void __launch_bounds__(Cfg<NP>::NT, cr_min_ctas<NP>()) cr_solve_kerne
     extern __shared__ __align__(16) double sm[];
     double* A0 = sm;
     double* A1 = A0 + C::TILE;
-    double* A2 = A1 + C::TILE;
-    double* A1h = cr_a1h_global<NP>() ? ws + (size_t)blockIdx.x * C::TILE : A2 + C::TILE;
-    double* W = A2 + (cr_a1h_global<NP>() ? 1 : 2) * C::TILE;
+    double* wsc = ws + (size_t)blockIdx.x * CrSmem<NP>::WS_TILES * C::TILE;  // this CTA's tiles in the L2-resident workspace
+    double* A2 = cr_a2_global<NP>() ? wsc + (cr_a1h_global<NP>() ? C::TILE : 0) : A1 + C::TILE;
+    double* nxt_sm = A1 + (cr_a2_global<NP>() ? 1 : 2) * C::TILE;
+    double* A1h = cr_a1h_global<NP>() ? wsc : nxt_sm;
+    double* W = nxt_sm + (cr_a1h_global<NP>() ? 0 : 1) * C::TILE;
     double* X0 = W + C::TILE;
     double* X2 = X0 + C::TILE;
     double* s_red = X2 + C::TILE;  // [8 NP]: two norm1_fast buffers
@@ -429,7 +439,7 @@ static int launch_cr(const gecon_cr_args& a, cudaStream_t st) {
     int rc = persistent_grid(cr_solve_kernel<NP>, Cfg<NP>::NT, CrSmem<NP>::bytes, a.N, &grid, nullptr, "GECON_CR_CTAS_PER_SM");
     if (rc) return rc;
     double *ws = nullptr, *scratch = nullptr;
-    if (cr_a1h_global<NP>()) GECON_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)grid * Cfg<NP>::TILE, st));
+    if (CrSmem<NP>::WS_TILES > 0) GECON_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)grid * CrSmem<NP>::WS_TILES * Cfg<NP>::TILE, st));
     gecon_compact_jac cj{};
     if (a.compact) {
         cj = *a.compact;
