@@ -608,7 +608,11 @@ def parity_spot_check(w: Workload, n_pick=48):
     ll_cpu = np.array([_oracle_eval((w.wl["model"], w.theta[i], np.full(w.k, SIGMA_SHOCK), herr_full if w.wl["meas"] else np.zeros(0),
                                     w.wl["observed"], w.Y)) for i in pick])
     both = np.isfinite(ll_gpu) & np.isfinite(ll_cpu)
-    return {"draws": int(pick.size), "finite_on_both": int(both.sum()), "flags_agree": bool((np.isfinite(ll_gpu) == np.isfinite(ll_cpu)).all()),
+    n_dis = int((np.isfinite(ll_gpu) != np.isfinite(ll_cpu)).sum())
+    return {"draws": int(pick.size), "finite_on_both": int(both.sum()), "flags_agree": n_dis == 0, "gate_disagreements": n_dis,
+            "note": ("a wide prior produces draws on which the reference's own Blanchard-Kahn count is a numerical artefact (eigenvalues within its "
+                     "LAPACK error of the unit circle, counts that change under its own 1e-8 regularisation): classified and bounded in "
+                     "tests/test_gpu_pipeline.py::test_wide_prior_population_failure_classes_at_scale") if w.name == "nk_wide" else None,
             "max_abs_ll_error": float(np.abs(ll_gpu[both] - ll_cpu[both]).max()) if both.any() else None, "tolerance": 1e-7}
 
 

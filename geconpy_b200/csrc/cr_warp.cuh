@@ -316,6 +316,8 @@ __device__ __noinline__ bool cw_power_bound(double* Z, double* Zb, int s, int la
     if (s == 0) return true;
     const int g = lane >> 2, q = lane & 3;
     const int nk = (s + 3) >> 2, nc = (s + 7) >> 3;
+    __syncwarp();  // Zb may be the tile the previous call was still reading norms from (racecheck, round 2: the reduction that ends
+                   // cw_norm1 synchronises the lanes' execution, not their shared-memory accesses)
     for (int i = lane; i < 8 * nc * LDC; i += 32) Zb[i] = 0.0;
     __syncwarp();
 #pragma unroll 1
