@@ -356,7 +356,12 @@ __device__ __noinline__ bool cw_power_bound(double* Z, double* Zb, int s, int la
 template <int NP, int C, int WPC>
 constexpr int cw_min_ctas() {
     const int by_smem = (int)((227 * 1024) / (CwCfg<NP, C>::bytes(WPC) + 1024));
-    const int cap = 16 / WPC > 0 ? 16 / WPC : 1;  // 16 warps of 128 registers fill the register file
+#ifndef GECON_CW_WARPS16
+#define GECON_CW_WARPS16 16  // resident warps per SM the register allocator is held to at NP <= 16.  Measured on the RBC workload (n = 9,
+                             // 65,536 draws): 16 warps (128 registers) 2.47 ms, 20 (96, spills) 2.60 ms, 24 (80, spills) 2.49 ms: not warp-count bound
+#endif
+    const int warps = NP <= 16 ? GECON_CW_WARPS16 : 16;  // 16 warps of 128 registers fill the register file
+    const int cap = warps / WPC > 0 ? warps / WPC : 1;
     return by_smem < 1 ? 1 : (by_smem > cap ? cap : by_smem);
 }
 
