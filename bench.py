@@ -744,6 +744,16 @@ def main():
                           "draw_outcomes": ro["draw_outcomes"]}
             # parity at each workload's own size: draws of THIS run against the CPU restatement (|ll - oracle| <= 1e-7, same gating)
             others[nm]["parity_spot_check"] = parity_spot_check(wo, {"rbc": 32, "large": 16, "large45": 12, "nk_wide": 96}[nm])
+            if nm == "nk_wide":
+                # the same population with the Blanchard-Kahn count restricted to the draws the gate has not rejected yet
+                # (configure(bk_on_rejected_draws=False) -> gecon_pipeline_args.check_bk = 2): identical log-likelihoods, what a sampler needs
+                ll_exact = wo.ll_d.clone()
+                wo.ss.configure(observed_states=wo.wl["observed"], measurement_error=wo.wl["meas"], tol=1e-8, max_iter=wo.max_iter,
+                                bk_on_rejected_draws=False)
+                rg = time_workload(wo, 3, 3, 1, flush, peak, with_e2e=False)
+                others[nm]["gate_only_bk"] = {"value": rg["value"], "unit": UNIT, "ms_per_step": rg["ms_per_step"],
+                                              "kernel_ms_per_step": rg["roofline"]["kernel_ms_per_step"],
+                                              "ll_identical": bool(torch.equal(torch.nan_to_num(ll_exact, neginf=-1e300), torch.nan_to_num(wo.ll_d, neginf=-1e300)))}
             del wo
             torch.cuda.empty_cache()
         extras["workloads"] = others

@@ -197,7 +197,11 @@ extern "C" int gecon_loglik_pipeline(const gecon_pipeline_args* a, void* stream)
             bk.accumulate = 1;
             bk.n_unstable = d_nu;
             bk.status = d_st;
-            bk.skip_mask = GECON_ST_BK_CERTIFIED | GECON_ST_JAC_NONFINITE;
+            // check_bk == 2 ("gate only"): a draw the gate already rejects (no convergence, residual, ...) is not counted -- its
+            // log-likelihood is -inf either way, only its Blanchard-Kahn BIT stays unset.  On a population where half the draws
+            // fail the count is most of the step; samplers that only consume the gate ask for this.
+            bk.skip_mask = GECON_ST_BK_CERTIFIED | GECON_ST_JAC_NONFINITE |
+                           (a->check_bk == 2 ? (a->gate_mask & ~(GECON_ST_BK | GECON_ST_BK_INCONCLUSIVE)) : 0);
             bk.compact = &cj;
             tm.begin(2);
             rc = gecon_bk_count_batched(&bk, stream);

@@ -166,6 +166,7 @@ class BatchedStateSpace:
         missing_fill_value: float = -9999.0,
         mvn_const: str = "per_obs",
         check_bk: bool = True,
+        bk_on_rejected_draws: bool = True,
         chunk: int = 65536,
         reduce_state: bool = True,
         n_streams: int | None = None,
@@ -209,7 +210,9 @@ class BatchedStateSpace:
         ``build_statespace_graph`` (statespace.py:1206-1215).  The reference defaults both to False; here both default to
         True because a population of prior draws always contains draws the solver rejects -- pass False, False to reproduce
         the reference's default graph (non-finite steady states and failed solves are gated either way: their logp is NaN in
-        the reference, -inf here).  ``check_bk`` is the older name of ``add_bk_check``."""
+        the reference, -inf here).  ``check_bk`` is the older name of ``add_bk_check``.  ``bk_on_rejected_draws=False`` (fused path only):
+        draws the gate already rejects for another reason are not Blanchard-Kahn-counted -- same log-likelihoods, their BK status bit
+        stays unset; on a population where half the draws fail the count is most of the step, and a sampler only consumes the gate."""
         m = self.model
         if solver not in ("cycle_reduction", "gensys", "scan_cycle_reduction", "backward_direct"):
             raise NotImplementedError(f"solver={solver!r}: expected cycle_reduction, gensys, scan_cycle_reduction or backward_direct")
@@ -320,6 +323,7 @@ class BatchedStateSpace:
         self.tol, self.max_iter, self.solver_tol = float(tol), int(max_iter), float(solver_tol)
         self.cov_jitter, self.missing_fill_value, self.mvn_const = float(cov_jitter), float(missing_fill_value), mvn_const
         self.check_bk = bool(check_bk)
+        self.bk_on_rejected_draws = bool(bk_on_rejected_draws)
         self.chunk = int(os.environ.get("GECON_CHUNK", chunk))
         self.full_covariance = bool(full_shock_covariance)
         self.mask_intercept = bool(mask_intercept)
@@ -560,7 +564,7 @@ class BatchedStateSpace:
             theta_stride=theta_full.shape[1], N=theta_full.shape[0], Y=Y.data_ptr(), Tobs=Y.shape[0], max_iter=self.max_iter, tol=self.tol,
             solver_tol=self.solver_tol, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
             mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), mask_intercept=int(self.mask_intercept), gate_mask=self.gate_mask,
-            check_bk=int(self.check_bk and lead.size > 0), scan_semantics=int(self.solver == "scan_cycle_reduction"),
+            check_bk=(int(self.check_bk and lead.size > 0) * (1 if self.bk_on_rejected_draws else 2)), scan_semantics=int(self.solver == "scan_cycle_reduction"),
             timing=int(events is not None), chunk=self.chunk, ll=ll.data_ptr(), status=status.data_ptr(),
             n_iter=(out_n_iter.data_ptr() if out_n_iter is not None else None),
         )  # fmt: skip

@@ -431,7 +431,8 @@ typedef struct gecon_pipeline_args {
     int32_t mvn_const_mode;
     int32_t mask_intercept;
     int32_t gate_mask;
-    int32_t check_bk;
+    int32_t check_bk;         /* 0: no Blanchard-Kahn check; 1: count every uncertified draw (status bits as the reference's); 2: "gate only" --
+                                 draws that gate_mask already rejects are not counted (same ll, their BK bit stays unset) */
     int32_t scan_semantics;
     int32_t timing;           /* != 0: CUDA events around every kernel; gecon_pipeline_stage_ms then returns the per-stage totals of
                                  the calling thread's last call (jacobian, cr_solve, bk_count, kalman_ll).  Synchronises the stream */

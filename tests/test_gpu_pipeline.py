@@ -320,3 +320,37 @@ def test_wide_prior_population_failure_classes_at_scale(compiled):
     # measured (640 draws): borderline_bk 15, regularisation_bk 9, overflow_scale 10, lyapunov 3, declined 0, no other disagreement
     assert accepted["borderline_bk"] <= pick.size // 20 and accepted["regularisation_bk"] <= pick.size // 30, accepted
     assert accepted["overflow_scale"] <= pick.size // 30 and accepted["lyapunov"] <= pick.size // 60 and n_declined <= pick.size // 50, (accepted, n_declined)
+
+
+def test_gate_only_blanchard_kahn_skips_rejected_draws_without_changing_the_likelihood(compiled):
+    """configure(bk_on_rejected_draws=False) -> gecon_pipeline_args.check_bk = 2: identical log-likelihoods and gating on a population
+    with every failure class; the status words differ only in the Blanchard-Kahn bits of draws that are rejected anyway."""
+    import sys
+
+    import torch
+
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    import bench
+
+    from geconpy_b200 import _lib as L
+    from geconpy_b200.model.compiled import BatchedStateSpace
+
+    wl = bench.WORKLOADS["nk_wide"]
+    cm, mod = compiled(wl["model"]), model(wl["model"])
+    N, Tobs = 8192, 60
+    kw = dict(observed_states=wl["observed"], measurement_error=wl["meas"], tol=1e-8, max_iter=wl["max_iter"])
+    full_ss = BatchedStateSpace(cm).configure(**kw)
+    gate_ss = BatchedStateSpace(cm).configure(bk_on_rejected_draws=False, **kw)
+    assert full_ss.fused and gate_ss.fused
+    theta = bench.make_draws(mod.spec, N, None, seed=5, box=wl["box"])
+    Y = simulate_obs(mod, Tobs, observed=wl["observed"], seed=3, sigma_err=SIGMA_ERR)
+    full = torch.as_tensor(np.hstack([theta, np.full((N, mod.k), SIGMA_SHOCK), np.full((N, len(wl["meas"])), SIGMA_ERR)]), device="cuda")
+    Yd = torch.as_tensor(Y, device="cuda")
+    ll_a, st_a = (x.cpu().numpy() for x in full_ss.loglik_device(full, Yd))
+    ll_b, st_b = (x.cpu().numpy() for x in gate_ss.loglik_device(full, Yd))
+    assert np.array_equal(ll_a, ll_b) and 0.2 < np.isfinite(ll_a).mean() < 0.8
+    bk_bits = L.ST_BK | L.ST_BK_INCONCLUSIVE
+    assert np.array_equal(st_a & ~bk_bits, st_b & ~bk_bits)
+    differ = st_a != st_b
+    other_gates = full_ss.gate_mask & ~bk_bits
+    assert differ.any() and ((st_a[differ] & other_gates) != 0).all() and ((st_b[differ] & bk_bits) == 0).all()
