@@ -29,8 +29,16 @@ struct BkSmem {
     static constexpr size_t bytes = sizeof(double) * (3 * Cfg<NP>::TILE + 2 * NP) + sizeof(int) * (3 * NP + 8);
 };
 
+// Resident CTAs per SM the register allocator must leave room for.  The kernel is bound by the barriers of its Gauss-Jordan solves, so
+// co-resident CTAs pay directly; shared memory (three tiles) allows 8 / 5 / 3 / 2 / 2 CTAs at NP = 32 / 40 / 48 / 56 / 64, and without a
+// bound ptxas takes 168-180 registers (2 CTAs at NP = 40).  Measured on the wide-prior population (m = 38, NP = 40): see DESIGN 3.3.
 template <int NP>
-__global__ void __launch_bounds__(Cfg<NP>::NT, 1) bk_count_kernel(const gecon_bk_args p, const gecon_compact_jac cj, double* __restrict__ scratch) {
+constexpr int bk_min_ctas() {
+    return NP <= 24 ? 1 : NP <= 40 ? 4 : NP <= 48 ? 3 : NP <= 64 ? 2 : 1;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(Cfg<NP>::NT, bk_min_ctas<NP>()) bk_count_kernel(const gecon_bk_args p, const gecon_compact_jac cj, double* __restrict__ scratch) {
     using C = Cfg<NP>;
     constexpr int LD = C::LD, NT = C::NT;
     extern __shared__ __align__(16) double sm[];
