@@ -4,7 +4,7 @@
 // gEconpy/model/statespace.py:1151-1157, restated in oracle/statespace.py): update -> jitter -> predict, Joseph-form
 // covariance update, missing observations masked, a0 = 0, P0 = dlyap(T, R Q R') by Smith doubling.
 //
-// Why a second kernel: with n <= 23 the filter step is a chain of tiny dependent phases, and in the CTA-per-draw kernel
+// Why a second kernel: with n <= 31 the filter step is a chain of tiny dependent phases, and in the CTA-per-draw kernel
 // five CTA barriers per step leave the SM idle most of the time.  Here a warp owns a draw, so the only synchronisation
 // is __syncwarp, and 16 draws per SM advance independently.  Per step:
 //   1  every lane redundantly: F = Z P Z' + H + jitter I, its L D L' factorisation, the innovation and its quadratic

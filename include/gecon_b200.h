@@ -193,6 +193,9 @@ int gecon_dlyap_host(const gecon_dlyap_args* args);
  *   x_t = T x_{t-1} + R eps_t, eps ~ N(0, diag(q));   y_t = d + Z x_t + eta_t, eta ~ N(0, diag(h)).
  * Z is either dense (p x n, shared by all draws or one per draw: z_stride) or a selector given by obs_idx
  * (Z[a][obs_idx[a]] = 1).
+ * Kernels behind it (same arithmetic; the Joseph update in its rank-p form P - K (P Z' + jitter K)'): one THREAD per draw for a
+ * selector Z with n <= 4, p <= 2; one WARP per draw for a selector Z with n <= 31 (n <= 23 when T_obs p is too large for four
+ * warps' tiles next to Y); one CTA per draw otherwise (dense Z, full shock covariance, n <= 64).  p <= 8.
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct gecon_kalman_args {
     size_t struct_size;
