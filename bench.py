@@ -768,9 +768,11 @@ def main():
         extras["strong_scaling_point"] = {"total_draws": int(ws_.n_draws * world), "draws_per_gpu": int(ws_.n_draws), "value": rs["value"], "unit": UNIT,
                                           "ms_per_step": rs["ms_per_step"], "scaling": "strong"}
     line["extras"] = extras
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
+        # parity at the benchmark's own size at every N: 48 draws of rank 0's shard of THIS run against the CPU restatement
         line["parity_spot_check"] = parity_spot_check(w)
-        line["cpu_baseline"] = cpu_arm(wl, w.Y, cores, seconds=args.cpu_seconds)
+        if world == 1:  # (the CPU baseline is timed at N = 1 only)
+            line["cpu_baseline"] = cpu_arm(wl, w.Y, cores, seconds=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
