@@ -140,6 +140,9 @@ def build_grad_spec(n: int, k: int, p: int, force: bool = False) -> Path:
         _run([find_nvcc(), *NVCC_FLAGS, "-shared", f"-DGECON_GRAD_CN={n}", f"-DGECON_GRAD_CK={k}", f"-DGECON_GRAD_CP={p}", "-o", str(tmp_lib),
               str(CSRC / "grad_spec.cu"), *link, "-lcudart"])
         os.replace(tmp_lib, lib)
+        for stale in MODEL_LIBDIR.glob(f"libgecon_grad_n{n}_k{k}_p{p}_*.so"):  # builds of older sources of the same configuration
+            if stale != lib:
+                stale.unlink(missing_ok=True)
     finally:
         if tmp_lib.exists():
             tmp_lib.unlink()

@@ -34,8 +34,18 @@
 #define GHD __device__ __forceinline__
 #define GHH __host__ __device__ __forceinline__
 #define G_TID ((int)threadIdx.x)
+#if defined(GECON_GRAD_CN) && GECON_GRAD_CN <= 12
+// per-configuration build with one warp per draw (grad_spec.cu): the CTA IS a warp -- compile-time thread count (every GFOR over a
+// compile-time extent resolves to straight-line predicated code: 8.1 k -> 4.1 k SASS instructions at n = 10), warp-level barrier
+#define G_NT 32
+#define GSYNC() __syncwarp()
+#elif defined(GECON_GRAD_CN)
+#define G_NT (GECON_GRAD_CN <= 32 ? 128 : 256)  // the thread count grad_spec.cu launches with
+#define GSYNC() __syncthreads()
+#else
 #define G_NT ((int)blockDim.x)
 #define GSYNC() __syncthreads()
+#endif
 #endif
 #define GFOR(i, count) for (int i = G_TID; i < (count); i += G_NT)
 
