@@ -117,6 +117,12 @@ def build_model(name: str, source: str, force: bool = False) -> Path:
         _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-o", str(tmp_lib), str(tmp_src), *link, "-lcudart"])
         os.replace(tmp_src, src)
         os.replace(tmp_lib, lib)
+        import re
+
+        stale = re.compile(rf"^(lib)?gecon_model_{re.escape(name)}_[0-9a-f]{{16}}\.(so|cu)$")  # builds of older sources of the same model
+        for f in MODEL_LIBDIR.iterdir():
+            if stale.match(f.name) and f not in (lib, src):
+                f.unlink(missing_ok=True)
     finally:
         for f in (tmp_src, tmp_lib):
             if f.exists():
