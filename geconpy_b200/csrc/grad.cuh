@@ -83,6 +83,65 @@ GHD void gemm4(int m, int n, int kk, FA a, FB b, FE epi, const int* tab = nullpt
     }
 }
 
+// Square product (m = n = kk = the filter dimension) of the sweeps.  Generic builds and the CPU check: the scalar gemm4 above.
+// Per-configuration builds (grad_spec.cu, compile-time n): the fp64 tensor path -- every warp accumulates whole 8-row strips of the
+// output with mma.sync.m8n8k4, all tiles of a strip (all tiles of the matrix when the CTA is one warp) at once, so the only dependent
+// chain is the k loop; operands and epilogue are the same inlined lambdas, guarded at the edges (the shared-memory tiles carry no
+// padding).  At n = 10: 12 DMMA + 12 predicated loads + 8 epilogue elements per lane instead of ~210 load / FMA / index instructions.
+// (With run-time dimensions the same idea was slower than gemm4 -- guards and loop control ate the gain)
+template <class FA, class FB, class FE>
+GHD void gemm_sq(int n_rt, FA a, FB b, FE epi, const int* tab) {
+#if defined(GECON_GRAD_CN) && !defined(GECON_HOST_CHECK)
+    (void)n_rt;
+    (void)tab;
+    constexpr int n = GECON_GRAD_CN, NSQ = (n + 7) / 8, NK = (n + 3) / 4, NWARP = G_NT / 32;
+    constexpr int SPW = NWARP == 1 ? NSQ : 1;  // strips per pass of a warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    for (int s0 = (NWARP == 1 ? 0 : warp); s0 < NSQ; s0 += (NWARP == 1 ? NSQ : NWARP)) {
+        double acc[SPW][NSQ][2];
+#pragma unroll
+        for (int s = 0; s < SPW; ++s)
+#pragma unroll
+            for (int ct = 0; ct < NSQ; ++ct) acc[s][ct][0] = acc[s][ct][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            const int kq = 4 * ks + q;
+            double av[SPW], bv[NSQ];
+#pragma unroll
+            for (int s = 0; s < SPW; ++s) {
+                const int r = 8 * (s0 + s) + g;
+                av[s] = (r < n && kq < n) ? a(r, kq) : 0.0;
+            }
+#pragma unroll
+            for (int ct = 0; ct < NSQ; ++ct) {
+                const int c = 8 * ct + g;
+                bv[ct] = (c < n && kq < n) ? b(kq, c) : 0.0;
+            }
+#pragma unroll
+            for (int s = 0; s < SPW; ++s)
+#pragma unroll
+                for (int ct = 0; ct < NSQ; ++ct)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[s][ct][0]), "+d"(acc[s][ct][1])
+                                 : "d"(av[s]), "d"(bv[ct]));
+        }
+#pragma unroll
+        for (int s = 0; s < SPW; ++s) {
+            const int r = 8 * (s0 + s) + g;
+#pragma unroll
+            for (int ct = 0; ct < NSQ; ++ct) {
+                const int oc = 8 * ct + 2 * q;
+                if (r < n && oc < n) epi(r, oc, acc[s][ct][0]);
+                if (r < n && oc + 1 < n) epi(r, oc + 1, acc[s][ct][1]);
+            }
+        }
+    }
+#else
+    gemm4(n_rt, n_rt, n_rt, a, b, epi, tab);
+#endif
+}
+
 // C (m x n, ldc) = alpha * op(A) * op(B) + beta * C;  op(A) is m x kk, op(B) is kk x n.  C must not alias A or B.
 template <bool TA, bool TB>
 GHD void mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n, int kk, double alpha, double beta) {
@@ -455,7 +514,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             sc[2] += -0.5 * (ll_const + sc[0] + quad);
         }
         GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
+        gemm_sq(n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
               [&](int i, int j, double v_) { W2[i * ld + j] = v_; }, decg);
         GFOR(i, n) {
             double s = 0.0;
@@ -463,7 +522,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             an[i] = s;
         }
         GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return W2[i * ld + k_]; }, [&](int k_, int j) { return Tm[j * ld + k_]; },
+        gemm_sq(n, [&](int i, int k_) { return W2[i * ld + k_]; }, [&](int k_, int j) { return Tm[j * ld + k_]; },
               [&](int i, int j, double v_) { P[i * ld + j] = v_ + C0[i * n + j]; }, decg);
         GFOR(i, n) a[i] = an[i];
         GSYNC();
@@ -509,15 +568,15 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         filtered_cov();
         GSYNC();
         // predict in reverse:  P' = T Pf T' + C0,  a' = T af
-        gemm4(n, n, n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
+        gemm_sq(n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
               [&](int i, int j, double v_) { W2[i * ld + j] = v_; }, decg);
         GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return Pb[i * ld + k_] + Pb[k_ * ld + i]; }, [&](int k_, int j) { return W2[k_ * ld + j]; },
+        gemm_sq(n, [&](int i, int k_) { return Pb[i * ld + k_] + Pb[k_ * ld + i]; }, [&](int k_, int j) { return W2[k_ * ld + j]; },
               [&](int i, int j, double v_) {
                   Tb[i * ld + j] += v_ + ab[i] * af[j];
                   gC0b[i * n + j] += Pb[i * ld + j];
               }, decg);
-        gemm4(n, n, n, [&](int i, int k_) { return Pb[i * ld + k_]; }, [&](int k_, int j) { return Tm[k_ * ld + j]; },
+        gemm_sq(n, [&](int i, int k_) { return Pb[i * ld + k_]; }, [&](int k_, int j) { return Tm[k_ * ld + j]; },
               [&](int i, int j, double v_) { W1[i * ld + j] = v_; }, decg);
         GFOR(i, n) {
             double s = 0.0;
@@ -525,7 +584,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             afb[i] = s;
         }
         GSYNC();
-        gemm4(n, n, n, [&](int i, int k_) { return Tm[k_ * ld + i]; }, [&](int k_, int j) { return W1[k_ * ld + j]; },
+        gemm_sq(n, [&](int i, int k_) { return Tm[k_ * ld + i]; }, [&](int k_, int j) { return W1[k_ * ld + j]; },
               [&](int i, int j, double v_) { Pfb[i * ld + j] = v_; }, decg);
         // log-likelihood term
         GFOR(idx, p * p) {
