@@ -533,6 +533,18 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
 
     // ---- reverse sweep
     GFOR(idx, n * ld) Pb[idx] = 0.0;
+#if defined(GECON_GRAD_CN) && !defined(GECON_HOST_CHECK)
+    constexpr int NPRE = (n * n + n + p * p + p + n * p + G_NT - 1) / G_NT;  // doubles of one trajectory record per thread
+    double pre[NPRE];
+    if (Tobs > 0) {
+        const double* trn = traj + (size_t)(Tobs - 1) * TS;
+#pragma unroll
+        for (int m_ = 0; m_ < NPRE; ++m_) {
+            const int idx = G_TID + m_ * G_NT;
+            pre[m_] = (idx < (int)TS) ? trn[idx] : 0.0;
+        }
+    }
+#endif
     GSYNC();
     for (int t = Tobs - 1; t >= 0; --t) {
         const double* tr = traj + (size_t)t * TS;
@@ -540,11 +552,35 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         const double* trv = trF + p * p;
         const double* trK = trv + p;
         // replay of the update: P, a, F^-1, v, K come back from the trajectory; PZ, e, af, Pf are recomputed (O(n^2 p))
+#if defined(GECON_GRAD_CN) && !defined(GECON_HOST_CHECK)
+        // per-configuration build: the record of step t was fetched into registers one step ahead (its global-memory latency was 11 % of
+        // the stall samples); commit it to the tiles, then start the loads of step t - 1
+        (void)trF, (void)trv, (void)trK;
+#pragma unroll
+        for (int m_ = 0; m_ < NPRE; ++m_) {
+            const int idx = G_TID + m_ * G_NT;
+            const double val = pre[m_];
+            if (idx < n * n) P[(dec[idx] >> 16) * ld + (dec[idx] & 0xffff)] = val;
+            else if (idx < n * n + n) a[idx - n * n] = val;
+            else if (idx < n * n + n + p * p) F[idx - n * n - n] = val;
+            else if (idx < n * n + n + p * p + p) v[idx - n * n - n - p * p] = val;
+            else if (idx < (int)TS) K[idx - n * n - n - p * p - p] = val;
+        }
+        if (t > 0) {
+            const double* trn = tr - TS;
+#pragma unroll
+            for (int m_ = 0; m_ < NPRE; ++m_) {
+                const int idx = G_TID + m_ * G_NT;
+                pre[m_] = (idx < (int)TS) ? trn[idx] : 0.0;
+            }
+        }
+#else
         GFOR(idx, n * n) P[(dec[idx] >> 16) * ld + (dec[idx] & 0xffff)] = tr[idx];
         GFOR(i, n) a[i] = tr[n * n + i];
         GFOR(idx, p * p) F[idx] = trF[idx];
         GFOR(c, p) v[c] = trv[c];
         GFOR(idx, n * p) K[idx] = trK[idx];
+#endif
         masks(t);
         GSYNC();
         pz_panel();
