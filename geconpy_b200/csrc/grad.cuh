@@ -89,12 +89,14 @@ GHD void gemm4(int m, int n, int kk, FA a, FB b, FE epi, const int* tab = nullpt
 // chain is the k loop; operands and epilogue are the same inlined lambdas, guarded at the edges (the shared-memory tiles carry no
 // padding).  At n = 10: 12 DMMA + 12 predicated loads + 8 epilogue elements per lane instead of ~210 load / FMA / index instructions.
 // (With run-time dimensions the same idea was slower than gemm4 -- guards and loop control ate the gain)
-template <class FA, class FB, class FE>
-GHD void gemm_sq(int n_rt, FA a, FB b, FE epi, const int* tab) {
+// KP = true: the contraction runs over the p observables instead of the n states (the rank-p terms K N', PZ_bar Zm).
+template <bool KP = false, class FA, class FB, class FE>
+GHD void gemm_sq(int n_rt, int kk_rt, FA a, FB b, FE epi, const int* tab) {
 #if defined(GECON_GRAD_CN) && !defined(GECON_HOST_CHECK)
     (void)n_rt;
+    (void)kk_rt;
     (void)tab;
-    constexpr int n = GECON_GRAD_CN, NSQ = (n + 7) / 8, NK = (n + 3) / 4, NWARP = G_NT / 32;
+    constexpr int n = GECON_GRAD_CN, kdim = KP ? GECON_GRAD_CP : GECON_GRAD_CN, NSQ = (n + 7) / 8, NK = (kdim + 3) / 4, NWARP = G_NT / 32;
     constexpr int SPW = NWARP == 1 ? NSQ : 1;  // strips per pass of a warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -111,12 +113,12 @@ GHD void gemm_sq(int n_rt, FA a, FB b, FE epi, const int* tab) {
 #pragma unroll
             for (int s = 0; s < SPW; ++s) {
                 const int r = 8 * (s0 + s) + g;
-                av[s] = (r < n && kq < n) ? a(r, kq) : 0.0;
+                av[s] = (r < n && kq < kdim) ? a(r, kq) : 0.0;
             }
 #pragma unroll
             for (int ct = 0; ct < NSQ; ++ct) {
                 const int c = 8 * ct + g;
-                bv[ct] = (c < n && kq < n) ? b(kq, c) : 0.0;
+                bv[ct] = (c < n && kq < kdim) ? b(kq, c) : 0.0;
             }
 #pragma unroll
             for (int s = 0; s < SPW; ++s)
@@ -138,7 +140,7 @@ GHD void gemm_sq(int n_rt, FA a, FB b, FE epi, const int* tab) {
         }
     }
 #else
-    gemm4(n_rt, n_rt, n_rt, a, b, epi, tab);
+    gemm4(n_rt, n_rt, kk_rt, a, b, epi, tab);
 #endif
 }
 
@@ -171,7 +173,7 @@ GHD double absmax(const double* X, int ldx, int m, int n, double* s_red) {
 }
 
 // In-place inverse of the SPD p x p matrix F (row-major, ld = PMAXG) by Gauss-Jordan without pivoting, executed by one
-// thread; returns log det F through *logdet and false if a pivot is not positive.
+// thread; returns det F through *logdet and false if a pivot is not positive.
 GHD bool spd_inverse_small(double* F, int p, int ps, double* logdet) {
     double det = 1.0;  // p <= 8 pivots of an innovation covariance: their product does not leave the double range
     bool ok = true;
@@ -189,7 +191,7 @@ GHD bool spd_inverse_small(double* F, int p, int ps, double* logdet) {
             for (int j = 0; j < p; ++j) F[i * ps + j] = fma(-f, F[c * ps + j], F[i * ps + j]);
         }
     }
-    if (logdet) *logdet = log(det);  // one log per step; the reverse sweep's recomputation does not need it at all
+    if (logdet) *logdet = det;  // the DETERMINANT: the caller multiplies them up and takes one logarithm per draw
     return ok;
 }
 
@@ -234,7 +236,7 @@ GHH size_t kalman_grad_traj_stride(int n, int p) { return (size_t)n * n + n + (s
 // doubles of shared memory needed by kalman_grad_draw
 GHH size_t kalman_grad_smem_doubles(int n, int k, int p, int nt) {
     const int ld = ldim(n);
-    return (size_t)8 * n * ld + (size_t)5 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 4 + (size_t)n * (k > 0 ? k : 1) +
+    return (size_t)8 * n * ld + (size_t)5 * n * p + (size_t)2 * p * n + 5 * (size_t)n + 2 * (size_t)p * p + 9 * (size_t)p + 6 + (size_t)n * (k > 0 ? k : 1) +
            k + (size_t)k * k + nt + 8 + ((size_t)n * n + (size_t)n * p + (size_t)n * ((n + 3) / 4) + 1) / 2;
 }
 
@@ -296,8 +298,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     double* dv = hv + p;
     double* hb = dv + p;
     double* db = hb + p;
-    double* sc = db + p;  // [0] logdet, [1] ok flag, [2] ll, [3] all-missing flag
-    double* Rs = sc + 4;  // [n][k]
+    double* sc = db + p;  // [0] det F, [1] ok flag, [2] ll without the log-determinants, [3] all-missing flag, [4], [5] their running product
+    double* Rs = sc + 6;  // [n][k]   (sc[4], sc[5]: mantissa and exponent of the running product of the determinants)
     double* qs = Rs + n * (k > 0 ? k : 1);
     double* Qs = qs + k;  // [k][k] full shock covariance (when g.qfull)
     double* s_red = Qs + k * k;
@@ -414,6 +416,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     if (G_TID == 0) {
         sc[2] = 0.0;
         sc[1] = 1.0;
+        sc[4] = 1.0;
+        sc[5] = 0.0;
     }
     GSYNC();
 
@@ -436,12 +440,8 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
     };
     // Pf = P - K (PZ + j K)' + j I   (N = PZ + j K is never stored)
     auto filtered_cov = [&]() {
-        GFOR(idx, n * n) {
-            const int i = dec[idx] >> 16, j = dec[idx] & 0xffff;
-            double s = P[i * ld + j] + ((i == j) ? jit : 0.0);
-            for (int c = 0; c < p; ++c) s = fma(-K[i * ps + c], fma(jit, K[j * ps + c], PZ[j * ps + c]), s);
-            Pf[i * ld + j] = s;
-        }
+        gemm_sq<true>(n, p, [&](int i, int c) { return -K[i * ps + c]; }, [&](int c, int j) { return fma(jit, K[j * ps + c], PZ[j * ps + c]); },
+                      [&](int i, int j, double v_) { Pf[i * ld + j] = v_ + P[i * ld + j] + ((i == j) ? jit : 0.0); }, decg);
     };
 
     // ---- forward sweep: store the predicted moments and the update's F^-1, v, K; filter; predict
@@ -511,10 +511,13 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         if (G_TID == 0 && sc[3] == 0.0) {
             double quad = 0.0;
             for (int c = 0; c < p; ++c) quad = fma(v[c], e[c], quad);
-            sc[2] += -0.5 * (ll_const + sc[0] + quad);
+            int ex, ex2;
+            sc[4] = frexp(sc[4] * frexp(sc[0], &ex), &ex2);  // running product of the determinants: mantissa in sc[4] ...
+            sc[5] += (double)(ex + ex2);                     // ... exponent in sc[5]
+            sc[2] += -0.5 * (ll_const + quad);
         }
         GSYNC();
-        gemm_sq(n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
+        gemm_sq(n, n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
               [&](int i, int j, double v_) { W2[i * ld + j] = v_; }, decg);
         GFOR(i, n) {
             double s = 0.0;
@@ -522,12 +525,12 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             an[i] = s;
         }
         GSYNC();
-        gemm_sq(n, [&](int i, int k_) { return W2[i * ld + k_]; }, [&](int k_, int j) { return Tm[j * ld + k_]; },
+        gemm_sq(n, n, [&](int i, int k_) { return W2[i * ld + k_]; }, [&](int k_, int j) { return Tm[j * ld + k_]; },
               [&](int i, int j, double v_) { P[i * ld + j] = v_ + C0[i * n + j]; }, decg);
         GFOR(i, n) a[i] = an[i];
         GSYNC();
     }
-    const double ll = sc[2];
+    const double ll = sc[2] - 0.5 * (log(sc[4]) + sc[5] * 0.6931471805599453);
     if (sc[1] == 0.0) status |= ST_NOT_PD;
     if (!(fabs(ll) <= 1.7e308)) status |= ST_LL_NONFINITE;
 
@@ -604,15 +607,15 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
         filtered_cov();
         GSYNC();
         // predict in reverse:  P' = T Pf T' + C0,  a' = T af
-        gemm_sq(n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
+        gemm_sq(n, n, [&](int i, int k_) { return Tm[i * ld + k_]; }, [&](int k_, int j) { return Pf[k_ * ld + j]; },
               [&](int i, int j, double v_) { W2[i * ld + j] = v_; }, decg);
         GSYNC();
-        gemm_sq(n, [&](int i, int k_) { return Pb[i * ld + k_] + Pb[k_ * ld + i]; }, [&](int k_, int j) { return W2[k_ * ld + j]; },
+        gemm_sq(n, n, [&](int i, int k_) { return Pb[i * ld + k_] + Pb[k_ * ld + i]; }, [&](int k_, int j) { return W2[k_ * ld + j]; },
               [&](int i, int j, double v_) {
                   Tb[i * ld + j] += v_ + ab[i] * af[j];
                   gC0b[i * n + j] += Pb[i * ld + j];
               }, decg);
-        gemm_sq(n, [&](int i, int k_) { return Pb[i * ld + k_]; }, [&](int k_, int j) { return Tm[k_ * ld + j]; },
+        gemm_sq(n, n, [&](int i, int k_) { return Pb[i * ld + k_]; }, [&](int k_, int j) { return Tm[k_ * ld + j]; },
               [&](int i, int j, double v_) { W1[i * ld + j] = v_; }, decg);
         GFOR(i, n) {
             double s = 0.0;
@@ -620,7 +623,7 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             afb[i] = s;
         }
         GSYNC();
-        gemm_sq(n, [&](int i, int k_) { return Tm[k_ * ld + i]; }, [&](int k_, int j) { return W1[k_ * ld + j]; },
+        gemm_sq(n, n, [&](int i, int k_) { return Tm[k_ * ld + i]; }, [&](int k_, int j) { return W1[k_ * ld + j]; },
               [&](int i, int j, double v_) { Pfb[i * ld + j] = v_; }, decg);
         // log-likelihood term
         GFOR(idx, p * p) {
@@ -671,12 +674,9 @@ GHD void kalman_grad_draw(const KalmanGradArgs& g, long long draw, int cta, doub
             db[c] -= (g.mask_intercept ? w[c] : 1.0) * vb[c];
         }
         GSYNC();
-        GFOR(idx, n * n) {  // P_bar = Pf_bar + PZ_bar Zm
-            const int i = dec[idx] >> 16, j = dec[idx] & 0xffff;
-            double s = Pfb[i * ld + j];
-            for (int c = 0; c < p; ++c) s = fma(PZb[i * ps + c] * w[c], Zs[c * n + j], s);
-            Pb[i * ld + j] = s;
-        }
+        // P_bar = Pf_bar + PZ_bar Zm
+        gemm_sq<true>(n, p, [&](int i, int c) { return PZb[i * ps + c] * w[c]; }, [&](int c, int j) { return Zs[c * n + j]; },
+                      [&](int i, int j, double v_) { Pb[i * ld + j] = v_ + Pfb[i * ld + j]; }, decg);
         if (g.Z_bar) {  // Zm = diag(w) Z enters v = ym - d - Zm a, PZ = P Zm', F = Zm PZ + ...
             GFOR(idx, p * n) {
                 const int c = idx / n, j = idx - c * n;
