@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CORE_LIB = PKG / "_lib" / "libgecon_b200.so"
-ABI_VERSION = 2  # include/gecon_b200.h: GECON_ABI_VERSION
+ABI_VERSION = 3  # include/gecon_b200.h: GECON_ABI_VERSION
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -136,6 +136,7 @@ class PipelineArgs(C.Structure):
         ("ll", C.c_void_p),
         ("status", C.c_void_p),
         ("n_iter", C.c_void_p),
+        ("cr_solve", C.c_void_p),
     ]
 
 

@@ -27,6 +27,9 @@ KALMAN_NPS = [8, 16, 24, 32, 40, 48, 56, 64]
 CR_WARP_INST = "cr_warp_inst.cu"
 CR_WARP_NPS = [8, 16, 24, 32]
 
+# what a generated model source pulls in when it carries its own build of the solver (model/codegen.py: cr_spec_block)
+MODEL_SOLVER_DEPS = ["cr_warp_spec.cu", "cr_warp.cuh", "linalg.cuh", "common.cuh"]
+
 NVCC_FLAGS = [
     "-O3",
     "-std=c++17",
@@ -97,8 +100,12 @@ def build_core(force: bool = False, verbose: bool = False) -> Path:
 def build_model(name: str, source: str, force: bool = False) -> Path:
     """Compile one generated model source (a string of CUDA C++) into its own shared library."""
     MODEL_LIBDIR.mkdir(parents=True, exist_ok=True)
-    header = (PKG.parent / "include" / "gecon_b200.h").read_text()  # the generated source includes it (gecon_pipeline_args)
-    dig = hashlib.sha256((source + header + " ".join(NVCC_FLAGS)).encode()).hexdigest()[:16]
+    # the generated source includes the public header (gecon_pipeline_args) and, for models the warp-per-draw solver covers, the
+    # per-model solver build (cr_warp_spec.cu and what it includes, found through -I csrc): all part of the digest
+    incl = [PKG.parent / "include" / "gecon_b200.h"]
+    if "cr_warp_spec.cu" in source:
+        incl += [CSRC / f for f in MODEL_SOLVER_DEPS]
+    dig = hashlib.sha256((source + "".join(f.read_text() for f in incl) + " ".join(NVCC_FLAGS)).encode()).hexdigest()[:16]
     lib = MODEL_LIBDIR / f"libgecon_model_{name}_{dig}.so"
     if lib.exists() and not force:
         return lib
@@ -114,7 +121,7 @@ def build_model(name: str, source: str, force: bool = False) -> Path:
         # (the fused entry point gecon_model_loglik calls gecon_loglik_pipeline of the core library: link it, found at run time
         # next door through $ORIGIN)
         link = ["-L", str(LIBDIR), "-lgecon_b200", "-Xlinker", "-rpath=$ORIGIN/.."]
-        _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-o", str(tmp_lib), str(tmp_src), *link, "-lcudart"])
+        _run([nvcc, *NVCC_FLAGS, "-shared", "-I", str(PKG.parent / "include"), "-I", str(CSRC), "-o", str(tmp_lib), str(tmp_src), *link, "-lcudart"])
         os.replace(tmp_src, src)
         os.replace(tmp_lib, lib)
         import re

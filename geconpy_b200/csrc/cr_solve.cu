@@ -509,6 +509,8 @@ static int launch_cr_warp(const gecon_cr_args& a, const cw_ranges& rg, int c, cu
     return GECON_E_UNSUPPORTED_SIZE;
 }
 
+extern "C" int gecon_cr_check_args(const gecon_cr_args* args) { return check_cr_args(args); }
+
 extern "C" int gecon_cr_solve_batched(const gecon_cr_args* args, void* stream) {
     int rc = check_cr_args(args);
     if (rc) return rc;

@@ -28,6 +28,16 @@
 #pragma once
 #include "linalg.cuh"
 
+// Per-model build (cr_warp_spec.cu, compiled into every generated model library): the number of variables and the packed lag / lead
+// column ranges are compile-time constants
+//     GECON_CW_SPEC_N, GECON_CW_SPEC_O0, GECON_CW_SPEC_W0, GECON_CW_SPEC_O2, GECON_CW_SPEC_W2
+// so every range guard of the products, the panel's column counts and the norm loops fold away (measured on the medium NK model: 33.4 ->
+// 28.3 ms per 262,144 draws, 0.43 -> 0.51 of the fp64 peak).  The kernel gets its own name there: it must never be confused with the
+// generic instantiation of the core library.
+#ifdef GECON_CW_SPEC_N
+#define cr_warp_kernel cr_warp_spec_kernel
+#endif
+
 namespace gecon {
 
 template <int NP, int C>
@@ -121,6 +131,9 @@ __device__ __noinline__ bool cw_gj(double* __restrict__ WA, int nta, int ntb, in
     constexpr int LDW = K::LDW, NS = K::NS;
     constexpr unsigned IDXBITS = 5u, IDXMASK = 31u;
     const int g = lane >> 2, q = lane & 3;
+#ifdef GECON_CW_SPEC_N
+    n = GECON_CW_SPEC_N;
+#endif
     const int nblk = (n + 7) >> 3;
     bool used = (lane >= n);
     unsigned fail = 0u;
@@ -383,7 +396,12 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
     int* s_perm = ibase + WPC * K::PER_WARP_I;
     int* s_lead = s_perm + NP;
 
+#ifdef GECON_CW_SPEC_N
+    constexpr int n = GECON_CW_SPEC_N;
+    const int k = p.k;
+#else
     const int n = p.n, k = p.k;
+#endif
     const int no = (p.unperm && p.n_out > 0) ? p.n_out : n;
     const int nl = p.lead_idx ? p.n_lead : 0;
     for (int i = tid; i < NP; i += WPC * 32) {
@@ -392,7 +410,12 @@ __global__ void __launch_bounds__(WPC * 32, cw_min_ctas<NP, C, WPC>()) cr_warp_k
     }
     __syncthreads();
 
+#ifdef GECON_CW_SPEC_N
+    constexpr int o0 = GECON_CW_SPEC_O0, w0 = GECON_CW_SPEC_W0, o2 = GECON_CW_SPEC_O2, w2 = GECON_CW_SPEC_W2;
+    (void)rg;
+#else
     const int o0 = rg.o0, w0 = rg.w0, o2 = rg.o2, w2 = rg.w2;
+#endif
     const int nt0 = (w0 + 7) >> 3, nt2 = (w2 + 7) >> 3;   // column tiles of the packed ranges
     const int nk0 = (w0 + 3) >> 2, nk2 = (w2 + 3) >> 2;   // k-steps
     const int kd = ((p.D || cj.vals) && p.R) ? k : 0;

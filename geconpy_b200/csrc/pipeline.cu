@@ -183,7 +183,7 @@ extern "C" int gecon_loglik_pipeline(const gecon_pipeline_args* a, void* stream)
         cr.scan_semantics = a->scan_semantics;
         cr.compact = &cj;
         tm.begin(1);
-        rc = gecon_cr_solve_batched(&cr, stream);
+        rc = a->cr_solve ? a->cr_solve(&cr, stream) : gecon_cr_solve_batched(&cr, stream);
         tm.end();
         if (rc) break;
         // 3 ---- exact Blanchard-Kahn count for the draws without a certificate

@@ -441,9 +441,31 @@ class LinearizedModel:
         offs = [sum(1 for key in nz if "ABCD".index(key[0]) < q) for q in range(5)]
         table = ", ".join(str((i << 16) | j) for (_m, i, j) in nz) or "0"
         return _TEMPLATE.format(name=ident, n=n, k=k, n_theta=self.n_theta, body=body, vjp_body=self.vjp_body(), nnz=len(nz),
+                                cr_spec=self.cr_spec_block(offs),
                                 nnz_alloc=max(1, len(nz)), table=table, offs=", ".join(map(str, offs)),
                                 lag_lo=self.col_ranges[0], lag_hi=self.col_ranges[1], lead_lo=self.col_ranges[2], lead_hi=self.col_ranges[3],
                                 n_lead=len(self.permuted_lead_var_idx), lead_list=", ".join(map(str, self.permuted_lead_var_idx)) or "0")
+
+    def cr_spec_block(self, offs) -> str:
+        """The per-model build of the warp-per-draw solver (csrc/cr_warp_spec.cu): number of variables, packed lag / lead column
+        ranges and packed width as compile-time constants, for systems the warp kernel covers (the eligibility rule of
+        ``cr_warp_eligible`` in csrc/cr_solve.cu: n <= 32, a forward-looking block, packed blocks no wider than the padded matrix).
+        Empty for the other models: they keep the generic kernels of the core library."""
+        n, k = len(self.var_names), len(self.shock_names)
+        lag_lo, lag_hi, lead_lo, lead_hi = self.col_ranges
+        hint = lag_hi > lag_lo or lead_hi > lead_lo
+        o0 = (lag_lo & ~1) if hint else 0
+        w0 = (lag_hi - o0) if hint else n
+        o2 = (lead_lo & ~1) if hint else 0
+        w2 = (lead_hi - o2) if hint else n
+        c = max(1, -(-max(w0, w2, k, len(self.permuted_lead_var_idx)) // 8))
+        np_ = -(-n // 8) * 8
+        if np_ > 32 or offs[3] <= offs[2] or 8 * c > np_:
+            return ""
+        return (f"// ---- the solver compiled for this model (one warp per draw; csrc/cr_warp_spec.cu, found through -I <csrc>)\n"
+                f"#define GECON_CW_SPEC_N {n}\n#define GECON_CW_SPEC_O0 {o0}\n#define GECON_CW_SPEC_W0 {w0}\n"
+                f"#define GECON_CW_SPEC_O2 {o2}\n#define GECON_CW_SPEC_W2 {w2}\n#define GECON_CW_SPEC_C {c}\n"
+                f'#include "cr_warp_spec.cu"\n')
 
     def nonzero_structure(self):
         """Structural non-zeros of A, B, C, D in solver order as a list of (matrix, row, col), grouped by matrix and row-major inside
@@ -595,10 +617,14 @@ extern "C" int gecon_model_structure(int32_t* nnz, const int32_t** table, const 
     return 0;
 }}
 
+{cr_spec}
 // The fused theta -> log-likelihood entry point of this model (include/gecon_b200.h, gecon_pipeline_args): fills in the model's
 // own kernel and structure tables and runs the core library's pipeline.
 extern "C" int gecon_model_loglik(gecon_pipeline_args* a, void* stream) {{
     if (!a) return -1;
+#ifdef GECON_CW_SPEC_N
+    if (a->struct_size >= offsetof(gecon_pipeline_args, cr_solve) + sizeof(a->cr_solve)) a->cr_solve = gecon_model_cr_solve;
+#endif
     a->jacobian = gecon_model_jacobian_compact;
     a->nz_table = gecon_nz_table_h;
     a->nz_off = gecon_nz_off_h;

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GECON_ABI_VERSION 2
+#define GECON_ABI_VERSION 3
 
 /* argument errors */
 #define GECON_E_BADARG (-1)
@@ -397,11 +397,13 @@ int gecon_real_eig_host(const double* M, int64_t N, int32_t m, int32_t balance, 
  * observation equations, no steady-state intercept (the Python pipeline handles those).
  * Every generated model library exports
  *     int gecon_model_loglik(gecon_pipeline_args* args, void* stream);
- * which fills in `jacobian`, `nz_table`, `nz_off`, `nnz`, `n`, `k`, `n_theta`, `col_ranges` (and `lead_idx` / `n_lead` when
- * they are NULL / 0 and check_bk != 0) from its own tables and calls gecon_loglik_pipeline.
+ * which fills in `jacobian`, `nz_table`, `nz_off`, `nnz`, `n`, `k`, `n_theta`, `col_ranges`, `cr_solve` (and `lead_idx` /
+ * `n_lead` when they are NULL / 0 and check_bk != 0) from its own tables and calls gecon_loglik_pipeline.
  * ------------------------------------------------------------------------------------------------------------- */
 typedef int (*gecon_jacobian_compact_fn)(const double* theta, int64_t theta_stride, int64_t N, double* vals, double* xss,
                                          int32_t* status, void* stream);
+
+typedef int (*gecon_cr_solve_fn)(const gecon_cr_args* args, void* stream); /* the contract of gecon_cr_solve_batched */
 
 typedef struct gecon_pipeline_args {
     size_t struct_size;
@@ -443,6 +445,10 @@ typedef struct gecon_pipeline_args {
     double* ll;               /* DEVICE [N] out */
     int32_t* status;          /* DEVICE [N] out */
     int32_t* n_iter;          /* DEVICE [N] out or NULL */
+    gecon_cr_solve_fn cr_solve; /* NULL: gecon_cr_solve_batched.  gecon_model_loglik sets it to the model library's own
+                                 gecon_model_cr_solve -- the warp-per-draw solver compiled with this model's n and column ranges as
+                                 compile-time constants (csrc/cr_warp_spec.cu); same contract, same results, falls back to the generic
+                                 entry point for arguments it was not built for (GECON_CR_SPEC=0 forces the generic kernel) */
 } gecon_pipeline_args;
 
 int gecon_loglik_pipeline(const gecon_pipeline_args* args, void* stream);

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared <= set(_lib.EXPORTS), declared - set(_lib.EXPORTS)
-    assert lib.gecon_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.gecon_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_ctypes_structs_match_the_header_layout(tmp_path):
