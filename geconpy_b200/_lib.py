@@ -137,6 +137,7 @@ class PipelineArgs(C.Structure):
         ("status", C.c_void_p),
         ("n_iter", C.c_void_p),
         ("cr_solve", C.c_void_p),
+        ("kalman_ll", C.c_void_p),
     ]
 
 

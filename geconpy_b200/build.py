@@ -162,6 +162,49 @@ def build_grad_spec(n: int, k: int, p: int, force: bool = False) -> Path:
     return lib
 
 
+def filter_spec_np(n: int, k: int, p: int) -> int:
+    """Padded dimension at which the warp-per-draw filter runs an (n filter variables, k shocks, p observables) configuration, or 0
+    when another kernel takes it (csrc/kalman.cu: thread per draw for n <= 4 and p <= 2, CTA per draw beyond 32)."""
+    np_ = -(-max(n + 1, k) // 8) * 8
+    if np_ > 32 or not (1 <= p <= 8) or p > n or (n <= 4 and p <= 2):
+        return 0
+    return np_
+
+
+def filter_spec_path(n: int, k: int, p: int):
+    """Where build_filter_spec puts (or would put) the library of this configuration; None when the configuration has no such build."""
+    np_ = filter_spec_np(n, k, p)
+    if not np_:
+        return None
+    deps = [CSRC / f for f in ("kalman_spec.cu", "kalman_warp_launch.cuh", "kalman_warp.cuh", "kalman.cuh", "linalg.cuh", "common.cuh")]
+    dig = _digest(deps + [PKG.parent / "include" / "gecon_b200.h"], NVCC_FLAGS)[:16]
+    return MODEL_LIBDIR / f"libgecon_kf_n{n}_np{np_}_p{p}_{dig}.so"
+
+
+def build_filter_spec(n: int, k: int, p: int, force: bool = False):
+    """The warp-per-draw Kalman filter compiled for ONE (filter dimension, padded dimension, observables) triple (csrc/kalman_spec.cu):
+    same source as the generic kernel, the filter dimension a compile-time constant.  Cached next to the model libraries."""
+    lib = filter_spec_path(n, k, p)
+    if lib is None or (lib.exists() and not force):
+        return lib
+    np_ = filter_spec_np(n, k, p)
+    MODEL_LIBDIR.mkdir(parents=True, exist_ok=True)
+    build_core()
+    tmp_lib = lib.with_name(lib.name + f".{os.getpid()}.tmp")
+    try:
+        link = ["-L", str(LIBDIR), "-lgecon_b200", "-Xlinker", "-rpath=$ORIGIN/.."]
+        _run([find_nvcc(), *NVCC_FLAGS, "-shared", f"-DGECON_KW_SPEC_N={n}", f"-DGECON_KW_SPEC_NP={np_}", f"-DGECON_KW_SPEC_P={p}", "-o", str(tmp_lib),
+              str(CSRC / "kalman_spec.cu"), *link, "-lcudart"])
+        os.replace(tmp_lib, lib)
+        for stale in MODEL_LIBDIR.glob(f"libgecon_kf_n{n}_np{np_}_p{p}_*.so"):  # builds of older sources of the same configuration
+            if stale != lib:
+                stale.unlink(missing_ok=True)
+    finally:
+        if tmp_lib.exists():
+            tmp_lib.unlink()
+    return lib
+
+
 if __name__ == "__main__":
     import sys
 

@@ -180,6 +180,16 @@ int lyap_kernel_info(int n, int* ctas, int* smem, int* threads) {
 
 using namespace gecon;
 
+// for the per-configuration builds (kalman_spec.cu): the argument validation of gecon_kalman_ll_*, and the padded dimension at which
+// the generic entry point would run the warp-per-draw kernel on these arguments (0: it would not -- thread-per-draw or CTA-per-draw)
+extern "C" int gecon_kalman_check_args(const gecon_kalman_args* args) { return check_kf_args(args); }
+extern "C" int gecon_kalman_warp_np(const gecon_kalman_args* args) {
+    bool taken = false;
+    int info[3];
+    if (launch_kf_thread(*args, nullptr, info, &taken) == 0 && taken) return 0;
+    return warp_kernel_np(*args);
+}
+
 extern "C" int gecon_kalman_ll_batched(const gecon_kalman_args* args, void* stream) {
     int rc = check_kf_args(args);
     if (rc) return rc;

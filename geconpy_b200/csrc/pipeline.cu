@@ -235,7 +235,7 @@ extern "C" int gecon_loglik_pipeline(const gecon_pipeline_args* a, void* stream)
         kf.status = a->status + lo;
         kf.mask_intercept = a->mask_intercept;
         tm.begin(3);
-        rc = gecon_kalman_ll_batched(&kf, stream);
+        rc = a->kalman_ll ? a->kalman_ll(&kf, stream) : gecon_kalman_ll_batched(&kf, stream);
         tm.end();
         if (rc) break;
         if (a->n_iter) {

@@ -54,6 +54,14 @@ class CompiledModel:
         self._loglik = self._lib.gecon_model_loglik  # the fused theta -> log-likelihood entry point (gecon_pipeline_args)
         self._loglik.restype = C.c_int
         self._loglik.argtypes = [C.POINTER(L.PipelineArgs), C.c_void_p]
+        # the model's own build of the warp-per-draw solver (csrc/cr_warp_spec.cu; same contract as gecon_cr_solve_batched, which it
+        # calls itself for arguments it was not built for); models the warp kernel does not cover have no such symbol
+        try:
+            self._cr_solve = self._lib.gecon_model_cr_solve
+            self._cr_solve.restype = C.c_int
+            self._cr_solve.argtypes = [C.POINTER(L.CrArgs), C.c_void_p]
+        except AttributeError:
+            self._cr_solve = None
         self._jac_compact = self._lib.gecon_model_jacobian_compact
         self._jac_compact.restype = C.c_int
         self._jac_compact.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -184,6 +192,7 @@ class BatchedStateSpace:
         use_direct_lyapunov: bool = False,
         add_bk_check: bool | None = None,
         add_solver_success_check: bool = True,
+        specialize: bool | None = None,
     ):
         """Same meaning as ``DSGEStateSpace.configure`` (gEconpy/model/statespace.py:822-1090) for the arguments it
         shares: ``temporal_aggregation`` {"sum" | "mean" | "first" | "last"} with ``aggregation_period`` adds cumulator
@@ -212,7 +221,11 @@ class BatchedStateSpace:
         the reference's default graph (non-finite steady states and failed solves are gated either way: their logp is NaN in
         the reference, -inf here).  ``check_bk`` is the older name of ``add_bk_check``.  ``bk_on_rejected_draws=False`` (fused path only):
         draws the gate already rejects for another reason are not Blanchard-Kahn-counted -- same log-likelihoods, their BK status bit
-        stays unset; on a population where half the draws fail the count is most of the step, and a sampler only consumes the gate."""
+        stays unset; on a population where half the draws fail the count is most of the step, and a sampler only consumes the gate.
+        ``specialize``: the filter kernel compiled for this configuration's (filter dimension, observables) pair (``build.build_filter_spec``:
+        3-7 s of nvcc once, cached on disk; same source as the generic kernel, identical results, ~12 % faster) -- True: build it now;
+        False: never use it; None (default): use it when it is already on disk, and build it the first time a population of at least
+        ``SPEC_MIN_DRAWS`` draws arrives.  (The solver's counterpart needs no switch: it is part of the model library.)"""
         m = self.model
         if solver not in ("cycle_reduction", "gensys", "scan_cycle_reduction", "backward_direct"):
             raise NotImplementedError(f"solver={solver!r}: expected cycle_reduction, gensys, scan_cycle_reduction or backward_direct")
@@ -324,6 +337,8 @@ class BatchedStateSpace:
         self.cov_jitter, self.missing_fill_value, self.mvn_const = float(cov_jitter), float(missing_fill_value), mvn_const
         self.check_bk = bool(check_bk)
         self.bk_on_rejected_draws = bool(bk_on_rejected_draws)
+        self.specialize = specialize
+        self.__dict__.pop("_kf_spec_cache", None)
         self.chunk = int(os.environ.get("GECON_CHUNK", chunk))
         self.full_covariance = bool(full_shock_covariance)
         self.mask_intercept = bool(mask_intercept)
@@ -442,6 +457,7 @@ class BatchedStateSpace:
             return self._loglik_fused(theta_full, Y, ll, status, out_n_iter, events)
         nc = min(self.chunk, N)
         n_err = len(self.measurement_error)
+        kf_spec = self._filter_spec_fn(self.n_aug, N)  # the staged path filters the (augmented) state at its full dimension
         n_streams = max(1, int(getattr(self, "n_streams", 1)))
         cur = torch.cuda.current_stream(dev)
         if n_streams > 1:
@@ -506,7 +522,7 @@ class BatchedStateSpace:
                     lag_lo=m.col_ranges[0], lag_hi=m.col_ranges[1], lead_lo=m.col_ranges[2], lead_hi=m.col_ranges[3],
                 )  # fmt: skip
                 e = mark("cr_solve")
-                L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
+                L.check((m._cr_solve or lib.gecon_cr_solve_batched)(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
                 e and e.record()
                 if self.check_bk:
                     bk = L.BkArgs(
@@ -534,7 +550,7 @@ class BatchedStateSpace:
                     ll_t=None, mask_intercept=int(self.mask_intercept),
                 )  # fmt: skip
                 e = mark("kalman_ll")
-                L.check(lib.gecon_kalman_ll_batched(C.byref(kf), C.c_void_p(stream)), "gecon_kalman_ll_batched")
+                L.check((kf_spec or lib.gecon_kalman_ll_batched)(C.byref(kf), C.c_void_p(stream)), "gecon_kalman_ll_batched")
                 e and e.record()
                 if out_n_iter is not None:
                     out_n_iter[lo : lo + cnt].copy_(ws["n_iter"][:cnt])
@@ -568,6 +584,9 @@ class BatchedStateSpace:
             timing=int(events is not None), chunk=self.chunk, ll=ll.data_ptr(), status=status.data_ptr(),
             n_iter=(out_n_iter.data_ptr() if out_n_iter is not None else None),
         )  # fmt: skip
+        kf_spec = self._filter_spec_fn(self.n_filter, theta_full.shape[0])
+        if kf_spec is not None:
+            args.kalman_ll = C.cast(kf_spec, C.c_void_p)
         stream = torch.cuda.current_stream(dev).cuda_stream
         before = L.load_library().gecon_launch_count()
         rc = m._loglik(C.byref(args), C.c_void_p(stream))
@@ -579,6 +598,34 @@ class BatchedStateSpace:
             events.append(("__fused_ms__", dict(zip(("jacobian", "cr_solve", "bk_count", "kalman_ll"), (float(v) for v in ms))), None))
         self.fused_launches = int(L.load_library().gecon_launch_count() - before)
         return ll, status
+
+    SPEC_MIN_DRAWS = 4096  # populations this large pay for the per-configuration build of the filter within their first evaluation
+
+    def _filter_spec_fn(self, n_filter: int, n_draws: int):
+        """``gecon_kalman_ll_spec`` of the filter library built for (n_filter, shocks, observables) -- ``build.build_filter_spec`` -- or
+        None: configure(specialize=False), ``GECON_KF_SPEC=0``, a configuration the warp-per-draw filter does not take (dense design
+        matrix, full shock covariance, thread-per-draw or CTA-per-draw sizes), or not built yet and the population is small.  The entry
+        point has the contract of ``gecon_kalman_ll_batched`` and calls it itself for arguments it was not built for."""
+        if self.specialize is False or os.environ.get("GECON_KF_SPEC", "1") == "0" or self.dense_Z is not None or self.full_covariance:
+            return None
+        from .. import build
+
+        key = (int(n_filter), self.model.k, self.p)
+        cache = self.__dict__.setdefault("_kf_spec_cache", {})
+        if key not in cache:
+            path = build.filter_spec_path(*key)
+            if path is None:
+                cache[key] = None
+            elif path.exists() or self.specialize or n_draws >= self.SPEC_MIN_DRAWS:
+                L.load_library()
+                lib = C.CDLL(str(build.build_filter_spec(*key)))
+                lib.gecon_kalman_ll_spec.restype = C.c_int
+                lib.gecon_kalman_ll_spec.argtypes = [C.POINTER(L.KalmanArgs), C.c_void_p]
+                cache[key] = lib
+            else:
+                return None  # not cached: a later, larger population may still build it
+        lib = cache[key]
+        return None if lib is None else lib.gecon_kalman_ll_spec
 
     # ------------------------------------------------------------------------------------------------ gradient
     def _grad_spec_lib(self):
@@ -683,7 +730,7 @@ class BatchedStateSpace:
                 lag_lo=m.col_ranges[0], lag_hi=m.col_ranges[1], lead_lo=m.col_ranges[2], lead_hi=m.col_ranges[3],
             )  # fmt: skip
             e = mark("cr_solve")
-            L.check(lib.gecon_cr_solve_batched(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
+            L.check((m._cr_solve or lib.gecon_cr_solve_batched)(C.byref(cr), C.c_void_p(stream)), "gecon_cr_solve_batched")
             e and e.record()
             if self.check_bk:
                 bk = L.BkArgs(

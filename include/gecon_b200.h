@@ -404,6 +404,7 @@ typedef int (*gecon_jacobian_compact_fn)(const double* theta, int64_t theta_stri
                                          int32_t* status, void* stream);
 
 typedef int (*gecon_cr_solve_fn)(const gecon_cr_args* args, void* stream); /* the contract of gecon_cr_solve_batched */
+typedef int (*gecon_kalman_ll_fn)(const gecon_kalman_args* args, void* stream); /* the contract of gecon_kalman_ll_batched */
 
 typedef struct gecon_pipeline_args {
     size_t struct_size;
@@ -449,6 +450,9 @@ typedef struct gecon_pipeline_args {
                                  gecon_model_cr_solve -- the warp-per-draw solver compiled with this model's n and column ranges as
                                  compile-time constants (csrc/cr_warp_spec.cu); same contract, same results, falls back to the generic
                                  entry point for arguments it was not built for (GECON_CR_SPEC=0 forces the generic kernel) */
+    gecon_kalman_ll_fn kalman_ll; /* NULL: gecon_kalman_ll_batched.  Else the filter compiled for this configuration's (filter
+                                 dimension, observables) pair -- gecon_kalman_ll_spec of a csrc/kalman_spec.cu build; same contract, same
+                                 results, falls back to the generic entry point by itself (GECON_KF_SPEC=0 forces the generic kernel) */
 } gecon_pipeline_args;
 
 int gecon_loglik_pipeline(const gecon_pipeline_args* args, void* stream);

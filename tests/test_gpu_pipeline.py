@@ -357,11 +357,13 @@ def test_gate_only_blanchard_kahn_skips_rejected_draws_without_changing_the_like
 
 
 @pytest.mark.parametrize("wl_name", ["rbc", "nk", "nk_wide", "large"])
-def test_per_model_solver_build_is_bit_identical_to_the_generic_kernel(compiled, wl_name, monkeypatch):
+@pytest.mark.parametrize("fused", [True, False])
+def test_per_model_solver_and_per_configuration_filter_builds_are_bit_identical_to_the_generic_kernels(compiled, wl_name, fused, monkeypatch):
     """Every model the warp-per-draw solver covers carries its own build of that kernel (csrc/cr_warp_spec.cu: n and the packed column
-    ranges compile-time constants), handed to the fused pipeline as gecon_pipeline_args.cr_solve.  Same source, same arithmetic:
-    log-likelihoods, status words and iteration counts are IDENTICAL to the generic kernel's (GECON_CR_SPEC=0), failure classes included."""
-    import ctypes
+    ranges compile-time constants), handed to the fused pipeline as gecon_pipeline_args.cr_solve; the filter is built per (filter
+    dimension, observables) pair (csrc/kalman_spec.cu, gecon_pipeline_args.kalman_ll).  Same source, same arithmetic: log-likelihoods
+    and status words are IDENTICAL to the generic kernels' (GECON_CR_SPEC=0, GECON_KF_SPEC=0), failure classes included, on the fused
+    and on the staged path, and each counts as one launch of ours like the kernel it replaces."""
     import sys
 
     import torch
@@ -374,21 +376,31 @@ def test_per_model_solver_build_is_bit_identical_to_the_generic_kernel(compiled,
 
     wl = bench.WORKLOADS[wl_name]
     cm, mod = compiled(wl["model"]), model(wl["model"])
-    assert hasattr(ctypes.CDLL(str(cm.lib_path)), "gecon_model_cr_solve")
+    assert cm._cr_solve is not None
     N, Tobs = 4096 + 37, 40
-    ss = BatchedStateSpace(cm).configure(observed_states=wl["observed"], measurement_error=wl["meas"], tol=1e-8, max_iter=wl.get("max_iter", 50))
-    assert ss.fused
+    kw = dict(observed_states=wl["observed"], measurement_error=wl["meas"], tol=1e-8, max_iter=wl.get("max_iter", 50), fused=fused)
+    ss = BatchedStateSpace(cm).configure(specialize=True, **kw)
+    assert ss.fused == fused
     theta = bench.make_draws(mod.spec, N, wl["width"], seed=11, box=wl.get("box"))
     Y = simulate_obs(mod, Tobs, observed=wl["observed"], seed=4, sigma_err=SIGMA_ERR)
     full = torch.as_tensor(np.hstack([theta, np.full((N, mod.k), SIGMA_SHOCK), np.full((N, len(wl["meas"])), SIGMA_ERR)]), device="cuda")
     Yd = torch.as_tensor(Y, device="cuda")
-    n0 = L.load_library().gecon_launch_count()
+    lib = L.load_library()
+    n0 = lib.gecon_launch_count()
     ll_s, st_s = (x.cpu().numpy() for x in ss.loglik_device(full, Yd))
-    n_spec = L.load_library().gecon_launch_count() - n0
+    n_spec = lib.gecon_launch_count() - n0
+    built = [k for k, v in ss._kf_spec_cache.items() if v is not None]
+    assert (built == []) == (wl_name == "rbc"), built  # RBC with one observable: thread-per-draw filter, no per-configuration build
     monkeypatch.setenv("GECON_CR_SPEC", "0")
-    n0 = L.load_library().gecon_launch_count()
+    monkeypatch.setenv("GECON_KF_SPEC", "0")
+    n0 = lib.gecon_launch_count()
     ll_g, st_g = (x.cpu().numpy() for x in ss.loglik_device(full, Yd))
-    assert L.load_library().gecon_launch_count() - n0 == n_spec  # the per-model kernel counts as ONE launch of ours, like the generic one
+    assert lib.gecon_launch_count() - n0 == n_spec
     assert np.array_equal(st_s, st_g)
     assert np.array_equal(ll_s, ll_g, equal_nan=True)
     assert np.isfinite(ll_s).mean() > 0.2
+    # specialize=False never loads the filter build; same numbers again
+    monkeypatch.delenv("GECON_KF_SPEC")
+    off = BatchedStateSpace(cm).configure(specialize=False, **kw)
+    ll_o, st_o = (x.cpu().numpy() for x in off.loglik_device(full, Yd))
+    assert "_kf_spec_cache" not in off.__dict__ and np.array_equal(ll_o, ll_s, equal_nan=True) and np.array_equal(st_o, st_s)

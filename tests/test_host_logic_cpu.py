@@ -246,6 +246,35 @@ def test_grad_spec_source_compiles_for_any_dimensions_and_exports_its_entry_poin
     assert lib.gecon_kalman_grad_spec(C.byref(a), None) == -1  # GECON_E_BADARG
 
 
+def test_filter_and_solver_spec_sources_compile_and_export_their_entry_points():
+    """csrc/kalman_spec.cu (per-configuration filter) and csrc/cr_warp_spec.cu (per-model solver, inside the generated model library)
+    cross-compile for sm_100a, link against the core library and export entry points with the contracts of the generic ones: the same
+    argument validation runs first (no compute call without a GPU)."""
+    import ctypes as C
+
+    from geconpy_b200 import _lib as L
+    from geconpy_b200.build import build_filter_spec, filter_spec_np, filter_spec_path
+    from geconpy_b200.model.compiled import CompiledModel
+
+    assert filter_spec_np(3, 1, 1) == 0 and filter_spec_path(3, 1, 1) is None  # thread-per-draw sizes have no such build
+    assert filter_spec_np(40, 4, 3) == 0 and filter_spec_np(10, 4, 9) == 0      # CTA-per-draw sizes, p > 8
+    assert filter_spec_np(10, 4, 3) == 16 and filter_spec_np(7, 4, 3) == 8 and filter_spec_np(5, 12, 3) == 16 and filter_spec_np(31, 9, 7) == 32
+    lib = C.CDLL(str(build_filter_spec(7, 2, 3)))
+    dims = (C.c_int32 * 3)()
+    assert lib.gecon_kalman_ll_spec_dims(C.byref(dims, 0), C.byref(dims, 4), C.byref(dims, 8)) == 0 and list(dims) == [7, 8, 3]
+    lib.gecon_kalman_ll_spec.argtypes = [C.POINTER(L.KalmanArgs), C.c_void_p]
+    kf = L.KalmanArgs(struct_size=C.sizeof(L.KalmanArgs), T=1, R=1, qdiag=1, Y=1, ll=1, status=1, Z=1, N=1, n=7, k=2, p=3, Tobs=1, z_stride=5)
+    assert lib.gecon_kalman_ll_spec(C.byref(kf), None) == -1 and b"z_stride" in L.load_library().gecon_get_last_error()
+    kf = L.KalmanArgs(struct_size=C.sizeof(L.KalmanArgs) - 8)
+    assert lib.gecon_kalman_ll_spec(C.byref(kf), None) == -1
+
+    cm = CompiledModel("rbc")
+    assert cm._cr_solve is not None
+    a = L.CrArgs(struct_size=C.sizeof(L.CrArgs), A=1, B=1, T=1, status=1, N=1, n=cm.n, k=0, max_iter=10, tol=1e-8, t_ld=3)
+    assert cm._cr_solve(C.byref(a), None) == -1
+    assert CompiledModel("nk_rbc_composite")._cr_solve is None  # n = 45: beyond the warp-per-draw solver, generic kernels only
+
+
 def test_posterior_helpers_validate_their_arguments_before_touching_the_device():
     from types import SimpleNamespace
 
