@@ -299,6 +299,9 @@ EXPORTS = {
     "gecon_launch_count": (C.c_int64, []),
     "gecon_kernel_info": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p]),
     "gecon_cr_solve_batched": (C.c_int, [C.POINTER(CrArgs), C.c_void_p]),
+    "gecon_cr_check_args": (C.c_int, [C.POINTER(CrArgs)]),
+    "gecon_kalman_check_args": (C.c_int, [C.POINTER(KalmanArgs)]),
+    "gecon_kalman_warp_np": (C.c_int, [C.POINTER(KalmanArgs)]),
     "gecon_cr_solve_host": (C.c_int, [C.POINTER(CrArgs)]),
     "gecon_bk_count_batched": (C.c_int, [C.POINTER(BkArgs), C.c_void_p]),
     "gecon_bk_count_host": (C.c_int, [C.POINTER(BkArgs)]),

@@ -458,6 +458,14 @@ typedef struct gecon_pipeline_args {
 int gecon_loglik_pipeline(const gecon_pipeline_args* args, void* stream);
 int gecon_pipeline_stage_ms(float* ms4);
 
+/* What the per-model solver builds (gecon_model_cr_solve, csrc/cr_warp_spec.cu) and the per-configuration filter builds
+ * (gecon_kalman_ll_spec, csrc/kalman_spec.cu) link against: the argument validation of gecon_cr_solve_* / gecon_kalman_ll_* (0 or
+ * GECON_E_*; no device work), and the padded dimension at which gecon_kalman_ll_batched would run the one-warp-per-draw kernel on
+ * these arguments (0: it would run the thread-per-draw or the CTA-per-draw kernel). */
+int gecon_cr_check_args(const gecon_cr_args* args);
+int gecon_kalman_check_args(const gecon_kalman_args* args);
+int gecon_kalman_warp_np(const gecon_kalman_args* args);
+
 /* library / device information */
 int gecon_abi_version(void);
 /* measured fp64 peaks of the current device in TFLOP/s: register-resident DFMA chains and mma.sync.m8n8k4.f64 chains (the
