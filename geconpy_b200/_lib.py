@@ -213,7 +213,7 @@ class KalmanArgs(C.Structure):
         ("qfull", C.c_void_p),
         ("qfull_stride", C.c_int64),
         ("h_count", C.c_int32),
-        ("reserved3", C.c_int32),
+        ("t_cols", C.c_int32),
         ("mask_intercept", C.c_int32),
         ("reserved2", C.c_int32),
     ]

@@ -288,6 +288,7 @@ def kalman_loglik(
     lyap_max_iter=0,
     Q=None,
     mask_intercept=False,
+    t_cols=0,
 ):
     """Batched Kalman-filter log-likelihood (``gecon_kalman_ll_*``): returns (ll[N], status[N][, ll_t[N, Tobs]]).
 
@@ -295,6 +296,7 @@ def kalman_loglik(
     SURVEY.md Appendix A.5.  ``qdiag`` / ``hdiag`` are VARIANCES, per draw (N, k) / (N, p) or shared (k,) / (p,).
     ``Z`` is (p, n) shared or (N, p, n), one design matrix per draw (parameter-dependent observation equations).
     ``Q``: full shock covariance, (k, k) shared or (N, k, k) (``full_shock_covariance``); ``qdiag`` is then ignored.
+    ``t_cols`` > 0: the caller's promise that only the first ``t_cols`` columns of T can be non-zero (``gecon_kalman_args.t_cols``).
     """
     if (Z is None) == (obs_idx is None):
         raise ValueError("give exactly one of Z (dense design matrix) and obs_idx (selector)")
@@ -327,7 +329,7 @@ def kalman_loglik(
         qfull_stride=(k * k if (Qa is not None and Qa.ndim == 3) else 0), N=N, n=n, k=k, p=p, Tobs=Tobs,
         jitter=float(jitter), missing_fill=float(missing_fill), mvn_const_mode=(0 if mvn_const == "per_obs" else 1),
         lyap_max_iter=int(lyap_max_iter), status_in=pSin, gate_mask=int(gate_mask), ll=pll, status=pS, ll_t=pllt,
-        z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0), mask_intercept=int(bool(mask_intercept)),
+        z_stride=(p * n if (Za is not None and Za.ndim == 3) else 0), mask_intercept=int(bool(mask_intercept)), t_cols=int(t_cols),
     )  # fmt: skip
     lib = L.load_library()
     if m.device:

@@ -171,32 +171,35 @@ def filter_spec_np(n: int, k: int, p: int) -> int:
     return np_
 
 
-def filter_spec_path(n: int, k: int, p: int):
+def filter_spec_path(n: int, k: int, p: int, t_cols: int = 0):
     """Where build_filter_spec puts (or would put) the library of this configuration; None when the configuration has no such build."""
     np_ = filter_spec_np(n, k, p)
     if not np_:
         return None
+    t_cols = t_cols if 0 < t_cols < n else 0
     deps = [CSRC / f for f in ("kalman_spec.cu", "kalman_warp_launch.cuh", "kalman_warp.cuh", "kalman.cuh", "linalg.cuh", "common.cuh")]
     dig = _digest(deps + [PKG.parent / "include" / "gecon_b200.h"], NVCC_FLAGS)[:16]
-    return MODEL_LIBDIR / f"libgecon_kf_n{n}_np{np_}_p{p}_{dig}.so"
+    return MODEL_LIBDIR / f"libgecon_kf_n{n}_np{np_}_p{p}_tc{t_cols}_{dig}.so"
 
 
-def build_filter_spec(n: int, k: int, p: int, force: bool = False):
-    """The warp-per-draw Kalman filter compiled for ONE (filter dimension, padded dimension, observables) triple (csrc/kalman_spec.cu):
-    same source as the generic kernel, the filter dimension a compile-time constant.  Cached next to the model libraries."""
-    lib = filter_spec_path(n, k, p)
+def build_filter_spec(n: int, k: int, p: int, t_cols: int = 0, force: bool = False):
+    """The warp-per-draw Kalman filter compiled for ONE (filter dimension, padded dimension, observables, non-zero columns of T) tuple
+    (csrc/kalman_spec.cu): same source as the generic kernel, the dimensions compile-time constants.  ``t_cols``: the leading columns of
+    T that can be non-zero (``gecon_kalman_args.t_cols``; 0 = dense).  Cached next to the model libraries."""
+    lib = filter_spec_path(n, k, p, t_cols)
     if lib is None or (lib.exists() and not force):
         return lib
     np_ = filter_spec_np(n, k, p)
+    t_cols = t_cols if 0 < t_cols < n else 0
     MODEL_LIBDIR.mkdir(parents=True, exist_ok=True)
     build_core()
     tmp_lib = lib.with_name(lib.name + f".{os.getpid()}.tmp")
     try:
         link = ["-L", str(LIBDIR), "-lgecon_b200", "-Xlinker", "-rpath=$ORIGIN/.."]
-        _run([find_nvcc(), *NVCC_FLAGS, "-shared", f"-DGECON_KW_SPEC_N={n}", f"-DGECON_KW_SPEC_NP={np_}", f"-DGECON_KW_SPEC_P={p}", "-o", str(tmp_lib),
+        _run([find_nvcc(), *NVCC_FLAGS, "-shared", f"-DGECON_KW_SPEC_N={n}", f"-DGECON_KW_SPEC_NP={np_}", f"-DGECON_KW_SPEC_P={p}", f"-DGECON_KW_SPEC_TC={t_cols}", "-o", str(tmp_lib),
               str(CSRC / "kalman_spec.cu"), *link, "-lcudart"])
         os.replace(tmp_lib, lib)
-        for stale in MODEL_LIBDIR.glob(f"libgecon_kf_n{n}_np{np_}_p{p}_*.so"):  # builds of older sources of the same configuration
+        for stale in MODEL_LIBDIR.glob(f"libgecon_kf_n{n}_np{np_}_p{p}_tc{t_cols}_*.so"):  # builds of older sources of the same configuration
             if stale != lib:
                 stale.unlink(missing_ok=True)
     finally:

@@ -66,6 +66,10 @@ static int check_kf_args(const gecon_kalman_args* a) {
         set_last_error("gecon_kalman_args: qfull_stride must be 0 (shared Q) or k * k");
         return GECON_E_BADARG;
     }
+    if (a->t_cols < 0 || a->t_cols > a->n) {
+        set_last_error("gecon_kalman_args: t_cols = %d needs 0 <= t_cols <= n", a->t_cols);
+        return GECON_E_BADARG;
+    }
     if (a->p > PMAX || a->p > a->n) {
         set_last_error("gecon_kalman_args: unsupported p = %d (max %d, and p <= n)", a->p, PMAX);
         return GECON_E_UNSUPPORTED_SIZE;

@@ -234,6 +234,12 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
     const double jitter = p.jitter;
     const bool keep_d = (p.mask_intercept == 0);  // the intercept is NOT masked at missing entries (pymc_extras: d + Z_masked a)
     const int nks = (n + 3) >> 2;
+    // k-steps of the two products with T: only its first t_cols columns can be non-zero when the caller says so (gecon_kalman_args.t_cols)
+#if defined(GECON_KW_SPEC_N) && defined(GECON_KW_SPEC_TC) && GECON_KW_SPEC_TC > 0
+    constexpr int nks_t = (GECON_KW_SPEC_TC + 3) >> 2;
+#else
+    const int nks_t = (p.t_cols > 0 && p.t_cols < n) ? ((p.t_cols + 3) >> 2) : nks;
+#endif
     const int il = lane < NP ? lane : 0;  // row handled by this lane in phase 1 (clamped: lanes >= n compute on row 0 and discard)
     const bool rowlane = lane < n;
 
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
             wacc_zero(w);
 #pragma unroll
             for (int ks = 0; ks < KSN; ++ks) {
-                if (ks < nks) {
+                if (ks < nks_t) {
                     double b[NS];
 #pragma unroll
                     for (int ct = 0; ct < NS; ++ct) b[ct] = ((ks >> 1) > ct) ? P[(8 * ct + g) * LD + 4 * ks + q] : P[(4 * ks + q) * LD + 8 * ct + g];
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(WPC_ * 32, MINB) kalman_ll_warp_kernel(const g
             else wacc_load_upper<NP>(pacc, C0t, lane);
 #pragma unroll
             for (int ks = 0; ks < KSN; ++ks) {
-                if (ks < nks) {
+                if (ks < nks_t) {
                     double a[NS];
 #pragma unroll
                     for (int s = 0; s < NS; ++s) a[s] = W[(8 * s + g) * LD + 4 * ks + q];

@@ -118,6 +118,18 @@ extern "C" int gecon_loglik_pipeline(const gecon_pipeline_args* a, void* stream)
     int32_t* d_idx = nullptr;
     rc = cached_tables(h, &d_idx);
     if (rc) return rc;
+    // T = -A1hat^-1 A has non-zero columns only at the lagged variables [lag_lo, lag_hi): when the filter variables come
+    // [lagged ... | others ...] (BatchedStateSpace orders them so), the filter is told how many leading columns of its T can be
+    // non-zero (gecon_kalman_args.t_cols) and skips the k-steps of its two products with T beyond them
+    int t_cols = 0;
+    if (a->col_ranges[1] > a->col_ranges[0]) {
+        auto lagged = [&](int v) { return v >= a->col_ranges[0] && v < a->col_ranges[1]; };
+        int t = 0;
+        while (t < nf && lagged(a->filter_vars[t])) ++t;
+        bool rest_outside = true;
+        for (int i = t; i < nf; ++i) rest_outside = rest_outside && !lagged(a->filter_vars[i]);
+        if (rest_outside && t > 0 && t < nf) t_cols = t;
+    }
     int32_t* d_table = d_idx;
     int32_t* d_fv = d_table + a->nnz;
     int32_t* d_obs = d_fv + nf;
@@ -234,6 +246,7 @@ extern "C" int gecon_loglik_pipeline(const gecon_pipeline_args* a, void* stream)
         kf.ll = a->ll + lo;
         kf.status = a->status + lo;
         kf.mask_intercept = a->mask_intercept;
+        kf.t_cols = t_cols;
         tm.begin(3);
         rc = a->kalman_ll ? a->kalman_ll(&kf, stream) : gecon_kalman_ll_batched(&kf, stream);
         tm.end();

@@ -281,11 +281,13 @@ class BatchedStateSpace:
         # kernel hands the filter the exact sub-blocks T[U][:, U], R[U] for U = states + observed (solver order).
         state_pos = m.inv_var_order[m.lin.state_var_idx]
         referenced = {int(m.inv_var_order[m.var_names.index(v)]) for _, co in self._obs_eq.values() for (v, _lag) in co}
-        self.filter_vars = (
-            np.array(sorted(set(state_pos.tolist()) | set(self.obs_idx.tolist()) | referenced), dtype=np.int32)
-            if reduce_state
-            else np.arange(m.n, dtype=np.int32)
-        )
+        # Order: the lagged (state) variables first, then the observed / referenced ones that are not states.  T = -A1hat^-1 A has
+        # non-zero columns only at the lagged variables, so in this order only the first len(states) columns of the filter's T can be
+        # non-zero: gecon_kalman_args.t_cols (large NK: 16 of 19 columns -> 4 instead of 5 k-steps in both products with T).
+        states = sorted(set(state_pos.tolist()))
+        others = sorted((set(self.obs_idx.tolist()) | referenced) - set(states))
+        self.filter_vars = np.array(states + others, dtype=np.int32) if reduce_state else np.arange(m.n, dtype=np.int32)
+        self.filter_t_cols = len(states) if (reduce_state and others and states) else 0
         self.n_filter = int(self.filter_vars.size)
         self.obs_idx_filter = np.array([int(np.flatnonzero(self.filter_vars == o)[0]) for o in self.obs_idx], dtype=np.int32)
         self.reduce_state = bool(reduce_state)
@@ -457,7 +459,10 @@ class BatchedStateSpace:
             return self._loglik_fused(theta_full, Y, ll, status, out_n_iter, events)
         nc = min(self.chunk, N)
         n_err = len(self.measurement_error)
-        kf_spec = self._filter_spec_fn(self.n_aug, N)  # the staged path filters the (augmented) state at its full dimension
+        # (the staged path filters the augmented state at its full dimension; the augmentation adds rows AND columns to T, so the
+        # promise about its zero columns is only made for the plain state space)
+        t_cols = self.filter_t_cols if self.n_aug == self.n_filter else 0
+        kf_spec = self._filter_spec_fn(self.n_aug, N, t_cols)
         n_streams = max(1, int(getattr(self, "n_streams", 1)))
         cur = torch.cuda.current_stream(dev)
         if n_streams > 1:
@@ -547,7 +552,7 @@ class BatchedStateSpace:
                     Tobs=Tobs, jitter=self.cov_jitter, missing_fill=self.missing_fill_value,
                     mvn_const_mode=(0 if self.mvn_const == "per_obs" else 1), lyap_max_iter=0, status_in=st.data_ptr(),
                     gate_mask=self.gate_mask, sigma_inputs=1, ll=ll[lo : lo + cnt].data_ptr(), status=status[lo : lo + cnt].data_ptr(),
-                    ll_t=None, mask_intercept=int(self.mask_intercept),
+                    ll_t=None, mask_intercept=int(self.mask_intercept), t_cols=t_cols,
                 )  # fmt: skip
                 e = mark("kalman_ll")
                 L.check((kf_spec or lib.gecon_kalman_ll_batched)(C.byref(kf), C.c_void_p(stream)), "gecon_kalman_ll_batched")
@@ -584,7 +589,7 @@ class BatchedStateSpace:
             timing=int(events is not None), chunk=self.chunk, ll=ll.data_ptr(), status=status.data_ptr(),
             n_iter=(out_n_iter.data_ptr() if out_n_iter is not None else None),
         )  # fmt: skip
-        kf_spec = self._filter_spec_fn(self.n_filter, theta_full.shape[0])
+        kf_spec = self._filter_spec_fn(self.n_filter, theta_full.shape[0], self.filter_t_cols)
         if kf_spec is not None:
             args.kalman_ll = C.cast(kf_spec, C.c_void_p)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -601,7 +606,7 @@ class BatchedStateSpace:
 
     SPEC_MIN_DRAWS = 4096  # populations this large pay for the per-configuration build of the filter within their first evaluation
 
-    def _filter_spec_fn(self, n_filter: int, n_draws: int):
+    def _filter_spec_fn(self, n_filter: int, n_draws: int, t_cols: int = 0):
         """``gecon_kalman_ll_spec`` of the filter library built for (n_filter, shocks, observables) -- ``build.build_filter_spec`` -- or
         None: configure(specialize=False), ``GECON_KF_SPEC=0``, a configuration the warp-per-draw filter does not take (dense design
         matrix, full shock covariance, thread-per-draw or CTA-per-draw sizes), or not built yet and the population is small.  The entry
@@ -610,7 +615,7 @@ class BatchedStateSpace:
             return None
         from .. import build
 
-        key = (int(n_filter), self.model.k, self.p)
+        key = (int(n_filter), self.model.k, self.p, int(t_cols))
         cache = self.__dict__.setdefault("_kf_spec_cache", {})
         if key not in cache:
             path = build.filter_spec_path(*key)

@@ -236,7 +236,11 @@ typedef struct gecon_kalman_args {
     int64_t qfull_stride;
     int32_t h_count;      /* 0: hdiag holds p entries per draw.  > 0: only the first h_count entries are read, the others are 0
                              (lets hdiag point INTO a wider parameter vector: error variances of the first h_count observables) */
-    int32_t reserved3;
+    int32_t t_cols;       /* 0: T is dense.  > 0: the caller's promise that only the first t_cols columns of T can be non-zero (T = -A1hat^-1 A
+                             has non-zero columns only at the lagged variables; BatchedStateSpace orders the filter variables [lagged |
+                             observed only]): the warp-per-draw kernel then runs the k-loops of T [P+ | a+] and W T' over those columns only.
+                             The columns beyond MUST hold zeros (the set-up, P0 = dlyap(T, R Q R'), still reads all of T).  The other
+                             kernels ignore it */
     int32_t mask_intercept; /* 0 (upstream StandardFilter as restated there): the intercept d is NOT masked at missing
                                entries, v_i = 0 - d_i there.  1: missing entries have v_i = 0 (d masked like Z and H), the
                                convention of a filter that drops missing rows.  tests/golden/make_kalman_goldens.py records which

@@ -355,6 +355,38 @@ def test_kalman_synthetic_sizes(B, rng, n, k, p):
             assert abs(ll[i] - ref) <= TOL_LL * scale and abs(ll1[i] - ref) <= TOL_LL * scale, (n, p, i, ll[i], ll1[i], ref)
 
 
+@pytest.mark.parametrize("n,k,p,tc", [(10, 4, 3, 9), (10, 3, 2, 5), (19, 9, 7, 16), (19, 4, 3, 7), (26, 13, 7, 23), (7, 2, 3, 4), (40, 5, 3, 20)])
+def test_kalman_zero_columns_promise(B, rng, n, k, p, tc):
+    """gecon_kalman_args.t_cols: with only the first t_cols columns of T non-zero (the structure of a policy matrix whose filter variables
+    are ordered [lagged | observed only]), the warp-per-draw kernel skips the k-steps beyond them -- the result is IDENTICAL to the
+    dense run (complete and incomplete samples) and both agree with the oracle.  (n = 40: the CTA kernel ignores the promise.)"""
+    N, Tobs = 6, 40
+    T, R = _random_statespace(rng, N, n, k)
+    T[:, :, tc:] = 0.0
+    for i in range(N):
+        T[i] *= 0.9 / np.abs(np.linalg.eigvals(T[i])).max()
+    q = 0.5 + rng.random((N, k))
+    h = 0.1 + rng.random((N, p))
+    obs = np.sort(rng.choice(n, size=p, replace=False)).astype(np.int32)
+    obs[-1] = n - 1  # an observed variable that is not a state
+    obs = np.unique(obs).astype(np.int32)
+    p = obs.size
+    h = h[:, :p]
+    Z = np.zeros((p, n))
+    Z[np.arange(p), obs] = 1.0
+    Y = rng.standard_normal((Tobs, p))
+    Y[rng.random(Y.shape) < 0.1] = np.nan
+    for Yc in (np.nan_to_num(Y, nan=0.3), Y):
+        ll0, st0 = B.kalman_loglik(T, R, q, Yc, obs_idx=obs, hdiag=h)
+        ll1, st1 = B.kalman_loglik(T, R, q, Yc, obs_idx=obs, hdiag=h, t_cols=tc)
+        assert np.array_equal(ll0, ll1) and np.array_equal(st0, st1) and (st0 == 0).all()
+        for i in range(N):
+            ref = oss.kalman_loglik(Yc, T[i], R[i], np.diag(q[i]), Z, np.diag(h[i]))
+            assert abs(ll1[i] - ref) <= TOL_LL * max(1.0, abs(ref) * 1e-9), (i, ll1[i], ref)
+    with pytest.raises(Exception, match="t_cols"):
+        B.kalman_loglik(T, R, q, Yc, obs_idx=obs, hdiag=h, t_cols=n + 1)
+
+
 def test_kalman_gating_and_given_P0(B):
     mod = model("rbc")
     th = draws(mod, 4, seed=8, width=0.02, valid=True)
