@@ -341,6 +341,7 @@ class BatchedStateSpace:
         self.bk_on_rejected_draws = bool(bk_on_rejected_draws)
         self.specialize = specialize
         self.__dict__.pop("_kf_spec_cache", None)
+        self.__dict__.pop("_kf_spec_paths", None)
         self.chunk = int(os.environ.get("GECON_CHUNK", chunk))
         self.full_covariance = bool(full_shock_covariance)
         self.mask_intercept = bool(mask_intercept)
@@ -618,7 +619,10 @@ class BatchedStateSpace:
         key = (int(n_filter), self.model.k, self.p, int(t_cols))
         cache = self.__dict__.setdefault("_kf_spec_cache", {})
         if key not in cache:
-            path = build.filter_spec_path(*key)
+            paths = self.__dict__.setdefault("_kf_spec_paths", {})  # (the digest in the file name reads the sources: once per key)
+            if key not in paths:
+                paths[key] = build.filter_spec_path(*key)
+            path = paths[key]
             if path is None:
                 cache[key] = None
             elif path.exists() or self.specialize or n_draws >= self.SPEC_MIN_DRAWS:
