@@ -211,4 +211,24 @@ def test_configure_layout_and_parameter_names(rbc_statespace):
     assert full.param_names[len(m.param_names) :] == ["state_cov[0,0]"]
     # reduce_state=False keeps every variable, in solver order
     allv = rbc_statespace().configure(observed_states=["Y"], reduce_state=False)
-    assert allv.n_filter == m.n and list(allv.filter_vars) == list(range(m.n))
+    assert allv.n_filter == m.n and list(allv.filter_vars) == list(range(m.n)) and allv.filter_t_cols == 0
+
+
+def test_filter_variables_come_lagged_first_and_t_cols_counts_them():
+    """The filter variables are ordered [lagged | observed only]: T = -A1hat^-1 A has non-zero columns only at the lagged variables, so
+    ``filter_t_cols`` (gecon_kalman_args.t_cols) is the number of lagged variables whenever something follows them."""
+    from geconpy_b200.model.compiled import BatchedStateSpace, CompiledModel
+
+    cm = CompiledModel("nk_complete_more_shocks")
+    lag_lo, lag_hi = cm.col_ranges[0], cm.col_ranges[1]
+    ss = BatchedStateSpace(cm).configure(observed_states=["Y", "C", "I", "N", "pi", "i", "w"])
+    fv = [int(v) for v in ss.filter_vars]
+    t = ss.filter_t_cols
+    assert (ss.n_filter, t) == (19, 16) == (len(fv), lag_hi - lag_lo)
+    assert fv[:t] == list(range(lag_lo, lag_hi)) and all(not (lag_lo <= v < lag_hi) for v in fv[t:]) and fv[t:] == sorted(fv[t:])
+    names = [cm.lin.vars_perm[v] for v in fv]
+    assert [names[i] for i in ss.obs_idx_filter] == ["Y", "C", "I", "N", "pi", "i", "w"]
+    # every observable a lagged variable: nothing follows the lagged block, T is dense in the filter's eyes
+    lagged_names = names[:t]
+    only = BatchedStateSpace(cm).configure(observed_states=lagged_names[:2])
+    assert only.n_filter == t and only.filter_t_cols == 0
